@@ -1,0 +1,121 @@
+/*
+ * unirec_b200 - C ABI of the B200 (sm_100a) kernels behind UniRec's nested Q-Former
+ * encode-and-rank path.
+ *
+ * The reference (ulab-uiuc/UniRec) is pure PyTorch: it has no FFI of its own, so the "binding a
+ * maintainer would add" is a ctypes stub.  Every entry point takes plain device
+ * pointers, sizes and a CUDA stream handle (cudaStream_t passed as void*; NULL = legacy default
+ * stream) - no torch types cross this boundary.  Pointers are BORROWED for the duration of the call;
+ * the library allocates nothing it returns, never synchronises the stream and never falls back to
+ * the CPU.  Every function returns 0 on success or a non-zero UNIREC_ERR_* code, in which case
+ * unirec_last_error() describes the failure (thread-local string).
+ *
+ * Conventions: bf16 = 16-bit bfloat16 storage; all matrices are row-major with an explicit row
+ * stride ("ld", in elements); rows must be 16-byte aligned.  `out_fp32` selects fp32 (1) or bf16 (0)
+ * output storage.  Reference file:line citations are relative to the reference repository root.
+ */
+#ifndef UNIREC_B200_H_
+#define UNIREC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UNIREC_B200_ABI_VERSION 1
+
+#define UNIREC_OK 0
+#define UNIREC_ERR_BAD_ARG 1
+#define UNIREC_ERR_CUDA 2
+#define UNIREC_ERR_TENSORMAP 3
+#define UNIREC_ERR_NO_DEVICE 4
+
+/* GEMM epilogues */
+#define UNIREC_EPI_BIAS 0          /* out = A W^T + b                                  */
+#define UNIREC_EPI_BIAS_GELU 1     /* out = gelu_erf(A W^T + b)   (models/qformer.py:359-361) */
+#define UNIREC_EPI_BIAS_RESIDUAL 2 /* out = A W^T + b + residual  (pre-LayerNorm sum, :286-288, :372-374) */
+
+int unirec_abi_version(void);
+const char* unirec_last_error(void);
+
+/* Number of kernels this library has launched in this process (all entry points), for bench.py's
+ * "gpu_launches" claim. */
+int64_t unirec_launch_count(void);
+
+/* nn.Linear on the path: out[M,N] = epilogue(A[M,K] @ W[N,K]^T + bias[N]).
+ * Replaces every nn.Linear of the path: Q/K/V projections models/qformer.py:185-198, attention output
+ * dense :286, FFN up :359 and down :372, heads models/qformer_utils.py:50,53 and
+ * training/user_qformer_training.py:38-43.  tcgen05/TMEM/TMA kernel.
+ * A, W bf16; bias fp32 or NULL; residual bf16 (epilogue 2), residual row = row % res_row_mod when
+ * res_row_mod > 0 (batch-invariant residual).  K % 64 == 0, N % 8 == 0.
+ * block_n: 0 = auto, 128 or 256.  max_ctas: 0 = one per SM. */
+int unirec_linear_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                       const void* residual, int64_t ldr, int64_t res_row_mod,
+                       void* out, int64_t ldo, int out_fp32,
+                       int64_t M, int64_t N, int64_t K, int epilogue, int block_n, int max_ctas, void* stream);
+
+/* nn.LayerNorm over the last dim (models/qformer.py:104, :288, :374; user head
+ * training/user_qformer_training.py:41): out = LN(x [+ residual]) * gamma + beta.
+ * x fp32 (x_fp32=1) or bf16; x row = row % in_row_mod when in_row_mod > 0; residual bf16 or NULL. */
+int unirec_layernorm(const void* x, int x_fp32, int64_t ldx, int64_t in_row_mod,
+                     const void* residual, int64_t ldres,
+                     const float* gamma, const float* beta, float eps,
+                     void* out, int out_fp32, int64_t ldo, int64_t rows, int64_t H, void* stream);
+
+/* Fused small-query multi-head attention, head_dim 64 (models/qformer.py:161-167, 205, 244-268).
+ * q [batch*nq rows] (q_batch_rows = nq, or 0 when the same queries serve every batch element),
+ * k, v [batch*kv_batch_rows rows]; head h occupies columns [h*64, (h+1)*64) of each row;
+ * key_mask [batch, nk] fp32 (1 = attend, 0 = masked) or NULL; out [batch*nq, ldo] head-merged. */
+int unirec_attention(const void* q, int64_t ldq, int64_t q_batch_rows,
+                     const void* k, int64_t ldk, const void* v, int64_t ldv, int64_t kv_batch_rows,
+                     const float* key_mask, void* out, int64_t ldo,
+                     int64_t batch, int64_t num_heads, int64_t nq, int64_t nk, int64_t head_dim,
+                     float scale, void* stream);
+
+/* fp32 -> bf16 (callers hand fp32 field embeddings, models/qformer_utils.py:37). n % 8 == 0. */
+int unirec_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream);
+
+/* out[b,:] = mean_t x[b,t,:]  (models/qformer_utils.py:50; training/user_qformer_training.py:60). */
+int unirec_mean_tokens(const void* x, int64_t ldx, int64_t B, int64_t T, int64_t H,
+                       void* out, int64_t ldo, int out_fp32, void* stream);
+
+/* out[b,f,:] = sum_t Wp[f,t] * rec[b,t,:] + bp[f]  (field_projection, models/qformer_utils.py:54). */
+int unirec_field_projection(const void* rec, const float* Wp, const float* bp, void* out, int out_fp32,
+                            int64_t B, int64_t T, int64_t F, int64_t E, void* stream);
+
+/* User-sequence builder (models/user_sequence_encoder.py:128-140 + padding of
+ * training/user_qformer_training.py:153-161): seq[b, h*Q+q, :] = table[history[b,h], q, :] (+ ctx[b,h,:])
+ * + PE[h*Q+q, :] for h < lengths[b], 0 otherwise; mask[b,s] = s < lengths[b]*Q.
+ * table bf16 [num_items, Q, D]; history int64 [B, Hmax]; lengths int32 [B]; ctx bf16 [B,Hmax,D] or NULL;
+ * seq bf16 [B, Hmax*Q, D]; mask fp32 [B, Hmax*Q]. */
+int unirec_build_user_sequence(const void* table, int64_t num_items, const int64_t* history,
+                               const int32_t* lengths, const void* ctx, void* seq, float* mask,
+                               int64_t B, int64_t Hmax, int64_t Q, int64_t D, void* stream);
+
+/* inv[r] = 1 / max(||x_r||_2, eps)  (F.normalize, training/train_item_individual_token_joint.py:405-406,412). */
+int unirec_inv_l2_norm(const void* x, int x_fp32, int64_t ldx, float* inv, int64_t rows, int64_t D,
+                       float eps, void* stream);
+
+/* Fused cosine scoring + top-k (training/train_item_individual_token_joint.py:405-415 at scale):
+ * scores[b,n] = <users[b], cands[n]> * user_inv[b] * cand_inv[n]; returns for each user the k best
+ * candidates in descending score order without materialising [B, N].
+ * users bf16 [B, D]; cands bf16 [N, D]; user_inv fp32 [B]; cand_inv fp32 [N]; index_base is added to
+ * every returned index (row-sharded candidate pools); out_scores fp32 [B, k]; out_idx int64 [B, k].
+ * workspace: unirec_score_topk_workspace_bytes(B, N, k) bytes of device memory. */
+int64_t unirec_score_topk_workspace_bytes(int64_t B, int64_t N, int64_t k);
+int unirec_score_topk(const void* users, int64_t ldu, const float* user_inv,
+                      const void* cands, int64_t ldc, const float* cand_inv,
+                      int64_t B, int64_t N, int64_t D, int64_t k, int64_t index_base,
+                      float* out_scores, int64_t* out_idx, void* workspace, int64_t workspace_bytes,
+                      void* stream);
+
+/* Merge per-shard top-k lists (after the NCCL all-gather of config 5): in_scores/in_idx
+ * [G, B, k] (each list descending) -> out [B, k] descending; ties broken by smaller index. */
+int unirec_topk_merge(const float* in_scores, const int64_t* in_idx, int64_t G, int64_t B, int64_t k,
+                      float* out_scores, int64_t* out_idx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNIREC_B200_H_ */

@@ -1,0 +1,195 @@
+"""GPU parity tests of the individual sm_100a kernels, called through the C ABI (ctypes), against
+plain fp32 PyTorch restatements of the same op (floating-point kernels: tolerance stated per test)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _randn(*shape, seed=0, scale=1.0, dtype=torch.float32):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(_dev())
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (448, 1024, 1024), (96, 3072, 1024),
+                                   (1000, 4096, 1024), (300, 1024, 4096), (8192, 1024, 1024), (37, 40, 192)])
+@pytest.mark.parametrize("block_n", [128, 256])
+def test_linear_bias(M, N, K, block_n):
+    from unirec_b200 import ops
+    a = _randn(M, K, seed=1, dtype=torch.bfloat16)
+    w = _randn(N, K, seed=2, scale=0.05, dtype=torch.bfloat16)
+    b = _randn(N, seed=3)
+    out = ops.linear(a, w, b, block_n=block_n, out_dtype=torch.float32)
+    ref = a.float() @ w.float().t() + b
+    # fp32 accumulation of exact bf16 products: only summation-order differences
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=2e-3)
+    out_bf = ops.linear(a, w, b, block_n=block_n)
+    torch.testing.assert_close(out_bf.float(), ref, rtol=1e-2, atol=2e-2)  # bf16 output rounding (2^-9)
+
+
+@pytest.mark.parametrize("block_n", [128, 256])
+def test_linear_gelu_and_residual(block_n):
+    from unirec_b200 import ops
+    M, N, K = 640, 1024, 1024
+    a = _randn(M, K, seed=4, dtype=torch.bfloat16)
+    w = _randn(N, K, seed=5, scale=0.04, dtype=torch.bfloat16)
+    b = _randn(N, seed=6, scale=0.5)
+    res = _randn(M, N, seed=7, dtype=torch.bfloat16)
+    lin = a.float() @ w.float().t() + b
+    out = ops.linear(a, w, b, epilogue=ops.EPI_BIAS_GELU, block_n=block_n, out_dtype=torch.float32)
+    torch.testing.assert_close(out, F.gelu(lin), rtol=1e-4, atol=2e-3)  # erf approximation error 1.5e-7
+    out = ops.linear(a, w, b, epilogue=ops.EPI_BIAS_RESIDUAL, residual=res, block_n=block_n,
+                     out_dtype=torch.float32)
+    torch.testing.assert_close(out, lin + res.float(), rtol=1e-4, atol=2e-3)
+    # batch-invariant residual: row r uses residual row r % 32
+    res32 = res[:32].contiguous()
+    out = ops.linear(a, w, b, epilogue=ops.EPI_BIAS_RESIDUAL, residual=res32, res_row_mod=32, block_n=block_n,
+                     out_dtype=torch.float32)
+    torch.testing.assert_close(out, lin + res32.float().repeat(M // 32, 1), rtol=1e-4, atol=2e-3)
+
+
+def test_linear_strided_views_and_many_tiles():
+    """A and out as column slices of wider buffers (fused QKV layout); more tiles than SMs so that the
+    persistent loop, the smem ring and both TMEM stages wrap many times."""
+    from unirec_b200 import ops
+    M, N, K = 20000, 2048, 1024
+    big_a = _randn(M, 2 * K, seed=8, dtype=torch.bfloat16)
+    a = big_a[:, K:]
+    w = _randn(N, K, seed=9, scale=0.05, dtype=torch.bfloat16)
+    big_out = torch.zeros(M, 3 * N, device=_dev(), dtype=torch.bfloat16)
+    ops.linear(a, w, None, out=big_out[:, N:2 * N])
+    ref = a.float() @ w.float().t()
+    torch.testing.assert_close(big_out[:, N:2 * N].float(), ref, rtol=1e-2, atol=2e-2)
+    assert float(big_out[:, :N].abs().max()) == 0.0 and float(big_out[:, 2 * N:].abs().max()) == 0.0
+    # a handful of CTAs only: every CTA loops over many tiles
+    out2 = ops.linear(a, w, None, max_ctas=5)
+    torch.testing.assert_close(out2.float(), ref, rtol=1e-2, atol=2e-2)
+
+
+def test_linear_rejects_bad_arguments():
+    from unirec_b200 import ops
+    a = _randn(64, 100, dtype=torch.bfloat16)  # K not a multiple of 64
+    w = _randn(64, 100, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError):
+        ops.linear(a, w, None)
+    with pytest.raises(RuntimeError):
+        ops.linear(a.cpu(), w, None)  # no CPU path
+
+
+# ------------------------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("H", [256, 1024, 4096])
+@pytest.mark.parametrize("in_dtype", [torch.float32, torch.bfloat16])
+def test_layernorm(H, in_dtype):
+    from unirec_b200 import ops
+    rows = 333
+    x = _randn(rows, H, seed=10, scale=3.0, dtype=in_dtype)
+    res = _randn(rows, H, seed=11, dtype=torch.bfloat16)
+    g = _randn(H, seed=12, scale=0.1) + 1.0
+    b = _randn(H, seed=13, scale=0.1)
+    out = ops.layernorm(x, g, b, 1e-12, residual=res, out_dtype=torch.float32)
+    ref = F.layer_norm(x.float() + res.float(), (H,), g, b, 1e-12)
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5)
+    out_b = ops.layernorm(x, g, b, 1e-12, rows=96, in_row_mod=32, out_dtype=torch.float32)
+    ref_b = F.layer_norm(x[:32].float(), (H,), g, b, 1e-12).repeat(3, 1)
+    torch.testing.assert_close(out_b, ref_b, rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------- attention
+def _ref_attention(q, k, v, mask, heads):
+    B, nq, hd = q.shape
+    nk = k.shape[1]
+    qh = q.float().view(B, nq, heads, 64).permute(0, 2, 1, 3)
+    kh = k.float().view(B, nk, heads, 64).permute(0, 2, 1, 3)
+    vh = v.float().view(B, nk, heads, 64).permute(0, 2, 1, 3)
+    s = qh @ kh.transpose(-1, -2) / 8.0
+    if mask is not None:
+        s = s + (1.0 - mask[:, None, None, :]) * torch.finfo(torch.float32).min
+    p = torch.softmax(s, dim=-1)
+    return (p @ vh).permute(0, 2, 1, 3).reshape(B, nq, hd)
+
+
+@pytest.mark.parametrize("nq,nk,heads", [(32, 32, 16), (32, 14, 16), (64, 64, 16), (64, 160, 16), (64, 1600, 4),
+                                         (32, 6, 4), (64, 97, 4)])
+def test_attention(nq, nk, heads):
+    from unirec_b200 import ops
+    B = 5
+    hd = heads * 64
+    q = _randn(B, nq, hd, seed=20, dtype=torch.bfloat16)
+    k = _randn(B, nk, hd, seed=21, dtype=torch.bfloat16)
+    v = _randn(B, nk, hd, seed=22, dtype=torch.bfloat16)
+    mask = (torch.rand(B, nk, generator=torch.Generator().manual_seed(23)) < 0.7).float()
+    mask[0] = 1.0
+    mask[1] = 0.0          # all keys masked -> uniform attention over all nk keys
+    mask[2, : nk // 2] = 0.0
+    mask = mask.to(_dev())
+    for m in (None, mask):
+        out = ops.attention(q.view(B * nq, hd), k.view(B * nk, hd), v.view(B * nk, hd), batch=B, num_heads=heads,
+                            nq=nq, nk=nk, key_mask=m).view(B, nq, hd)
+        ref = _ref_attention(q, k, v, m, heads)
+        assert torch.isfinite(out).all()
+        # P is rounded to bf16 before PV and the output is bf16: |err| <~ 2^-8 * |v|max
+        torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)
+    if True:
+        uniform = v[1].float().mean(dim=0, keepdim=True).expand(nq, hd)
+        torch.testing.assert_close(out[1].float(), uniform, rtol=2e-2, atol=2e-2)
+
+
+def test_attention_fused_qkv_layout_and_broadcast_queries():
+    """q/k/v as column slices of one fused [rows, 3*H] buffer; one query block shared by all items."""
+    from unirec_b200 import ops
+    B, nq, heads = 7, 32, 16
+    hd = heads * 64
+    qkv = _randn(B * nq, 3 * hd, seed=30, dtype=torch.bfloat16)
+    q, k, v = qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:]
+    out = ops.attention(q, k, v, batch=B, num_heads=heads, nq=nq, nk=nq).view(B, nq, hd)
+    ref = _ref_attention(q.reshape(B, nq, hd), k.reshape(B, nq, hd), v.reshape(B, nq, hd), None, heads)
+    torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)
+    q1 = q[:nq].contiguous()
+    out = ops.attention(q1, k, v, batch=B, num_heads=heads, nq=nq, nk=nq, q_broadcast=True).view(B, nq, hd)
+    ref = _ref_attention(q1.view(1, nq, hd).expand(B, nq, hd), k.reshape(B, nq, hd), v.reshape(B, nq, hd), None, heads)
+    torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)
+
+
+# ------------------------------------------------------------------------------- row-wise kernels
+def test_cast_mean_fieldproj_invnorm():
+    from unirec_b200 import ops
+    x = _randn(9, 32, 1024, seed=40)
+    xb = ops.cast_bf16(x)
+    assert xb.dtype == torch.bfloat16 and torch.equal(xb, x.to(torch.bfloat16))
+    m = ops.mean_tokens(xb, out_dtype=torch.float32)
+    torch.testing.assert_close(m, xb.float().mean(dim=1), rtol=1e-5, atol=1e-5)
+    wp = _randn(14, 32, seed=41, scale=0.2)
+    bp = _randn(14, seed=42)
+    fp = ops.field_projection(xb, wp, bp, out_dtype=torch.float32)
+    ref = torch.einsum("ft,bte->bfe", wp, xb.float()) + bp[None, :, None]
+    torch.testing.assert_close(fp, ref, rtol=1e-4, atol=1e-4)
+    inv = ops.inv_l2_norm(xb.view(-1, 1024))
+    torch.testing.assert_close(inv, 1.0 / xb.float().view(-1, 1024).norm(dim=-1).clamp_min(1e-12), rtol=1e-5, atol=0)
+    z = torch.zeros(4, 1024, device=_dev(), dtype=torch.bfloat16)
+    assert float(ops.inv_l2_norm(z).max()) == pytest.approx(1e12, rel=1e-5)
+
+
+def test_build_user_sequence_matches_oracle():
+    from oracle import qformer_oracle as O
+    from unirec_b200 import ops
+    N, Q, D, B, Hmax = 40, 32, 1024, 6, 5
+    table = _randn(N, Q, D, seed=50, dtype=torch.bfloat16)
+    g = torch.Generator().manual_seed(51)
+    history = torch.randint(0, N, (B, Hmax), generator=g)
+    lengths = torch.tensor([5, 1, 3, 5, 2, 4], dtype=torch.int32)
+    ctx = _randn(B, Hmax, D, seed=52, scale=0.3, dtype=torch.bfloat16)
+    for c in (None, ctx):
+        seq, mask = ops.build_user_sequence(table, history.to(_dev()), lengths.to(_dev()), c)
+        ref_seq, ref_mask = O.build_user_sequences(table.cpu().float(), history, lengths.long(),
+                                                   None if c is None else c.cpu().float())
+        assert torch.equal(mask.cpu(), ref_mask)
+        # bf16 output rounding of values up to ~5
+        torch.testing.assert_close(seq.cpu().float(), ref_seq, rtol=1e-2, atol=2e-2)

@@ -1,0 +1,95 @@
+// extern "C" surface of libunirec_b200.so (declared in include/unirec_b200.h): thin argument
+// marshalling over the kernel launchers; no torch types, borrowed device pointers, caller's stream.
+#include "common.cuh"
+#include "../../include/unirec_b200.h"
+
+#include <atomic>
+
+namespace unirec {
+const char* get_last_error();
+int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias, const void* residual,
+              long long ldr, int res_row_mod, void* out, long long ldo, int out_fp32, long long M, long long N,
+              long long K, int epilogue, int block_n, int max_ctas, cudaStream_t stream);
+int layernorm(const void* x, int x_fp32, long long ldx, int in_row_mod, const void* residual, long long ldres,
+              const float* gamma, const float* beta, float eps, void* out, int out_fp32, long long ldo,
+              long long rows, long long H, cudaStream_t stream);
+int cast_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t stream);
+int mean_tokens(const void* x, long long ldx, long long B, long long T, long long H, void* out, long long ldo,
+                int out_fp32, cudaStream_t stream);
+int field_projection(const void* rec, const float* Wp, const float* bp, void* out, int out_fp32, long long B,
+                     long long T, long long F, long long E, cudaStream_t stream);
+int build_user_sequence(const void* table, long long num_items, const long long* history, const int* lengths,
+                        const void* ctx, void* seq, float* mask, long long B, long long Hmax, long long Q, long long D,
+                        cudaStream_t stream);
+int inv_l2_norm(const void* x, int x_fp32, long long ldx, float* inv, long long rows, long long D, float eps,
+                cudaStream_t stream);
+int attention(const void* q, long long ldq, long long q_batch_rows, const void* k, long long ldk, const void* v,
+              long long ldv, long long kv_batch_rows, const float* key_mask, void* out, long long ldo, long long batch,
+              long long num_heads, long long nq, long long nk, long long head_dim, float scale, cudaStream_t stream);
+
+std::atomic<long long> g_launch_count{0};
+}  // namespace unirec
+
+using namespace unirec;
+
+#define COUNTED(expr)                                                                  \
+    do {                                                                               \
+        int rc__ = (expr);                                                             \
+        if (rc__ == UNIREC_OK) g_launch_count.fetch_add(1, std::memory_order_relaxed); \
+        return rc__;                                                                   \
+    } while (0)
+
+extern "C" {
+
+int unirec_abi_version(void) { return UNIREC_B200_ABI_VERSION; }
+const char* unirec_last_error(void) { return get_last_error(); }
+int64_t unirec_launch_count(void) { return g_launch_count.load(std::memory_order_relaxed); }
+
+int unirec_linear_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                       const void* residual, int64_t ldr, int64_t res_row_mod, void* out, int64_t ldo, int out_fp32,
+                       int64_t M, int64_t N, int64_t K, int epilogue, int block_n, int max_ctas, void* stream) {
+    COUNTED(gemm_bf16(A, lda, W, ldw, bias, residual, ldr, static_cast<int>(res_row_mod), out, ldo, out_fp32, M, N, K,
+                      epilogue, block_n, max_ctas, static_cast<cudaStream_t>(stream)));
+}
+
+int unirec_layernorm(const void* x, int x_fp32, int64_t ldx, int64_t in_row_mod, const void* residual, int64_t ldres,
+                     const float* gamma, const float* beta, float eps, void* out, int out_fp32, int64_t ldo,
+                     int64_t rows, int64_t H, void* stream) {
+    COUNTED(layernorm(x, x_fp32, ldx, static_cast<int>(in_row_mod), residual, ldres, gamma, beta, eps, out, out_fp32,
+                      ldo, rows, H, static_cast<cudaStream_t>(stream)));
+}
+
+int unirec_attention(const void* q, int64_t ldq, int64_t q_batch_rows, const void* k, int64_t ldk, const void* v,
+                     int64_t ldv, int64_t kv_batch_rows, const float* key_mask, void* out, int64_t ldo, int64_t batch,
+                     int64_t num_heads, int64_t nq, int64_t nk, int64_t head_dim, float scale, void* stream) {
+    COUNTED(attention(q, ldq, q_batch_rows, k, ldk, v, ldv, kv_batch_rows, key_mask, out, ldo, batch, num_heads, nq, nk,
+                      head_dim, scale, static_cast<cudaStream_t>(stream)));
+}
+
+int unirec_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream) {
+    COUNTED(cast_f32_to_bf16(in, out, n, static_cast<cudaStream_t>(stream)));
+}
+
+int unirec_mean_tokens(const void* x, int64_t ldx, int64_t B, int64_t T, int64_t H, void* out, int64_t ldo,
+                       int out_fp32, void* stream) {
+    COUNTED(mean_tokens(x, ldx, B, T, H, out, ldo, out_fp32, static_cast<cudaStream_t>(stream)));
+}
+
+int unirec_field_projection(const void* rec, const float* Wp, const float* bp, void* out, int out_fp32, int64_t B,
+                            int64_t T, int64_t F, int64_t E, void* stream) {
+    COUNTED(field_projection(rec, Wp, bp, out, out_fp32, B, T, F, E, static_cast<cudaStream_t>(stream)));
+}
+
+int unirec_build_user_sequence(const void* table, int64_t num_items, const int64_t* history, const int32_t* lengths,
+                               const void* ctx, void* seq, float* mask, int64_t B, int64_t Hmax, int64_t Q, int64_t D,
+                               void* stream) {
+    COUNTED(build_user_sequence(table, num_items, reinterpret_cast<const long long*>(history), lengths, ctx, seq, mask,
+                                B, Hmax, Q, D, static_cast<cudaStream_t>(stream)));
+}
+
+int unirec_inv_l2_norm(const void* x, int x_fp32, int64_t ldx, float* inv, int64_t rows, int64_t D, float eps,
+                       void* stream) {
+    COUNTED(inv_l2_norm(x, x_fp32, ldx, inv, rows, D, eps, static_cast<cudaStream_t>(stream)));
+}
+
+}  // extern "C"

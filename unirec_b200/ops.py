@@ -1,0 +1,246 @@
+"""Tensor-level wrappers over the C ABI (include/unirec_b200.h).
+
+PyTorch is used for what it is good at here - owning device memory and the current CUDA stream; every
+arithmetic op below is one launch of a hand-written sm_100a kernel in libunirec_b200.so.  Inputs
+must be CUDA tensors; anything else raises (no CPU fallback).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t: torch.Tensor, dtype, name: str):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (unirec_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if t.dim() >= 1 and t.stride(-1) != 1 and t.shape[-1] != 1:
+        raise RuntimeError(f"{name}: last dimension must be contiguous")
+
+
+def _rows2d(t: torch.Tensor, name: str) -> Tuple[int, int, int]:
+    """(rows, cols, ld) of a tensor viewed as 2-D [rows, cols] with a uniform row stride."""
+    if t.dim() == 2:
+        return t.shape[0], t.shape[1], t.stride(0)
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name}: tensors with more than 2 dims must be contiguous")
+    return t.numel() // t.shape[-1], t.shape[-1], t.shape[-1]
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def linear(a: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
+           epilogue: int = EPI_BIAS, residual: Optional[torch.Tensor] = None, res_row_mod: int = 0,
+           out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16,
+           block_n: int = 0, max_ctas: int = 0) -> torch.Tensor:
+    """out = epilogue(a @ weight.T + bias); a [.., K] bf16, weight [N, K] bf16, bias [N] fp32."""
+    _req(a, torch.bfloat16, "linear.a")
+    _req(weight, torch.bfloat16, "linear.weight")
+    M, K, lda = _rows2d(a, "linear.a")
+    N, K2 = weight.shape
+    if K2 != K:
+        raise RuntimeError(f"linear: inner dims differ ({K} vs {K2})")
+    if bias is not None:
+        _req(bias, torch.float32, "linear.bias")
+    if out is None:
+        out = torch.empty(*a.shape[:-1], N, device=a.device, dtype=out_dtype)
+    else:
+        _req(out, out.dtype, "linear.out")
+    _, No, ldo = _rows2d(out, "linear.out")
+    if No != N:
+        raise RuntimeError("linear: out has the wrong width")
+    ldr = 0
+    if residual is not None:
+        _req(residual, torch.bfloat16, "linear.residual")
+        _, _, ldr = _rows2d(residual, "linear.residual")
+    if out.dtype not in (torch.bfloat16, torch.float32):
+        raise RuntimeError("linear: out must be bf16 or fp32")
+    rc = _lib.load().unirec_linear_bf16(a.data_ptr(), lda, weight.data_ptr(), weight.stride(0), _ptr(bias),
+                                        _ptr(residual), ldr, res_row_mod, out.data_ptr(), ldo,
+                                        1 if out.dtype == torch.float32 else 0, M, N, K, epilogue, block_n, max_ctas,
+                                        _stream())
+    _lib.check(rc, "unirec_linear_bf16")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *,
+              residual: Optional[torch.Tensor] = None, rows: Optional[int] = None, in_row_mod: int = 0,
+              out_dtype: torch.dtype = torch.bfloat16, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """LayerNorm(x [+ residual]) over the last dim.  With in_row_mod > 0 the input has in_row_mod rows
+    that are broadcast over `rows` output rows."""
+    if x.dtype not in (torch.bfloat16, torch.float32):
+        raise RuntimeError("layernorm: x must be bf16 or fp32")
+    _req(x, x.dtype, "layernorm.x")
+    _req(gamma, torch.float32, "layernorm.gamma")
+    _req(beta, torch.float32, "layernorm.beta")
+    xr, H, ldx = _rows2d(x, "layernorm.x")
+    if rows is None:
+        rows = xr
+    if out is None:
+        shape = (rows, H) if (in_row_mod > 0 or x.dim() == 2) else x.shape
+        out = torch.empty(shape, device=x.device, dtype=out_dtype)
+    _, _, ldo = _rows2d(out, "layernorm.out")
+    ldres = 0
+    if residual is not None:
+        _req(residual, torch.bfloat16, "layernorm.residual")
+        _, _, ldres = _rows2d(residual, "layernorm.residual")
+    rc = _lib.load().unirec_layernorm(x.data_ptr(), 1 if x.dtype == torch.float32 else 0, ldx, in_row_mod,
+                                      _ptr(residual), ldres, gamma.data_ptr(), beta.data_ptr(), float(eps),
+                                      out.data_ptr(), 1 if out.dtype == torch.float32 else 0, ldo, rows, H, _stream())
+    _lib.check(rc, "unirec_layernorm")
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, batch: int, num_heads: int, nq: int, nk: int,
+              key_mask: Optional[torch.Tensor] = None, q_broadcast: bool = False,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Multi-head attention with head_dim 64.  q/k/v are 2-D row views (possibly column slices of a fused
+    projection buffer): q [batch*nq (or nq if q_broadcast), heads*64], k/v [batch*nk, heads*64]."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _req(t, torch.bfloat16, f"attention.{n}")
+        if t.dim() != 2:
+            raise RuntimeError("attention: q/k/v must be 2-D row views")
+    hd = num_heads * 64
+    if q.shape[1] != hd or k.shape[1] != hd or v.shape[1] != hd:
+        raise RuntimeError("attention: width must be num_heads*64")
+    if out is None:
+        out = torch.empty(batch * nq, hd, device=q.device, dtype=torch.bfloat16)
+    if key_mask is not None:
+        _req(key_mask, torch.float32, "attention.key_mask")
+        if tuple(key_mask.shape) != (batch, nk) or not key_mask.is_contiguous():
+            raise RuntimeError("attention: key_mask must be contiguous [batch, nk]")
+    rc = _lib.load().unirec_attention(q.data_ptr(), q.stride(0), 0 if q_broadcast else nq, k.data_ptr(), k.stride(0),
+                                      v.data_ptr(), v.stride(0), nk, _ptr(key_mask), out.data_ptr(), out.stride(0),
+                                      batch, num_heads, nq, nk, 64, 0.125, _stream())
+    _lib.check(rc, "unirec_attention")
+    return out
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    if x.dtype == torch.bfloat16:
+        return x
+    _req(x, torch.float32, "cast_bf16.x")
+    x = x.contiguous()
+    out = torch.empty_like(x, dtype=torch.bfloat16)
+    rc = _lib.load().unirec_cast_f32_to_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream())
+    _lib.check(rc, "unirec_cast_f32_to_bf16")
+    return out
+
+
+def mean_tokens(x: torch.Tensor, out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """x bf16 [B, T, H] -> [B, H] mean over T."""
+    _req(x, torch.bfloat16, "mean_tokens.x")
+    if x.dim() != 3 or not x.is_contiguous():
+        raise RuntimeError("mean_tokens: x must be contiguous [B, T, H]")
+    B, T, H = x.shape
+    out = torch.empty(B, H, device=x.device, dtype=out_dtype)
+    rc = _lib.load().unirec_mean_tokens(x.data_ptr(), H, B, T, H, out.data_ptr(), H,
+                                        1 if out_dtype == torch.float32 else 0, _stream())
+    _lib.check(rc, "unirec_mean_tokens")
+    return out
+
+
+def field_projection(rec: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor,
+                     out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """rec bf16 [B, T, E], weight fp32 [F, T], bias fp32 [F] -> [B, F, E]."""
+    _req(rec, torch.bfloat16, "field_projection.rec")
+    _req(weight, torch.float32, "field_projection.weight")
+    _req(bias, torch.float32, "field_projection.bias")
+    B, T, E = rec.shape
+    F = weight.shape[0]
+    out = torch.empty(B, F, E, device=rec.device, dtype=out_dtype)
+    rc = _lib.load().unirec_field_projection(rec.contiguous().data_ptr(), weight.contiguous().data_ptr(),
+                                             bias.data_ptr(), out.data_ptr(), 1 if out_dtype == torch.float32 else 0,
+                                             B, T, F, E, _stream())
+    _lib.check(rc, "unirec_field_projection")
+    return out
+
+
+def build_user_sequence(table: torch.Tensor, history: torch.Tensor, lengths: torch.Tensor,
+                        context: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """table bf16 [N, Q, D]; history int64 [B, Hmax]; lengths int32 [B]; context bf16 [B, Hmax, D] or None.
+    Returns (seq bf16 [B, Hmax*Q, D], mask fp32 [B, Hmax*Q])."""
+    _req(table, torch.bfloat16, "build_user_sequence.table")
+    _req(history, torch.int64, "build_user_sequence.history")
+    _req(lengths, torch.int32, "build_user_sequence.lengths")
+    if not (table.is_contiguous() and history.is_contiguous() and lengths.is_contiguous()):
+        raise RuntimeError("build_user_sequence: inputs must be contiguous")
+    N, Q, D = table.shape
+    B, Hmax = history.shape
+    if context is not None:
+        _req(context, torch.bfloat16, "build_user_sequence.context")
+        context = context.contiguous()
+    seq = torch.empty(B, Hmax * Q, D, device=table.device, dtype=torch.bfloat16)
+    mask = torch.empty(B, Hmax * Q, device=table.device, dtype=torch.float32)
+    rc = _lib.load().unirec_build_user_sequence(table.data_ptr(), N, history.data_ptr(), lengths.data_ptr(),
+                                                _ptr(context), seq.data_ptr(), mask.data_ptr(), B, Hmax, Q, D,
+                                                _stream())
+    _lib.check(rc, "unirec_build_user_sequence")
+    return seq, mask
+
+
+def inv_l2_norm(x: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    if x.dtype not in (torch.bfloat16, torch.float32):
+        raise RuntimeError("inv_l2_norm: x must be bf16 or fp32")
+    _req(x, x.dtype, "inv_l2_norm.x")
+    rows, D, ldx = _rows2d(x, "inv_l2_norm.x")
+    out = torch.empty(rows, device=x.device, dtype=torch.float32)
+    rc = _lib.load().unirec_inv_l2_norm(x.data_ptr(), 1 if x.dtype == torch.float32 else 0, ldx, out.data_ptr(), rows,
+                                        D, float(eps), _stream())
+    _lib.check(rc, "unirec_inv_l2_norm")
+    return out
+
+
+def score_topk(users: torch.Tensor, cands: torch.Tensor, k: int, *, user_inv: Optional[torch.Tensor] = None,
+               cand_inv: Optional[torch.Tensor] = None, index_base: int = 0
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Cosine top-k of users bf16 [B, D] against cands bf16 [N, D] -> (scores fp32 [B,k], idx int64 [B,k])."""
+    _req(users, torch.bfloat16, "score_topk.users")
+    _req(cands, torch.bfloat16, "score_topk.cands")
+    B, D = users.shape
+    N, D2 = cands.shape
+    if D != D2:
+        raise RuntimeError("score_topk: dims differ")
+    if user_inv is None:
+        user_inv = inv_l2_norm(users)
+    if cand_inv is None:
+        cand_inv = inv_l2_norm(cands)
+    lib = _lib.load()
+    ws_bytes = int(lib.unirec_score_topk_workspace_bytes(B, N, k))
+    if ws_bytes < 0:
+        _lib.check(1, "unirec_score_topk_workspace_bytes")
+    ws = torch.empty(max(ws_bytes, 16), device=users.device, dtype=torch.uint8)
+    scores = torch.empty(B, k, device=users.device, dtype=torch.float32)
+    idx = torch.empty(B, k, device=users.device, dtype=torch.int64)
+    rc = lib.unirec_score_topk(users.data_ptr(), users.stride(0), user_inv.data_ptr(), cands.data_ptr(),
+                               cands.stride(0), cand_inv.data_ptr(), B, N, D, k, index_base, scores.data_ptr(),
+                               idx.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
+    _lib.check(rc, "unirec_score_topk")
+    return scores, idx
+
+
+def topk_merge(scores: torch.Tensor, idx: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """scores fp32 [G, B, k], idx int64 [G, B, k] (each list descending) -> merged [B, k]."""
+    _req(scores, torch.float32, "topk_merge.scores")
+    _req(idx, torch.int64, "topk_merge.idx")
+    G, B, k = scores.shape
+    scores = scores.contiguous()
+    idx = idx.contiguous()
+    out_s = torch.empty(B, k, device=scores.device, dtype=torch.float32)
+    out_i = torch.empty(B, k, device=scores.device, dtype=torch.int64)
+    rc = _lib.load().unirec_topk_merge(scores.data_ptr(), idx.data_ptr(), G, B, k, out_s.data_ptr(), out_i.data_ptr(),
+                                       _stream())
+    _lib.check(rc, "unirec_topk_merge")
+    return out_s, out_i
