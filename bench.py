@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""Benchmark of the nested Q-Former encode-and-rank hot path (BASELINE.json north_star / config 5).
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+One JSON line on stdout (rank 0).  A "step" of the headline metric is one pass of the nested user path
+over one batch of synthetic users: gather 50 history items x 32 query tokens from the resident item-token
+table (+ sinusoidal PE) -> UserQFormer (64 queries x 1600 keys x 4 layers) -> prediction head -> pooled
+scoring vector -> cosine scoring against the 1M-row candidate pool -> top-100.  The item-token table and
+the candidate pool are produced beforehand by the item Q-Former over 1M synthetic items (config 3,
+item-range sharded); that run is timed too and reported as the "items" block (items/sec).
+
+Scaling is weak: every rank encodes --users-per-gpu users per step; user vectors are all-gathered, each
+rank scores all users against its 1/N of the candidate rows, per-rank top-100 lists are all-gathered and
+merged.  value = (N * users_per_gpu * K) / max-over-ranks device time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "users/sec (nested item->user Q-Former encode + top-100 rank over a 1M-item pool)"
+FLOPS_PER_USER = 36_173_774_848          # SURVEY.md section 8d (user Q-Former + head, S = 1600)
+FLOPS_PER_ITEM = 10_882_646_016          # SURVEY.md section 8d (item Q-Former -> query_outputs)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pool-items", type=int, default=1_000_000)
+    ap.add_argument("--users-per-gpu", type=int, default=4096)
+    ap.add_argument("--item-batch", type=int, default=4096)
+    ap.add_argument("--history", type=int, default=50)
+    ap.add_argument("--top-k", type=int, default=100)
+    ap.add_argument("--cpu-users", type=int, default=8, help="users in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def config_dict(args, n_gpus):
+    return {
+        "workload": "cfg5 nested item->user Q-Former encode + cosine top-100 over a 1M-item candidate pool "
+                    "(item-token table + pool produced by cfg3 item-token generation)",
+        "users_per_gpu_per_step": args.users_per_gpu, "global_users_per_step": args.users_per_gpu * n_gpus,
+        "history_items": args.history, "tokens_per_item": 32, "keys_per_user": args.history * 32,
+        "user_qformer": "4 layers x 64 queries, hidden 1024, 16 heads, FFN 4096, cross-attn every layer",
+        "item_qformer": "12 layers x 32 queries, 14 fields x 1024, cross-attn every 2nd layer",
+        "pool_items": args.pool_items, "top_k": args.top_k, "item_batch": args.item_batch,
+        "parallelism": f"users dp{n_gpus}; candidate rows sharded /{n_gpus}; all-gather + merge of top-k",
+        "l2": "inputs larger than L2 every step (user sequences 13.4 GB, candidate pool 2 GB / n_gpus, "
+              "item field batches cycled over a 0.9 GB pool)",
+    }
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+                power.append(float(p[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, p[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"], "hbm": d["hbm_gbs"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------- CPU baseline (oracle)
+def cpu_user_rank_sample(usd, tokens_cpu, history, lengths, cands_cpu, k, heads=16, predict=32):
+    """One pass of the oracle (CPU restatement of the reference) over a bounded sample of users."""
+    import torch
+    from oracle import qformer_oracle as O
+    with torch.no_grad():
+        seq, mask = O.build_user_sequences(tokens_cpu, history, lengths)
+        pred = O.user_qformer_forward(usd, seq, mask, num_heads=heads, num_item_tokens_to_predict=predict)
+        u = O.pooled_scoring_vector(pred)
+        return O.cosine_topk(u, cands_cpu, k)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (the oracle port - the reference is
+    Python and /root/reference does not travel to the GPU box), all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    import torch
+    from unirec_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    B, H = args.cpu_users, args.history
+    usd = synth.user_qformer_state_dict(seed=0, live_only=True)
+    g = torch.Generator().manual_seed(0)
+    n_tok = B * H
+    tokens = torch.randn(n_tok, 32, 1024, generator=g)
+    history = torch.arange(n_tok).view(B, H)
+    lengths = torch.full((B,), H, dtype=torch.long)
+    cands = torch.randn(args.pool_items, 1024, generator=g)
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_user_rank_sample(usd, tokens[:H], history[:1], lengths[:1], cands[:4096], args.top_k)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_user_rank_sample(usd, tokens, history, lengths, cands, args.top_k)
+    dt = time.perf_counter() - t0
+    value = B * args.steps / dt
+    sample = (f"{B} users/step x {args.steps} steps: sequence build + user Q-Former (S={H * 32}) + cosine top-"
+              f"{args.top_k} over {args.pool_items} candidates, fp32, torch CPU")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "users/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "users/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------- ours
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from unirec_b200 import _lib, ops
+    from unirec_b200.modules import QFormerForItemRepresentation, UserQFormer
+    from unirec_b200.pipeline import NestedRanker, shard_range
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a GPU: unirec_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    pk = peaks()
+    torch.manual_seed(0)   # same random-init weights on every rank
+    with torch.device(dev):
+        item = QFormerForItemRepresentation(num_fields=14).eval()
+        user = UserQFormer().eval()
+    item.prelayernorm_dtype = torch.bfloat16
+    user.prelayernorm_dtype = torch.bfloat16
+
+    # ------------------------------------------------------------------ stage A: item-token generation (cfg 3)
+    N, Bi = args.pool_items, args.item_batch
+    lo, hi = shard_range(N, rank, world)
+    n_local = hi - lo
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    pool_chunks = 4
+    fpool = torch.randn(pool_chunks, Bi, 14, 1024, device=dev, generator=gen)
+    fpool[:, :, 7, 768:] = 0                     # CLIP ViT-L/14 768-d field zero-padded to 1024
+    fmask = torch.ones(Bi, 14, device=dev, dtype=torch.long)
+    tokens = torch.empty(N if world > 1 else n_local, 32, 1024, device=dev, dtype=torch.bfloat16)
+    tok_local = tokens[lo:hi] if world > 1 else tokens
+    pooled = torch.empty(n_local, 1024, device=dev, dtype=torch.bfloat16)
+    chunks = [(c0, min(c0 + Bi, n_local)) for c0 in range(0, n_local, Bi)]
+
+    def encode_chunk(ci):
+        c0, c1 = chunks[ci]
+        tok = item.encode_query_tokens(fpool[ci % pool_chunks, :c1 - c0], fmask[:c1 - c0], out_dtype=torch.bfloat16)
+        tok_local[c0:c1].copy_(tok)
+        pooled[c0:c1].copy_(ops.mean_tokens(tok))
+
+    w_items = min(args.warmup, max(len(chunks) - 1, 0))
+    for ci in range(w_items):
+        encode_chunk(ci)
+    barrier()
+    l0 = _lib.launch_count()
+    ops.start_timing()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for ci in range(w_items, len(chunks)):
+        encode_chunk(ci)
+    e1.record()
+    barrier()
+    item_ms = max_over_ranks(e0.elapsed_time(e1))
+    item_stats = ops.stop_timing()
+    items_timed_local = sum(c1 - c0 for c0, c1 in chunks[w_items:])
+    items_timed = items_timed_local * world if world > 1 else items_timed_local
+    item_launches = _lib.launch_count() - l0
+    items_per_sec = items_timed / (item_ms * 1e-3) if item_ms > 0 else 0.0
+
+    if world > 1:   # replicate the token table (history gathers hit arbitrary items); setup, untimed
+        for r in range(world):
+            rlo, rhi = shard_range(N, r, world)
+            step_rows = 8192
+            for s0 in range(rlo, rhi, step_rows):
+                dist.broadcast(tokens[s0:min(s0 + step_rows, rhi)], src=r)
+
+    # ------------------------------------------------------------------ stage B: nested user encode + rank (cfg 5)
+    Bu, Hh, k = args.users_per_gpu, args.history, args.top_k
+    ranker = NestedRanker(user, tokens, pooled, k=k, index_base=lo)
+    hgen = torch.Generator(device=dev).manual_seed(99 + rank)
+    hist_batches = [torch.randint(0, N, (Bu, Hh), device=dev, generator=hgen) for _ in range(3)]
+    lengths = torch.full((Bu,), Hh, device=dev, dtype=torch.int32)
+
+    for s in range(args.warmup):
+        ranker(hist_batches[s % 3], lengths)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ops.start_timing()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        scores, idx = ranker(hist_batches[s % 3], lengths)
+    e1.record()
+    barrier()
+    user_ms = max_over_ranks(e0.elapsed_time(e1))
+    user_stats = ops.stop_timing()
+    clocks = sampler.stop() if rank == 0 else None
+    user_launches = _lib.launch_count() - l0
+    users_per_sec = Bu * world * args.steps / (user_ms * 1e-3)
+
+    # ------------------------------------------------------------------ e2e: host buffers in, host results out
+    h_hist = [b.cpu().pin_memory() for b in hist_batches]
+    h_len = lengths.cpu().pin_memory()
+    h_scores = torch.empty(Bu * world, k, dtype=torch.float32).pin_memory()
+    h_idx = torch.empty(Bu * world, k, dtype=torch.int64).pin_memory()
+
+    def e2e_step(s):
+        d_hist = h_hist[s % 3].to(dev, non_blocking=True)
+        d_len = h_len.to(dev, non_blocking=True)
+        sc, ix = ranker(d_hist, d_len)
+        h_scores.copy_(sc, non_blocking=True)
+        h_idx.copy_(ix, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        e2e_step(s)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_users = Bu * world * args.steps / e2e_s
+    h2d = Bu * Hh * 8 + Bu * 4
+    d2h = Bu * world * k * 12
+
+    # items e2e: fp32 field embeddings from pinned host memory, bf16 tokens back to pinned host memory
+    h_fields = fpool[0].cpu().pin_memory()
+    h_fmask = fmask.cpu().pin_memory()
+    h_tok = torch.empty(Bi, 32, 1024, dtype=torch.bfloat16).pin_memory()
+
+    def item_e2e_step():
+        x = h_fields.to(dev, non_blocking=True)
+        m = h_fmask.to(dev, non_blocking=True)
+        h_tok.copy_(item.encode_query_tokens(x, m, out_dtype=torch.bfloat16), non_blocking=True)
+        torch.cuda.synchronize()
+
+    item_e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e_items = 3
+    for _ in range(n_e2e_items):
+        item_e2e_step()
+    barrier()
+    item_e2e_s = max_over_ranks(time.perf_counter() - t0)
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N == 1 only)
+    cpu_baseline, items_cpu = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import qformer_oracle as O
+        torch.set_num_threads(os.cpu_count() or 1)
+        cores = torch.get_num_threads()
+        Bc = args.cpu_users
+        usd = {k_: v.detach().float().cpu() for k_, v in user.state_dict().items()}
+        hist_c = hist_batches[0][:Bc]
+        uniq = hist_c.reshape(-1)
+        tok_c = tokens[uniq].float().cpu()
+        hist_local = torch.arange(Bc * Hh).view(Bc, Hh)
+        len_c = torch.full((Bc,), Hh, dtype=torch.long)
+        cands_c = pooled.float().cpu()
+        cpu_user_rank_sample(usd, tok_c[:Hh], hist_local[:1], len_c[:1], cands_c[:4096], k)   # warm-up
+        t0 = time.perf_counter()
+        ref_s, ref_i = cpu_user_rank_sample(usd, tok_c, hist_local, len_c, cands_c, k)
+        dt = time.perf_counter() - t0
+        got_s, got_i = ranker(hist_c.contiguous(), lengths[:Bc].contiguous())
+        overlap = sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(got_i.cpu(), ref_i)) / (Bc * k)
+        cpu_baseline = {"value": Bc / dt, "unit": "users/s", "cores": cores, "kind": "port",
+                        "sample": f"{Bc} users of the timed workload (S={Hh * 32} keys, {N} candidates, top-{k}), "
+                                  f"oracle fp32 on torch CPU, 1 pass after warm-up",
+                        "parity_vs_gpu": {"score_max_abs_diff": float((got_s.cpu() - ref_s).abs().max()),
+                                          "topk_overlap": overlap}}
+        isd = {k_: v.detach().float().cpu() for k_, v in item.state_dict().items()}
+        xi = fpool[0, :32].cpu()
+        O.item_qformer_forward(isd, xi[:2], None)
+        t0 = time.perf_counter()
+        O.item_qformer_forward(isd, xi, None)
+        items_cpu = {"value": 32 / (time.perf_counter() - t0), "unit": "items/s", "cores": cores, "kind": "port",
+                     "sample": "32 items (14 fields x 1024), oracle fp32 on torch CPU"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    def roof(stats, kind, peak, unit_scale):
+        if kind not in stats or stats[kind][2] <= 0:
+            return None
+        n, work, ms = stats[kind]
+        ach = work / (ms * 1e-3) / unit_scale
+        return {"launches": n, "achieved": ach, "peak": peak, "frac": ach / peak, "avg_launch_ms": ms / n}
+
+    g_user = roof(user_stats, "gemm", pk["bf16_sustained"], 1e12)
+    g_item = roof(item_stats, "gemm", pk["bf16_sustained"], 1e12)
+    out = {
+        "metric": METRIC, "value": users_per_sec, "unit": "users/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": user_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config_dict(args, world),
+        "clocks": clocks,
+        "e2e": {"value": e2e_users, "unit": "users/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": user_launches,
+        "roofline": {
+            "kernel": "gemm_bf16_tcgen05_kernel (all projection/FFN GEMMs of the timed steps)",
+            "bound": "tensor", "achieved": g_user["achieved"] if g_user else None, "peak": pk["bf16_sustained"],
+            "unit": "TFLOP/s", "frac": g_user["frac"] if g_user else None, "traffic": None,
+            "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
+            "launches": g_user["launches"] if g_user else 0,
+            "share_of_step": (user_stats["gemm"][2] / user_ms) if g_user else None,
+            "end_to_end_frac_of_tensor_peak": users_per_sec / world * FLOPS_PER_USER / (pk["bf16_sustained"] * 1e12),
+            "other_kernels": {
+                "attention": roof(user_stats, "attention", pk["hbm"], 1e9),
+                "score_topk": roof(user_stats, "score_topk", pk["bf16_sustained"], 1e12),
+            },
+        },
+        "cpu_baseline": cpu_baseline,
+        "items": {
+            "metric": "items/sec (item Q-Former: 14 x 1024 field embeddings -> 32 x 1024 query tokens + pooled row)",
+            "value": items_per_sec, "unit": "items/s", "items_timed": items_timed, "ms_total": item_ms,
+            "gpu_launches": item_launches,
+            "e2e": {"value": Bi * world * n_e2e_items / item_e2e_s, "unit": "items/s",
+                    "h2d_bytes_per_step": Bi * 14 * 1024 * 4 + Bi * 14 * 8, "d2h_bytes_per_step": Bi * 32 * 1024 * 2},
+            "roofline": {"bound": "tensor", "achieved": g_item["achieved"] if g_item else None,
+                         "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": g_item["frac"] if g_item else None,
+                         "share_of_step": (item_stats["gemm"][2] / item_ms) if g_item else None,
+                         "end_to_end_frac_of_tensor_peak":
+                             items_per_sec / world * FLOPS_PER_ITEM / (pk["bf16_sustained"] * 1e12),
+                         "attention": roof(item_stats, "attention", pk["hbm"], 1e9)},
+            "cpu_baseline": items_cpu,
+        },
+    }
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # convenience: re-launch under torchrun when called directly with --gpus N
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"),
+               os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

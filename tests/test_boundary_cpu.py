@@ -1,0 +1,118 @@
+"""CPU: the drop-in boundary - C-ABI symbols, header/binding agreement, module contract, loud failure
+without a GPU.  No compute kernel is launched here."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "unirec_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return set(re.findall(r"\b(unirec_[a-z0-9_]+)\s*\(", src))
+
+
+def test_library_exports_every_declared_symbol():
+    from unirec_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "build the extension first: make -C unirec_b200/csrc"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _header_symbols()
+    assert declared, "no symbols parsed from include/unirec_b200.h"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/unirec_b200.h but not exported"
+    # the ctypes binding covers exactly the declared surface
+    assert set(_lib.EXPORTED_SYMBOLS) == declared
+    assert _lib.load().unirec_abi_version() == 1
+
+
+def test_workspace_query_is_host_only():
+    from unirec_b200 import _lib
+    lib = _lib.load()
+    assert lib.unirec_score_topk_workspace_bytes(4096, 1_000_000, 100) > 0
+    assert lib.unirec_score_topk_workspace_bytes(4096, 1_000_000, 1000) < 0   # k > 128 unsupported
+    assert b"k" in lib.unirec_last_error()
+
+
+def test_state_dict_keys_match_reference_layout():
+    from unirec_b200 import synth
+    from unirec_b200.modules import QFormerForItemRepresentation, UserQFormer
+    kw = dict(hidden_size=256, num_hidden_layers=4, num_attention_heads=4, intermediate_size=512)
+    item = QFormerForItemRepresentation(field_embedding_dim=256, num_fields=6, **kw)
+    ref_keys = set(synth.item_qformer_state_dict(hidden=256, layers=4, inter=512, field_dim=256, num_fields=6))
+    assert set(item.state_dict()) == ref_keys
+    # cross-attention only in even layers for the item model (cross_attention_freq=2), all layers for the user model
+    assert "qformer.encoder.layer.0.crossattention.self.key.weight" in ref_keys
+    assert "qformer.encoder.layer.1.crossattention.self.key.weight" not in ref_keys
+    user = UserQFormer(input_embedding_dim=256, num_item_tokens_to_predict=8, **kw)
+    ukeys = set(synth.user_qformer_state_dict(hidden=256, layers=4, inter=512, input_dim=256, num_predict=8))
+    assert set(user.state_dict()) == ukeys
+    assert "qformer.encoder.layer.1.crossattention.self.key.weight" in ukeys
+    # dead tensors of the reference checkpoint round-trip
+    for k in ("qformer.embeddings.word_embeddings.weight", "qformer.embeddings.position_ids",
+              "qformer.encoder.layer.0.intermediate.dense.weight", "qformer.encoder.layer.0.output.LayerNorm.bias"):
+        assert k in ref_keys
+    sd = synth.item_qformer_state_dict(hidden=256, layers=4, inter=512, field_dim=256, num_fields=6)
+    item.load_state_dict(sd, strict=True)
+    for k, v in item.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+
+
+def test_constructor_contract_and_attributes():
+    from unirec_b200.modules import QFormerForItemRepresentation, UserQFormer
+    with pytest.raises(ValueError):
+        QFormerForItemRepresentation()                      # num_fields is required (qformer_utils.py:21)
+    with pytest.raises(ValueError):
+        QFormerForItemRepresentation(hidden_size=250, num_attention_heads=4, num_fields=3)
+    m = QFormerForItemRepresentation(hidden_size=256, num_hidden_layers=2, num_attention_heads=4,
+                                     intermediate_size=512, field_embedding_dim=256, num_fields=6, dropout=0.2)
+    c = m.config
+    assert (c.hidden_size, c.num_hidden_layers, c.num_attention_heads, c.intermediate_size) == (256, 2, 4, 512)
+    assert (c.query_length, c.encoder_width, c.hidden_dropout_prob, c.cross_attention_freq) == (32, 256, 0.2, 2)
+    assert m.num_query_tokens == 32 and tuple(m.query_embeddings.shape) == (1, 32, 256)
+    u = UserQFormer(hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=512,
+                    input_embedding_dim=256, num_item_tokens_to_predict=8)
+    assert u.num_query_tokens == 64 and u.config.cross_attention_freq == 1
+    assert u.prediction_head[3].out_features == 8 * 256 and u.prediction_head[2].eps == 1e-5
+    # reference init rule: zero Linear bias, N(0, 0.02) weights
+    w = m.qformer.encoder.layer[0].attention.self.query.weight
+    assert 0.015 < float(w.detach().std()) < 0.025
+    assert float(m.qformer.encoder.layer[0].attention.self.query.bias.detach().abs().max()) == 0
+
+
+def test_no_cpu_fallback():
+    from unirec_b200 import ops
+    from unirec_b200.modules import QFormerForItemRepresentation
+    m = QFormerForItemRepresentation(hidden_size=256, num_hidden_layers=2, num_attention_heads=4,
+                                     intermediate_size=512, field_embedding_dim=256, num_fields=6).eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.randn(2, 6, 256))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.linear(torch.randn(4, 64).bfloat16(), torch.randn(8, 64).bfloat16())
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.score_topk(torch.randn(4, 64).bfloat16(), torch.randn(8, 64).bfloat16(), 2)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "unirec_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("qformer_oracle", "oracle") or "import oracle" not in src
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+
+
+def test_shard_range_partitions_exactly():
+    from unirec_b200.pipeline import shard_range
+    for n in (0, 1, 7, 1000, 1_000_000, 1_000_003):
+        for g in (1, 2, 3, 4, 8):
+            spans = [shard_range(n, r, g) for r in range(g)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(g - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)

@@ -1,0 +1,70 @@
+"""CPU, world_size 2 over gloo: the host-side multi-GPU logic of config 5 (row-sharded candidate pool,
+all-gather of user vectors and of per-rank top-k lists with global indices).  The per-rank top-k here is
+computed by the ORACLE (no GPU on this box); what is under test is the sharding + exchange plumbing in
+unirec_b200/pipeline.py, which is the same code that runs over NCCL."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import qformer_oracle as O
+        from unirec_b200.pipeline import gather_lists, gather_rows, shard_range
+        g = torch.Generator().manual_seed(5)
+        B, N, D, k = 6, 1001, 64, 20
+        users = torch.randn(B, D, generator=g)
+        cands = torch.randn(N, D, generator=g)
+        # users are encoded B/G per rank, then all-gathered
+        ulo, uhi = shard_range(B, rank, world)
+        u_all = gather_rows(users[ulo:uhi].contiguous())
+        assert torch.equal(u_all, users)
+        # each rank ranks all users against its candidate rows; indices are made global with index_base
+        lo, hi = shard_range(N, rank, world)
+        s, i = O.cosine_topk(u_all, cands[lo:hi], k)
+        s_all, i_all = gather_lists(s, i + lo)
+        assert tuple(s_all.shape) == (world, B, k)
+        merged_s, pos = torch.topk(s_all.permute(1, 0, 2).reshape(B, world * k), k, dim=-1)
+        merged_i = torch.gather(i_all.permute(1, 0, 2).reshape(B, world * k), 1, pos)
+        ref_s, ref_i = O.cosine_topk(users, cands, k)
+        ok = torch.allclose(merged_s, ref_s, atol=1e-6) and torch.equal(merged_i, ref_i)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_rank_and_gather_world2():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    results = dict(q.get(timeout=5) for _ in range(world))
+    assert results == {0: True, 1: True}
+
+
+def test_gather_is_identity_without_process_group():
+    from unirec_b200.pipeline import gather_lists, gather_rows
+    s, i = torch.randn(3, 5), torch.arange(15).view(3, 5)
+    s_all, i_all = gather_lists(s, i)
+    assert tuple(s_all.shape) == (1, 3, 5) and torch.equal(i_all[0], i)
+    assert gather_rows(s) is s

@@ -1,0 +1,121 @@
+"""GPU parity of the drop-in modules (CUDA path through the C ABI) against (a) the golden vectors the
+UNMODIFIED reference produced and (b) the CPU oracle, on the same synthetic weights and inputs.
+
+Tolerances (measured basis: reference fp32 vs reference cast to bf16 gives max|d| 0.086,
+mean|d| 0.0108, cosine 0.99989 on query_outputs): bf16 kernels vs fp32 reference must reach per-tensor
+cosine >= 0.9995, mean|d| <= 0.02, max|d| <= 0.15 on post-LayerNorm outputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.golden_cases import ITEM_CASES, USER_CASES
+from unirec_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda:0"
+
+
+def _report(name, out, ref):
+    out = out.float().cpu().flatten()
+    ref = torch.as_tensor(ref).float().flatten()
+    d = (out - ref).abs()
+    cos = float(torch.nn.functional.cosine_similarity(out, ref, dim=0))
+    print(f"{name}: max|d|={float(d.max()):.4f} mean|d|={float(d.mean()):.5f} cos={cos:.6f} |ref|max={float(ref.abs().max()):.3f}")
+    return float(d.max()), float(d.mean()), cos
+
+
+def _check(name, out, ref, max_tol=0.15, mean_tol=0.02, cos_tol=0.9995):
+    assert torch.isfinite(out).all(), name
+    mx, mean, cos = _report(name, out, ref)
+    assert mx <= max_tol and mean <= mean_tol and cos >= cos_tol, (name, mx, mean, cos)
+
+
+@pytest.mark.parametrize("name", list(ITEM_CASES))
+def test_item_qformer_matches_reference_golden(name):
+    from unirec_b200.modules import QFormerForItemRepresentation
+    c = ITEM_CASES[name]
+    mk = c["model"]
+    sd = synth.item_qformer_state_dict(**mk, seed=c["seed"], attn_std=c["attn_std"])
+    model = QFormerForItemRepresentation(hidden_size=mk["hidden"], num_hidden_layers=mk["layers"],
+                                         num_attention_heads=c["heads"], intermediate_size=mk["inter"],
+                                         num_query_tokens=mk["num_query"], field_embedding_dim=mk["field_dim"],
+                                         num_fields=mk["num_fields"])
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).eval()
+    x, mask = synth.item_fields(**c["input"])
+    g = np.load(os.path.join(GOLDEN, f"item_{name}.npz"))
+    out = model(x.to(DEV), mask.to(DEV))
+    assert set(out) == {"query_outputs", "item_representation", "reconstructed_fields"}
+    assert out["query_outputs"].dtype == torch.float32
+    _check(f"item[{name}].query_outputs", out["query_outputs"], g["query_outputs"])
+    _check(f"item[{name}].item_representation", out["item_representation"], g["item_representation"],
+           max_tol=0.05, mean_tol=0.01)
+    _check(f"item[{name}].reconstructed_fields", out["reconstructed_fields"], g["reconstructed_fields"],
+           max_tol=0.05, mean_tol=0.01, cos_tol=0.999)
+    # attention_mask=None path (models/qformer_utils.py:40-41)
+    out0 = model(x[:1].to(DEV), None)
+    _check(f"item[{name}].nomask", out0["query_outputs"], g["query_outputs_nomask_row0"])
+    # bf16 pre-LayerNorm buffers (the faster setting) must meet the same bar
+    model.prelayernorm_dtype = torch.bfloat16
+    out_b = model(x.to(DEV), mask.to(DEV))
+    _check(f"item[{name}].query_outputs(bf16 pre-LN)", out_b["query_outputs"], g["query_outputs"])
+    # token-only entry point used by generation
+    tok = model.encode_query_tokens(x.to(DEV), mask.to(DEV))
+    assert tok.dtype == torch.bfloat16
+    _check(f"item[{name}].encode_query_tokens", tok, g["query_outputs"])
+
+
+@pytest.mark.parametrize("name", list(USER_CASES))
+def test_user_qformer_matches_reference_golden(name):
+    from unirec_b200.modules import UserQFormer
+    c = USER_CASES[name]
+    mk = c["model"]
+    sd = synth.user_qformer_state_dict(**mk, seed=c["seed"], attn_std=c["attn_std"])
+    model = UserQFormer(hidden_size=mk["hidden"], num_hidden_layers=mk["layers"], num_attention_heads=c["heads"],
+                        intermediate_size=mk["inter"], num_query_tokens=mk["num_query"],
+                        input_embedding_dim=mk["input_dim"], num_item_tokens_to_predict=mk["num_predict"])
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).eval()
+    x, mask = synth.user_sequences(**c["input"])
+    g = np.load(os.path.join(GOLDEN, f"user_{name}.npz"))["predicted_item_tokens"]
+    out = model(x.to(DEV), mask.to(DEV))
+    assert tuple(out.shape) == g.shape and out.dtype == torch.float32
+    # prediction-head output is not LayerNorm-ed: |ref|max ~ 2.8, absolute bar scaled accordingly
+    _check(f"user[{name}].predicted_item_tokens", out, g, max_tol=0.1, mean_tol=0.015, cos_tol=0.9995)
+    # chunked execution (K/V workspace cap) gives the same answer
+    model.max_kv_bytes = 1
+    out_c = model(x.to(DEV), mask.to(DEV))
+    _check(f"user[{name}].chunked", out_c, g, max_tol=0.1, mean_tol=0.015, cos_tol=0.9995)
+
+
+def test_item_qformer_against_oracle_larger_batch():
+    """B = 300 (not a multiple of any tile size) on the small model, oracle computed here on CPU."""
+    from oracle import qformer_oracle as O
+    from unirec_b200.modules import QFormerForItemRepresentation
+    c = ITEM_CASES["small"]
+    mk = c["model"]
+    sd = synth.item_qformer_state_dict(**mk, seed=21, attn_std=0.1)
+    model = QFormerForItemRepresentation(hidden_size=mk["hidden"], num_hidden_layers=mk["layers"],
+                                         num_attention_heads=c["heads"], intermediate_size=mk["inter"],
+                                         num_query_tokens=mk["num_query"], field_embedding_dim=mk["field_dim"],
+                                         num_fields=mk["num_fields"])
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).eval()
+    x, mask = synth.item_fields(batch=300, num_fields=6, dim=256, seed=22, clip_field=2, presence=0.5, all_masked_row=7)
+    ref = O.item_qformer_forward(sd, x, mask, num_heads=c["heads"])
+    out = model(x.to(DEV), mask.to(DEV))
+    for k in ref:
+        _check(f"item[small,B=300].{k}", out[k], ref[k], max_tol=0.15 if k == "query_outputs" else 0.05,
+               mean_tol=0.02, cos_tol=0.999)
+
+
+def test_train_mode_with_dropout_is_refused():
+    from unirec_b200.modules import QFormerForItemRepresentation
+    m = QFormerForItemRepresentation(hidden_size=256, num_hidden_layers=2, num_attention_heads=4,
+                                     intermediate_size=512, field_embedding_dim=256, num_fields=6).to(DEV)
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(torch.randn(2, 6, 256, device=DEV))

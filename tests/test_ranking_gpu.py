@@ -1,0 +1,134 @@
+"""GPU parity of fused cosine scoring + top-k, the top-k merge and the nested ranker against the oracle.
+
+Scores: the kernel multiplies bf16 inputs exactly and accumulates in fp32, the oracle does the same in
+fp32 on the same bf16-rounded inputs, so scores agree to fp32 summation-order error (atol 2e-5).  Indices
+must be identical except where the oracle's neighbouring scores tie within that tolerance."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import qformer_oracle as O
+from tests.golden_cases import SCORING_CASE
+from unirec_b200 import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 2e-5
+
+
+def _assert_topk_matches(s, i, users_bf, cands_bf, k):
+    full = O.cosine_scores(users_bf.cpu().float(), cands_bf.cpu().float())     # [B, N] oracle
+    ks = min(k, full.shape[1])
+    ref_s, ref_i = torch.topk(full, ks, dim=-1)
+    s, i = s.cpu(), i.cpu()
+    assert torch.allclose(s[:, :ks], ref_s, atol=TOL, rtol=0), float((s[:, :ks] - ref_s).abs().max())
+    # every returned index really has the returned score, no duplicates, descending order
+    got = torch.gather(full, 1, i[:, :ks])
+    assert torch.allclose(got, s[:, :ks], atol=TOL, rtol=0)
+    assert all(len(set(r.tolist())) == ks for r in i[:, :ks])
+    assert bool((s[:, :-1] >= s[:, 1:]).all())
+    # index identity wherever the oracle's gap to both neighbours exceeds the tolerance
+    gap_ok = torch.ones_like(ref_s, dtype=torch.bool)
+    d = (ref_s[:, :-1] - ref_s[:, 1:]) > 4 * TOL
+    gap_ok[:, 1:] &= d
+    gap_ok[:, :-1] &= d
+    kth_gap = (ref_s[:, -1] - torch.topk(full, min(ks + 1, full.shape[1]), dim=-1)[0][:, -1]) > 4 * TOL
+    gap_ok[:, -1] &= kth_gap if ks < full.shape[1] else True
+    assert bool((i[:, :ks][gap_ok] == ref_i[gap_ok]).all())
+    if ks < k:
+        assert bool((i[:, ks:] == -1).all()) and bool(torch.isinf(s[:, ks:]).all())
+
+
+def test_scoring_golden_case():
+    from unirec_b200 import ops
+    c = SCORING_CASE
+    u = synth.normal("score_users", (c["users"], c["dim"]), c["seed"]).to(torch.bfloat16).to(DEV)
+    C = synth.normal("score_cands", (c["cands"], c["dim"]), c["seed"]).to(torch.bfloat16).to(DEV)
+    s, i = ops.score_topk(u, C, c["k"])
+    _assert_topk_matches(s, i, u, C, c["k"])
+    # against the reference-produced golden (fp32 inputs): bf16 input rounding moves cosine by <~ 4e-3
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "scoring.npz"))
+    assert np.abs(s.cpu().numpy() - g["scores"]).max() < 4e-3
+    overlap = np.mean([len(set(a.tolist()) & set(b.tolist())) / c["k"] for a, b in zip(i.cpu().numpy(), g["indices"])])
+    assert overlap > 0.9
+
+
+@pytest.mark.parametrize("B,N,k", [(1, 300, 100), (130, 5000, 100), (64, 70001, 100), (300, 40960, 128), (5, 50, 100),
+                                   (17, 4096, 1)])
+def test_score_topk_random(B, N, k):
+    from unirec_b200 import ops
+    g = torch.Generator().manual_seed(B * 31 + N)
+    u = torch.randn(B, 256, generator=g).to(torch.bfloat16).to(DEV)
+    C = (torch.randn(N, 256, generator=g) * torch.rand(N, 1, generator=g) * 3).to(torch.bfloat16).to(DEV)
+    s, i = ops.score_topk(u, C, k, index_base=0)
+    _assert_topk_matches(s, i, u, C, k)
+    s2, i2 = ops.score_topk(u, C, k, index_base=1000)
+    assert torch.equal(i2[i >= 0], i[i >= 0] + 1000)
+
+
+def test_score_topk_adversarial_order_and_ties():
+    """Candidates sorted by ascending similarity to user 0 (every new tile beats the running threshold,
+    forcing repeated list compactions), plus exact duplicates (ties)."""
+    from unirec_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    N, D = 60000, 128
+    u = torch.randn(4, D, generator=g).to(torch.bfloat16)
+    C = torch.randn(N, D, generator=g).to(torch.bfloat16)
+    order = torch.argsort(O.cosine_scores(u[:1].float(), C.float())[0])
+    C = C[order].contiguous()
+    C[100:400] = C[N - 1]       # 300 copies of the best candidate for user 0: massive tie at the top
+    s, i = ops.score_topk(u.to(DEV), C.to(DEV), 100)
+    _assert_topk_matches(s, i, u, C, 100)
+    assert float(s[0, 0]) == pytest.approx(float(s[0, 99]), abs=TOL)   # all 100 winners are the tied copies
+
+
+def test_topk_merge_matches_global_topk():
+    from unirec_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    B, N, k, G = 33, 8000, 100, 4
+    u = torch.randn(B, 128, generator=g).to(torch.bfloat16).to(DEV)
+    C = torch.randn(N, 128, generator=g).to(torch.bfloat16).to(DEV)
+    parts_s, parts_i = [], []
+    for r in range(G):
+        lo, hi = r * N // G, (r + 1) * N // G
+        s, i = ops.score_topk(u, C[lo:hi], k, index_base=lo)
+        parts_s.append(s)
+        parts_i.append(i)
+    ms, mi = ops.topk_merge(torch.stack(parts_s), torch.stack(parts_i))
+    _assert_topk_matches(ms, mi, u, C, k)
+
+
+def test_nested_ranker_end_to_end_small():
+    """item tokens -> user sequence -> UserQFormer -> pooled vector -> top-k, vs the oracle chain."""
+    from unirec_b200 import ops
+    from unirec_b200.modules import UserQFormer
+    from unirec_b200.pipeline import NestedRanker
+    mk = dict(hidden=256, layers=2, inter=512, num_query=64, input_dim=256, num_predict=8)
+    sd = synth.user_qformer_state_dict(**mk, seed=31, attn_std=0.1)
+    um = UserQFormer(hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=512,
+                     num_query_tokens=64, input_embedding_dim=256, num_item_tokens_to_predict=8)
+    um.load_state_dict(sd, strict=True)
+    um = um.to(DEV).eval()
+    N, Q, D, B, Hmax, k = 3000, 32, 256, 9, 6, 100
+    table = synth.normal("tok_table", (N, Q, D), 32).to(torch.bfloat16)
+    cands = table.float().mean(dim=1).to(torch.bfloat16)
+    gen = torch.Generator().manual_seed(33)
+    history = torch.randint(0, N, (B, Hmax), generator=gen)
+    lengths = torch.randint(1, Hmax + 1, (B,), generator=gen).to(torch.int32)
+    ranker = NestedRanker(um, table.to(DEV), cands.to(DEV), k=k)
+    uvec = ranker.encode_users(history.to(DEV), lengths.to(DEV))
+    # oracle chain on CPU (fp32) from the same bf16 table
+    seq, mask = O.build_user_sequences(table.float(), history, lengths.long())
+    pred = O.user_qformer_forward(sd, seq, mask, num_heads=4, num_item_tokens_to_predict=8)
+    u_ref = O.pooled_scoring_vector(pred)
+    cos = torch.nn.functional.cosine_similarity(uvec.float().cpu(), u_ref, dim=-1)
+    print("user-vector cosine vs oracle:", cos.min().item())
+    assert float(cos.min()) > 0.999
+    s, i = ranker.rank(uvec)
+    _assert_topk_matches(s, i, uvec, cands, k)           # exact w.r.t. the vectors actually scored
+    ref_s, ref_i = O.cosine_topk(u_ref, cands.float(), k)
+    overlap = np.mean([len(set(a.tolist()) & set(b.tolist())) / k for a, b in zip(i.cpu().numpy(), ref_i.numpy())])
+    print("top-100 overlap with the fp32 oracle chain:", overlap)
+    assert overlap > 0.85 and float((s.cpu() - ref_s).abs().max()) < 2e-2

@@ -36,9 +36,10 @@ _SIGNATURES = {
     "unirec_build_user_sequence": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "unirec_inv_l2_norm": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_int64, c_float, c_void_p]),
-    # TMP "unirec_score_topk_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
-    # TMP score_topk
-    # TMP "unirec_topk_merge": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "unirec_score_topk_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
+    "unirec_score_topk": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64,
+                                  c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "unirec_topk_merge": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -12,6 +12,7 @@
 // models/qformer.py:185-198, attention output dense :286, FFN up :359 (+ GELU :360), FFN down :372,
 // heads models/qformer_utils.py:50,53 and training/user_qformer_training.py:38-43.
 #include "common.cuh"
+#include "umma_pipe.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -42,120 +43,45 @@ struct GemmParams {
     int num_m_blocks, num_n_blocks;
 };
 
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;
-constexpr int UMMA_K = 16;
+constexpr int BLOCK_M = PIPE_BLOCK_M;
+constexpr int BLOCK_K = PIPE_BLOCK_K;
 constexpr int NUM_THREADS = 384;
 constexpr int NUM_EPI_THREADS = 256;
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 
 template <int BLOCK_N>
-struct Cfg {
-    static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
-    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
-    static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages (power of two: 256 / 512)
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-};
+using Cfg = UmmaPipe<BLOCK_N, (BLOCK_N == 256) ? 4 : 6>;
 
 template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmParams p) {
-    using C = Cfg<BLOCK_N>;
-    constexpr int STAGES = C::STAGES;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
-    uint64_t* full_bar = bars;
-    uint64_t* empty_bar = bars + STAGES;
-    uint64_t* tmem_full_bar = bars + 2 * STAGES;
-    uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
     }
-    if (warp_idx == 1 && lane == 0) {
-        for (int i = 0; i < STAGES; ++i) {
-            mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
-        }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&tmem_full_bar[i], 1);
-            mbar_init(&tmem_empty_bar[i], NUM_EPI_THREADS);
-        }
-        fence_mbar_init();
-    }
-    if (warp_idx == 2) {
-        tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
+    Cfg<BLOCK_N> pipe;
+    pipe.setup(smem_raw, warp_idx, lane, NUM_EPI_THREADS);
 
     const int num_kb = p.K / BLOCK_K;
     const int num_tiles = p.num_m_blocks * p.num_n_blocks;
 
     if (warp_idx == 0) {
         // ===================== TMA producer =====================
-        int stage = 0;
-        uint32_t phase = 0;
+        RingState rs;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_blk = tile / p.num_n_blocks;
             const int n_blk = tile % p.num_n_blocks;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-                    tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K,
-                                m_blk * BLOCK_M);
-                    tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * C::B_STAGE_BYTES, kb * BLOCK_K,
-                                n_blk * BLOCK_N);
-                }
-                __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            }
+            pipe_produce_tile(pipe, rs, &tmap_a, &tmap_b, m_blk * BLOCK_M, n_blk * BLOCK_N, num_kb, lane);
         }
     } else if (warp_idx == 1) {
         // ===================== UMMA issuer =====================
-        constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
-        int stage = 0;
-        uint32_t phase = 0;
+        RingState rs;
         uint32_t iter = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
-            const uint32_t as = iter & 1u;
-            const uint32_t aphase = (iter >> 1) & 1u;
-            mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_base + as * BLOCK_N;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t a_addr = smem_u32(smem_a + stage * A_STAGE_BYTES);
-                    const uint32_t b_addr = smem_u32(smem_b + stage * C::B_STAGE_BYTES);
-#pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        const uint64_t da = umma_smem_desc_sw128(a_addr + k * UMMA_K * 2);
-                        const uint64_t db = umma_smem_desc_sw128(b_addr + k * UMMA_K * 2);
-                        umma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-                    }
-                    umma_commit(&empty_bar[stage]);                       // frees this smem slot
-                    if (kb == num_kb - 1) umma_commit(&tmem_full_bar[as]);  // accumulator complete
-                }
-                __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            }
-        }
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter)
+            pipe_mma_tile<BLOCK_N>(pipe, rs, iter, num_kb, lane);
     } else if (warp_idx >= 4) {
         // ===================== epilogue =====================
         const int q = warp_idx & 3;             // TMEM lane quadrant this warp may access
@@ -165,10 +91,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
             const int m_blk = tile / p.num_n_blocks;
             const int n_blk = tile % p.num_n_blocks;
-            const uint32_t as = iter & 1u;
-            const uint32_t aphase = (iter >> 1) & 1u;
-            mbar_wait(&tmem_full_bar[as], aphase);
-            tc_fence_after();
+            const uint32_t tmem_acc = pipe_epilogue_wait<BLOCK_N>(pipe, iter);
 
             const int row = m_blk * BLOCK_M + q * 32 + lane;
             const bool row_ok = row < p.M;
@@ -178,7 +101,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 const int col_in_tile = half * COLS_PER_WARP + c * 32;
                 const int n0 = n_blk * BLOCK_N + col_in_tile;
                 uint32_t v[32];
-                tmem_ld_32x32(tmem_base + as * BLOCK_N + col_in_tile + (static_cast<uint32_t>(q * 32) << 16), v);
+                tmem_ld_32x32(tmem_acc + col_in_tile + (static_cast<uint32_t>(q * 32) << 16), v);
 
                 uint4 res[4];
                 if constexpr (MODE == EPI_BIAS_RESIDUAL) {
@@ -192,8 +115,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 tmem_ld_wait();
                 if (c == COLS_PER_WARP / 32 - 1) {
                     // all TMEM reads of this accumulator stage are in registers: hand it back to the issuer
-                    tc_fence_before();
-                    mbar_arrive(&tmem_empty_bar[as]);
+                    pipe_epilogue_release(pipe, iter);
                 }
                 float f[32];
 #pragma unroll
@@ -244,13 +166,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             }
         }
     }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp_idx == 2) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, C::TMEM_COLS);
-    }
+    pipe.teardown(warp_idx);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,394 @@
+"""Drop-in nn.Module mirrors of the reference's Q-Former wrappers, running on the sm_100a kernels.
+
+Same class names, constructor arguments, attributes (`.config`, `.num_query_tokens`, `.qformer`,
+`.query_embeddings`), output contract and **state-dict keys** as
+  * QFormerForItemRepresentation  - models/qformer_utils.py:16-60 (identical copy models/qformer_model.py:6-50)
+  * UserQFormer                   - training/user_qformer_training.py:17-68
+so that `load_state_dict(checkpoint['model_state_dict'])` of a reference checkpoint works unchanged,
+including the tensors the query-only path never executes (word/position embeddings, the text-branch
+FFN `intermediate`/`output`).
+
+The forward pass is NOT the reference's eager op sequence.  Per call it runs, per layer:
+  one fused QKV projection GEMM (tcgen05) -> fused self-attention -> output-projection GEMM with the
+  residual added in the epilogue -> LayerNorm; cross-attention K/V for ALL cross layers come from ONE
+  GEMM over the field/sequence embeddings (the encoder input is layer-invariant); the FFN is a
+  GEMM+bias+erf-GELU and a GEMM+bias+residual, then LayerNorm.  The query-token LayerNorm is
+  batch-invariant and is computed on Q rows and broadcast.  Activations are bf16, accumulation and all
+  softmax / LayerNorm statistics are fp32.
+
+There is no CPU fallback: inputs must be CUDA tensors and the module must live on a CUDA device.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+LN_EPS = 1e-12  # BertConfig.layer_norm_eps default used by the reference backbone (models/qformer.py:65)
+
+
+def _bert_config(**kw):
+    from transformers.models.bert.configuration_bert import BertConfig
+    return BertConfig(**kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# Parameter containers with the reference's attribute names (no compute in these classes).
+# ------------------------------------------------------------------------------------------------
+class _SelfAttentionParams(nn.Module):
+    def __init__(self, hidden: int, kv_in: int):
+        super().__init__()
+        self.query = nn.Linear(hidden, hidden)
+        self.key = nn.Linear(kv_in, hidden)
+        self.value = nn.Linear(kv_in, hidden)
+
+
+class _DenseLN(nn.Module):
+    def __init__(self, fan_in: int, hidden: int, eps: float):
+        super().__init__()
+        self.dense = nn.Linear(fan_in, hidden)
+        self.LayerNorm = nn.LayerNorm(hidden, eps=eps)
+
+
+class _AttentionParams(nn.Module):
+    def __init__(self, hidden: int, kv_in: int, eps: float):
+        super().__init__()
+        setattr(self, "self", _SelfAttentionParams(hidden, kv_in))
+        self.output = _DenseLN(hidden, hidden, eps)
+
+
+class _Dense(nn.Module):
+    def __init__(self, fan_in: int, fan_out: int):
+        super().__init__()
+        self.dense = nn.Linear(fan_in, fan_out)
+
+
+class _LayerParams(nn.Module):
+    def __init__(self, cfg, layer_num: int):
+        super().__init__()
+        h, i = cfg.hidden_size, cfg.intermediate_size
+        self.attention = _AttentionParams(h, h, cfg.layer_norm_eps)
+        self.has_cross_attention = bool(cfg.add_cross_attention and layer_num % cfg.cross_attention_freq == 0)
+        if self.has_cross_attention:
+            self.crossattention = _AttentionParams(h, cfg.encoder_width, cfg.layer_norm_eps)
+        # text branch: allocated and checkpointed by the reference, never executed on this path
+        self.intermediate = _Dense(h, i)
+        self.output = _DenseLN(i, h, cfg.layer_norm_eps)
+        self.intermediate_query = _Dense(h, i)
+        self.output_query = _DenseLN(i, h, cfg.layer_norm_eps)
+
+
+class _EncoderParams(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.layer = nn.ModuleList([_LayerParams(cfg, i) for i in range(cfg.num_hidden_layers)])
+
+
+class _EmbeddingParams(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.word_embeddings = nn.Embedding(cfg.vocab_size, cfg.hidden_size, padding_idx=cfg.pad_token_id)
+        self.position_embeddings = nn.Embedding(cfg.max_position_embeddings, cfg.hidden_size)
+        self.LayerNorm = nn.LayerNorm(cfg.hidden_size, eps=cfg.layer_norm_eps)
+        self.register_buffer("position_ids", torch.arange(cfg.max_position_embeddings).expand((1, -1)))
+
+
+class QFormerBackbone(nn.Module):
+    """Parameter tree of the reference `BertModel(config, add_pooling_layer=False)`
+    (models/qformer.py:677-697) plus the fused CUDA forward of its query-only mode (:804-972)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        if cfg.hidden_size % cfg.num_attention_heads != 0:
+            raise ValueError("The hidden size (%d) is not a multiple of the number of attention heads (%d)"
+                             % (cfg.hidden_size, cfg.num_attention_heads))  # models/qformer.py:115-121
+        if cfg.hidden_size // cfg.num_attention_heads != 64:
+            raise ValueError("unirec_b200 attention kernels are built for head_dim 64 "
+                             f"(got {cfg.hidden_size // cfg.num_attention_heads})")
+        self.config = cfg
+        self.embeddings = _EmbeddingParams(cfg)
+        self.encoder = _EncoderParams(cfg)
+        self._init_weights()
+        self._pack: Optional[dict] = None
+        self._pack_key = None
+
+    def _init_weights(self):
+        # reference rule, models/qformer.py:664-674: N(0, initializer_range) weights, zero bias, LN (1, 0)
+        std = self.config.initializer_range
+        for m in self.modules():
+            if isinstance(m, (nn.Linear, nn.Embedding)):
+                m.weight.data.normal_(mean=0.0, std=std)
+            elif isinstance(m, nn.LayerNorm):
+                m.bias.data.zero_()
+                m.weight.data.fill_(1.0)
+            if isinstance(m, nn.Linear) and m.bias is not None:
+                m.bias.data.zero_()
+
+    # -------------------------------------------------------------------------------- weight packing
+    def _live_params(self) -> List[torch.Tensor]:
+        ps = [self.embeddings.LayerNorm.weight, self.embeddings.LayerNorm.bias]
+        for lyr in self.encoder.layer:
+            blocks = [lyr.attention] + ([lyr.crossattention] if lyr.has_cross_attention else [])
+            for blk in blocks:
+                s = getattr(blk, "self")
+                ps += [s.query.weight, s.query.bias, s.key.weight, s.key.bias, s.value.weight, s.value.bias,
+                       blk.output.dense.weight, blk.output.dense.bias, blk.output.LayerNorm.weight,
+                       blk.output.LayerNorm.bias]
+            ps += [lyr.intermediate_query.dense.weight, lyr.intermediate_query.dense.bias,
+                   lyr.output_query.dense.weight, lyr.output_query.dense.bias,
+                   lyr.output_query.LayerNorm.weight, lyr.output_query.LayerNorm.bias]
+        return ps
+
+    def packed(self) -> dict:
+        """bf16 / fused copies of the live weights, rebuilt only when a parameter changed."""
+        live = self._live_params()
+        key = (live[0].device, tuple(p._version for p in live), tuple(p.data_ptr() for p in live[:4]))
+        if self._pack is not None and self._pack_key == key:
+            return self._pack
+        bf = torch.bfloat16
+        f32 = lambda t: t.detach().float().contiguous()
+        layers = []
+        kv_w, kv_b = [], []
+        for lyr in self.encoder.layer:
+            a = getattr(lyr.attention, "self")
+            d = {
+                "w_qkv": torch.cat([a.query.weight, a.key.weight, a.value.weight], 0).detach().to(bf).contiguous(),
+                "b_qkv": torch.cat([a.query.bias, a.key.bias, a.value.bias], 0).detach().float().contiguous(),
+                "w_o": lyr.attention.output.dense.weight.detach().to(bf).contiguous(),
+                "b_o": f32(lyr.attention.output.dense.bias),
+                "ln1_g": f32(lyr.attention.output.LayerNorm.weight), "ln1_b": f32(lyr.attention.output.LayerNorm.bias),
+                "w_1": lyr.intermediate_query.dense.weight.detach().to(bf).contiguous(),
+                "b_1": f32(lyr.intermediate_query.dense.bias),
+                "w_2": lyr.output_query.dense.weight.detach().to(bf).contiguous(),
+                "b_2": f32(lyr.output_query.dense.bias),
+                "ln3_g": f32(lyr.output_query.LayerNorm.weight), "ln3_b": f32(lyr.output_query.LayerNorm.bias),
+                "cross": lyr.has_cross_attention,
+            }
+            if lyr.has_cross_attention:
+                c = getattr(lyr.crossattention, "self")
+                d.update({
+                    "w_qc": c.query.weight.detach().to(bf).contiguous(), "b_qc": f32(c.query.bias),
+                    "w_oc": lyr.crossattention.output.dense.weight.detach().to(bf).contiguous(),
+                    "b_oc": f32(lyr.crossattention.output.dense.bias),
+                    "ln2_g": f32(lyr.crossattention.output.LayerNorm.weight),
+                    "ln2_b": f32(lyr.crossattention.output.LayerNorm.bias),
+                    "kv_slot": len(kv_w),
+                })
+                kv_w.append(torch.cat([c.key.weight, c.value.weight], 0))
+                kv_b.append(torch.cat([c.key.bias, c.value.bias], 0))
+            layers.append(d)
+        pack = {
+            "layers": layers,
+            "w_kv_all": torch.cat(kv_w, 0).detach().to(bf).contiguous() if kv_w else None,
+            "b_kv_all": torch.cat(kv_b, 0).detach().float().contiguous() if kv_b else None,
+            "emb_g": f32(self.embeddings.LayerNorm.weight), "emb_b": f32(self.embeddings.LayerNorm.bias),
+        }
+        self._pack, self._pack_key = pack, key
+        return pack
+
+    # -------------------------------------------------------------------------------------- forward
+    def encode(self, query_embeddings: torch.Tensor, encoder_hidden_states: torch.Tensor,
+               encoder_attention_mask: Optional[torch.Tensor], out_dtype: torch.dtype = torch.float32,
+               prelayernorm_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+        """query_embeddings [1, Q, H] (learned tokens, fp32); encoder_hidden_states [B, S, E] (bf16 or
+        fp32); encoder_attention_mask [B, S] (1 attend / 0 masked) or None.  Returns last_hidden_state
+        [B, Q, H] in `out_dtype` (models/qformer.py:957)."""
+        cfg = self.config
+        if not encoder_hidden_states.is_cuda:
+            raise RuntimeError("unirec_b200: encoder_hidden_states must be a CUDA tensor (no CPU fallback)")
+        if encoder_attention_mask is not None and encoder_attention_mask.dim() != 2:
+            raise ValueError("Wrong shape for encoder_attention_mask (shape {})".format(
+                tuple(encoder_attention_mask.shape)))
+        B, S, E = encoder_hidden_states.shape
+        H, heads = cfg.hidden_size, cfg.num_attention_heads
+        Q = query_embeddings.shape[1]
+        if E != cfg.encoder_width:
+            raise ValueError(f"encoder width {E} != config.encoder_width {cfg.encoder_width}")
+        pk = self.packed()
+
+        enc = ops.cast_bf16(encoder_hidden_states.contiguous()).view(B * S, E)
+        mask = None
+        if encoder_attention_mask is not None:
+            mask = encoder_attention_mask.to(device=enc.device, dtype=torch.float32).contiguous()
+        # cross-attention K/V of every cross layer in one GEMM (the encoder input is layer-invariant)
+        kv_all = ops.linear(enc, pk["w_kv_all"], pk["b_kv_all"]) if pk["w_kv_all"] is not None else None
+
+        # BertEmbeddings query-only branch: LayerNorm of the learned tokens, batch-invariant -> broadcast
+        q0 = query_embeddings.detach().reshape(Q, H).float().contiguous()
+        h = ops.layernorm(q0, pk["emb_g"], pk["emb_b"], cfg.layer_norm_eps, rows=B * Q, in_row_mod=Q)
+
+        nl = len(pk["layers"])
+        for li, L in enumerate(pk["layers"]):
+            last = li == nl - 1
+            qkv = ops.linear(h, L["w_qkv"], L["b_qkv"])
+            ctx = ops.attention(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], batch=B, num_heads=heads, nq=Q, nk=Q)
+            pre = ops.linear(ctx, L["w_o"], L["b_o"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=h,
+                             out_dtype=prelayernorm_dtype)
+            h = ops.layernorm(pre, L["ln1_g"], L["ln1_b"], cfg.layer_norm_eps)
+            if L["cross"]:
+                qc = ops.linear(h, L["w_qc"], L["b_qc"])
+                off = L["kv_slot"] * 2 * H
+                ctx = ops.attention(qc, kv_all[:, off:off + H], kv_all[:, off + H:off + 2 * H], batch=B,
+                                    num_heads=heads, nq=Q, nk=S, key_mask=mask)
+                pre = ops.linear(ctx, L["w_oc"], L["b_oc"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=h,
+                                 out_dtype=prelayernorm_dtype)
+                h = ops.layernorm(pre, L["ln2_g"], L["ln2_b"], cfg.layer_norm_eps)
+            inter = ops.linear(h, L["w_1"], L["b_1"], epilogue=ops.EPI_BIAS_GELU)
+            pre = ops.linear(inter, L["w_2"], L["b_2"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=h,
+                             out_dtype=prelayernorm_dtype)
+            h = ops.layernorm(pre, L["ln3_g"], L["ln3_b"], cfg.layer_norm_eps,
+                              out_dtype=out_dtype if last else torch.bfloat16)
+        return h.view(B, Q, H)
+
+
+def _check_inference_mode(module: nn.Module, dropout: float):
+    if module.training and dropout > 0.0:
+        raise NotImplementedError(
+            "unirec_b200: the CUDA forward implements eval-mode semantics (dropout = identity); call .eval() "
+            "or construct with dropout=0.0.  Train-mode dropout and the backward kernels are not built yet.")
+
+
+class QFormerForItemRepresentation(nn.Module):
+    """Item Q-Former (reference: models/qformer_utils.py:16-60)."""
+
+    def __init__(self, hidden_size: int = 1024, num_hidden_layers: int = 12, num_attention_heads: int = 16,
+                 intermediate_size: int = 4096, num_query_tokens: int = 32, field_embedding_dim: int = 1024,
+                 num_fields: int = None, dropout: float = 0.2):
+        super().__init__()
+        if num_fields is None:
+            raise ValueError("num_fields must be provided")
+        self.config = _bert_config(
+            hidden_size=hidden_size, num_hidden_layers=num_hidden_layers, num_attention_heads=num_attention_heads,
+            intermediate_size=intermediate_size, hidden_dropout_prob=dropout, attention_probs_dropout_prob=dropout,
+            add_cross_attention=True, query_length=num_query_tokens, encoder_width=field_embedding_dim,
+            cross_attention_freq=2)
+        self.num_query_tokens = num_query_tokens
+        self.query_embeddings = nn.Parameter(torch.randn(1, num_query_tokens, hidden_size))
+        self.qformer = QFormerBackbone(self.config)
+        self.item_representation_head = nn.Linear(hidden_size, field_embedding_dim)
+        self.reconstruction_head = nn.Linear(hidden_size, field_embedding_dim)
+        self.field_projection = nn.Linear(num_query_tokens, num_fields)
+        self.output_dtype = torch.float32          # the reference returns fp32 tensors
+        self.prelayernorm_dtype = torch.float32
+        self._head_pack = None
+        self._head_key = None
+
+    def _heads(self):
+        ps = [self.item_representation_head.weight, self.item_representation_head.bias,
+              self.reconstruction_head.weight, self.reconstruction_head.bias,
+              self.field_projection.weight, self.field_projection.bias]
+        key = (ps[0].device, tuple(p._version for p in ps), ps[0].data_ptr())
+        if self._head_pack is None or self._head_key != key:
+            self._head_pack = {
+                "w_rep": ps[0].detach().to(torch.bfloat16).contiguous(), "b_rep": ps[1].detach().float().contiguous(),
+                "w_rec": ps[2].detach().to(torch.bfloat16).contiguous(), "b_rec": ps[3].detach().float().contiguous(),
+                "w_fp": ps[4].detach().float().contiguous(), "b_fp": ps[5].detach().float().contiguous(),
+            }
+            self._head_key = key
+        return self._head_pack
+
+    @torch.no_grad()
+    def encode_query_tokens(self, field_embeddings: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+                            out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+        """query_outputs only ([B, Q, H]); what batched item-token generation needs
+        (data_processing/qformer_inference.py:160-163)."""
+        _check_inference_mode(self, self.config.hidden_dropout_prob)
+        return self.qformer.encode(self.query_embeddings, field_embeddings, attention_mask, out_dtype,
+                                   self.prelayernorm_dtype)
+
+    @torch.no_grad()
+    def forward(self, field_embeddings: torch.Tensor, attention_mask: torch.Tensor = None) -> Dict[str, torch.Tensor]:
+        _check_inference_mode(self, self.config.hidden_dropout_prob)
+        od = self.output_dtype
+        query_outputs = self.qformer.encode(self.query_embeddings, field_embeddings, attention_mask, od,
+                                            self.prelayernorm_dtype)
+        hp = self._heads()
+        qo = ops.cast_bf16(query_outputs)
+        item_representation = ops.linear(ops.mean_tokens(qo), hp["w_rep"], hp["b_rep"], out_dtype=od)
+        rec = ops.linear(qo, hp["w_rec"], hp["b_rec"])
+        reconstructed_fields = ops.field_projection(rec, hp["w_fp"], hp["b_fp"], out_dtype=od)
+        return {"query_outputs": query_outputs, "item_representation": item_representation,
+                "reconstructed_fields": reconstructed_fields}
+
+
+class UserQFormer(nn.Module):
+    """User Q-Former (reference: training/user_qformer_training.py:17-68)."""
+
+    def __init__(self, hidden_size: int = 1024, num_hidden_layers: int = 4, num_attention_heads: int = 16,
+                 intermediate_size: int = 4096, num_query_tokens: int = 64, input_embedding_dim: int = 1024,
+                 num_item_tokens_to_predict: int = 32, dropout: float = 0.1):
+        super().__init__()
+        self.config = _bert_config(
+            hidden_size=hidden_size, num_hidden_layers=num_hidden_layers, num_attention_heads=num_attention_heads,
+            intermediate_size=intermediate_size, hidden_dropout_prob=dropout, attention_probs_dropout_prob=dropout,
+            add_cross_attention=True, query_length=num_query_tokens, encoder_width=input_embedding_dim,
+            cross_attention_freq=1)
+        self.num_query_tokens = num_query_tokens
+        self.query_embeddings = nn.Parameter(torch.randn(1, num_query_tokens, hidden_size))
+        self.qformer = QFormerBackbone(self.config)
+        self.prediction_head = nn.Sequential(
+            nn.Linear(hidden_size, hidden_size),
+            nn.GELU(),
+            nn.LayerNorm(hidden_size),
+            nn.Linear(hidden_size, num_item_tokens_to_predict * input_embedding_dim))
+        self.num_item_tokens_to_predict = num_item_tokens_to_predict
+        self.input_embedding_dim = input_embedding_dim
+        self.output_dtype = torch.float32
+        self.prelayernorm_dtype = torch.float32
+        # cross-attention K/V for all layers are materialised per chunk of users:
+        # chunk * S * layers * 2 * H * 2 bytes (6.7 GB for 256 users x 1600 keys x 4 layers)
+        self.max_kv_bytes = 8 << 30
+        self._head_pack = None
+        self._head_key = None
+
+    def _heads(self):
+        ph = self.prediction_head
+        ps = [ph[0].weight, ph[0].bias, ph[2].weight, ph[2].bias, ph[3].weight, ph[3].bias]
+        key = (ps[0].device, tuple(p._version for p in ps), ps[0].data_ptr())
+        if self._head_pack is None or self._head_key != key:
+            self._head_pack = {
+                "w0": ps[0].detach().to(torch.bfloat16).contiguous(), "b0": ps[1].detach().float().contiguous(),
+                "g": ps[2].detach().float().contiguous(), "b": ps[3].detach().float().contiguous(),
+                "w3": ps[4].detach().to(torch.bfloat16).contiguous(), "b3": ps[5].detach().float().contiguous(),
+            }
+            self._head_key = key
+        return self._head_pack
+
+    def _chunk_users(self, S: int) -> int:
+        cfg = self.config
+        per_user = S * cfg.num_hidden_layers * 2 * cfg.hidden_size * 2
+        return max(1, int(self.max_kv_bytes // max(per_user, 1)))
+
+    @torch.no_grad()
+    def encode_queries(self, user_sequence_tokens: torch.Tensor, attention_mask: Optional[torch.Tensor],
+                       out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+        """last_hidden_state [B, num_query_tokens, H] of the user Q-Former."""
+        _check_inference_mode(self, self.config.hidden_dropout_prob)
+        B, S, _ = user_sequence_tokens.shape
+        step = self._chunk_users(S)
+        outs = []
+        for lo in range(0, B, step):
+            m = None if attention_mask is None else attention_mask[lo:lo + step]
+            outs.append(self.qformer.encode(self.query_embeddings, user_sequence_tokens[lo:lo + step], m, out_dtype,
+                                            self.prelayernorm_dtype))
+        return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+
+    @torch.no_grad()
+    def predict_from_queries(self, hidden: torch.Tensor, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+        """mean-pool + prediction head (training/user_qformer_training.py:60-66)."""
+        hp = self._heads()
+        od = self.output_dtype if out_dtype is None else out_dtype
+        B = hidden.shape[0]
+        rep = ops.mean_tokens(ops.cast_bf16(hidden))
+        g = ops.linear(rep, hp["w0"], hp["b0"], epilogue=ops.EPI_BIAS_GELU)
+        g = ops.layernorm(g, hp["g"], hp["b"], self.prediction_head[2].eps)
+        flat = ops.linear(g, hp["w3"], hp["b3"], out_dtype=od)
+        return flat.view(B, self.num_item_tokens_to_predict, self.input_embedding_dim)
+
+    @torch.no_grad()
+    def forward(self, user_sequence_tokens: torch.Tensor, attention_mask: torch.Tensor) -> torch.Tensor:
+        hidden = self.encode_queries(user_sequence_tokens, attention_mask, torch.bfloat16)
+        return self.predict_from_queries(hidden)

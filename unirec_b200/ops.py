@@ -14,6 +14,45 @@ from . import _lib
 
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2
 
+# Optional per-launch device timing (bench.py's roofline): when a list is installed, every wrapped
+# launch is bracketed by CUDA events on the launching stream and (kind, work, start, end) is appended;
+# `work` is the launch's ALGORITHMIC flops (GEMM, scoring) or bytes (attention).
+_timing = None
+
+
+def start_timing():
+    global _timing
+    _timing = []
+
+
+def stop_timing():
+    """Returns {kind: (launches, total_work, total_ms)}; call after torch.cuda.synchronize()."""
+    global _timing
+    rec, _timing = _timing or [], None
+    out = {}
+    for kind, work, e0, e1 in rec:
+        n, w, ms = out.get(kind, (0, 0.0, 0.0))
+        out[kind] = (n + 1, w + work, ms + e0.elapsed_time(e1))
+    return out
+
+
+class _Timed:
+    def __init__(self, kind, work):
+        self.kind, self.work = kind, work
+
+    def __enter__(self):
+        if _timing is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _timing is not None:
+            self.e1.record()
+            _timing.append((self.kind, float(self.work), self.e0, self.e1))
+        return False
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -67,10 +106,11 @@ def linear(a: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         _, _, ldr = _rows2d(residual, "linear.residual")
     if out.dtype not in (torch.bfloat16, torch.float32):
         raise RuntimeError("linear: out must be bf16 or fp32")
-    rc = _lib.load().unirec_linear_bf16(a.data_ptr(), lda, weight.data_ptr(), weight.stride(0), _ptr(bias),
-                                        _ptr(residual), ldr, res_row_mod, out.data_ptr(), ldo,
-                                        1 if out.dtype == torch.float32 else 0, M, N, K, epilogue, block_n, max_ctas,
-                                        _stream())
+    with _Timed("gemm", 2.0 * M * N * K):
+        rc = _lib.load().unirec_linear_bf16(a.data_ptr(), lda, weight.data_ptr(), weight.stride(0), _ptr(bias),
+                                            _ptr(residual), ldr, res_row_mod, out.data_ptr(), ldo,
+                                            1 if out.dtype == torch.float32 else 0, M, N, K, epilogue, block_n,
+                                            max_ctas, _stream())
     _lib.check(rc, "unirec_linear_bf16")
     return out
 
@@ -121,9 +161,11 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, batch: int, 
         _req(key_mask, torch.float32, "attention.key_mask")
         if tuple(key_mask.shape) != (batch, nk) or not key_mask.is_contiguous():
             raise RuntimeError("attention: key_mask must be contiguous [batch, nk]")
-    rc = _lib.load().unirec_attention(q.data_ptr(), q.stride(0), 0 if q_broadcast else nq, k.data_ptr(), k.stride(0),
-                                      v.data_ptr(), v.stride(0), nk, _ptr(key_mask), out.data_ptr(), out.stride(0),
-                                      batch, num_heads, nq, nk, 64, 0.125, _stream())
+    # algorithmic bytes: Q, K, V read once + context written once (bf16)
+    with _Timed("attention", 2.0 * hd * batch * ((1 if q_broadcast else 1) * nq + 2 * nk + nq)):
+        rc = _lib.load().unirec_attention(q.data_ptr(), q.stride(0), 0 if q_broadcast else nq, k.data_ptr(),
+                                          k.stride(0), v.data_ptr(), v.stride(0), nk, _ptr(key_mask), out.data_ptr(),
+                                          out.stride(0), batch, num_heads, nq, nk, 64, 0.125, _stream())
     _lib.check(rc, "unirec_attention")
     return out
 
@@ -224,9 +266,10 @@ def score_topk(users: torch.Tensor, cands: torch.Tensor, k: int, *, user_inv: Op
     ws = torch.empty(max(ws_bytes, 16), device=users.device, dtype=torch.uint8)
     scores = torch.empty(B, k, device=users.device, dtype=torch.float32)
     idx = torch.empty(B, k, device=users.device, dtype=torch.int64)
-    rc = lib.unirec_score_topk(users.data_ptr(), users.stride(0), user_inv.data_ptr(), cands.data_ptr(),
-                               cands.stride(0), cand_inv.data_ptr(), B, N, D, k, index_base, scores.data_ptr(),
-                               idx.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
+    with _Timed("score_topk", 2.0 * B * N * D):
+        rc = lib.unirec_score_topk(users.data_ptr(), users.stride(0), user_inv.data_ptr(), cands.data_ptr(),
+                                   cands.stride(0), cand_inv.data_ptr(), B, N, D, k, index_base, scores.data_ptr(),
+                                   idx.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
     _lib.check(rc, "unirec_score_topk")
     return scores, idx
 

@@ -1,0 +1,148 @@
+"""Host-side drivers of the nested encode-and-rank path.
+
+  * generate_item_tokens  - batched item-query-token generation, item-range sharded (config 3;
+                            intent of data_processing/generate_all_item_embeddings.py:238-267, working
+                            equivalent data_processing/qformer_inference.py:143-168): no collective.
+  * NestedRanker          - user-sequence build (models/user_sequence_encoder.py:128-140) -> UserQFormer
+                            -> pooled scoring vector -> cosine top-k over a row-sharded candidate pool with
+                            an NCCL all-gather + merge of the per-GPU top-k lists (config 5).
+One process per GPU; torch.distributed is used for the two all-gathers only.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple, Union
+
+import torch
+
+from . import ops
+from .modules import QFormerForItemRepresentation, UserQFormer
+
+
+def shard_range(n: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous range [lo, hi) of rank `rank` when n rows are split over world_size ranks
+    (ranges differ by at most one row)."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError(f"bad rank/world_size {rank}/{world_size}")
+    base, rem = divmod(n, world_size)
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi
+
+
+FieldSource = Union[torch.Tensor, Callable[[int, int], Tuple[torch.Tensor, Optional[torch.Tensor]]]]
+
+
+@torch.no_grad()
+def generate_item_tokens(model: QFormerForItemRepresentation, fields: FieldSource, num_items: Optional[int] = None,
+                         mask: Optional[torch.Tensor] = None, *, batch_size: int = 4096, rank: int = 0,
+                         world_size: int = 1, tokens_out: Optional[torch.Tensor] = None,
+                         pooled_out: Optional[torch.Tensor] = None, keep_tokens: bool = True):
+    """Run the item Q-Former over this rank's item range in chunks of `batch_size`.
+
+    fields: a [N, F, E] tensor (CUDA) or a callable (lo, hi) -> (fields[hi-lo, F, E], mask or None)
+    producing the chunk on the device.  Returns (tokens bf16 [n_local, Q, H] or None, pooled bf16
+    [n_local, H], (lo, hi)); `pooled` = tokens.mean(dim=1), the candidate scoring vector.
+    """
+    if isinstance(fields, torch.Tensor):
+        n_total = fields.shape[0]
+    else:
+        if num_items is None:
+            raise ValueError("num_items is required when fields is a callable")
+        n_total = num_items
+    lo, hi = shard_range(n_total, rank, world_size)
+    n_local = hi - lo
+    Q, H = model.num_query_tokens, model.config.hidden_size
+    dev = next(model.parameters()).device
+    if keep_tokens and tokens_out is None:
+        tokens_out = torch.empty(n_local, Q, H, device=dev, dtype=torch.bfloat16)
+    if pooled_out is None:
+        pooled_out = torch.empty(n_local, H, device=dev, dtype=torch.bfloat16)
+    for c0 in range(lo, hi, batch_size):
+        c1 = min(c0 + batch_size, hi)
+        if isinstance(fields, torch.Tensor):
+            x, m = fields[c0:c1], (None if mask is None else mask[c0:c1])
+        else:
+            x, m = fields(c0, c1)
+        tok = model.encode_query_tokens(x, m, out_dtype=torch.bfloat16)
+        if keep_tokens:
+            tokens_out[c0 - lo:c1 - lo].copy_(tok)
+        pooled_out[c0 - lo:c1 - lo].copy_(ops.mean_tokens(tok))
+    return (tokens_out if keep_tokens else None), pooled_out, (lo, hi)
+
+
+def gather_lists(scores: torch.Tensor, idx: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """all-gather per-rank top-k lists [B, k] -> [G, B, k] (works on NCCL and gloo)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return scores.unsqueeze(0), idx.unsqueeze(0)
+    g = dist.get_world_size(group)
+    b = scores.shape[0]
+    # concatenated-along-dim-0 output layout is the one every backend (NCCL, gloo) accepts
+    s_all = torch.empty((g * b,) + tuple(scores.shape[1:]), dtype=scores.dtype, device=scores.device)
+    i_all = torch.empty((g * b,) + tuple(idx.shape[1:]), dtype=idx.dtype, device=idx.device)
+    dist.all_gather_into_tensor(s_all, scores.contiguous(), group=group)
+    dist.all_gather_into_tensor(i_all, idx.contiguous(), group=group)
+    return s_all.view((g,) + tuple(scores.shape)), i_all.view((g,) + tuple(idx.shape))
+
+
+def gather_rows(x: torch.Tensor, group=None) -> torch.Tensor:
+    """all-gather equal-sized row blocks [b, D] -> [G*b, D]."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return x
+    g = dist.get_world_size(group)
+    out = torch.empty((g * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+    return out
+
+
+class NestedRanker:
+    """item-token table -> user sequence -> UserQFormer -> pooled vector -> top-k over the candidate pool.
+
+    item_tokens : bf16 [N_items, Q, D]  item query-token table used for history gathering (replicated)
+    candidates  : bf16 [N_local, D]     this rank's rows of the pooled candidate table
+    index_base  : global row index of candidates[0]
+    """
+
+    def __init__(self, user_model: UserQFormer, item_tokens: torch.Tensor, candidates: torch.Tensor, k: int = 100,
+                 index_base: int = 0, group=None):
+        self.user_model = user_model
+        self.item_tokens = item_tokens
+        self.candidates = candidates
+        self.cand_inv = ops.inv_l2_norm(candidates)   # candidate norms are computed once, not per query batch
+        self.k = k
+        self.index_base = index_base
+        self.group = group
+
+    @torch.no_grad()
+    def encode_users(self, history: torch.Tensor, lengths: torch.Tensor,
+                     context: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """history int64 [B, Hmax], lengths int32 [B] -> pooled predicted-item vector bf16 [B, D]."""
+        um = self.user_model
+        B = history.shape[0]
+        S = history.shape[1] * self.item_tokens.shape[1]
+        step = um._chunk_users(S)
+        outs = []
+        for lo in range(0, B, step):
+            hi = min(lo + step, B)
+            seq, mask = ops.build_user_sequence(self.item_tokens, history[lo:hi].contiguous(),
+                                                lengths[lo:hi].contiguous(),
+                                                None if context is None else context[lo:hi])
+            hidden = um.encode_queries(seq, mask, torch.bfloat16)
+            pred = um.predict_from_queries(hidden, out_dtype=torch.bfloat16)     # [b, T, D]
+            outs.append(ops.mean_tokens(pred))                                   # scoring vector
+        return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+
+    @torch.no_grad()
+    def rank(self, user_vectors: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """user_vectors bf16 [B_local, D] (this rank's users).  Returns (scores fp32 [B, k], idx int64
+        [B, k]) for ALL users of the group, identical on every rank."""
+        u_all = gather_rows(user_vectors, self.group)
+        s, i = ops.score_topk(u_all, self.candidates, self.k, cand_inv=self.cand_inv, index_base=self.index_base)
+        s_all, i_all = gather_lists(s, i, self.group)
+        if s_all.shape[0] == 1:
+            return s, i
+        return ops.topk_merge(s_all, i_all)
+
+    def __call__(self, history, lengths, context=None):
+        return self.rank(self.encode_users(history, lengths, context))
