@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--top-k", type=int, default=100)
     ap.add_argument("--cpu-users", type=int, default=8, help="users in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-range", default="", choices=["", "items", "users"],
+                    help="bracket that timed region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     return ap.parse_args()
 
 
@@ -236,12 +238,16 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     l0 = _lib.launch_count()
     ops.start_timing()
+    if args.profile_range == "items":
+        torch.cuda.profiler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for ci in range(w_items, len(chunks)):
         encode_chunk(ci)
     e1.record()
     barrier()
+    if args.profile_range == "items":
+        torch.cuda.profiler.stop()
     item_ms = max_over_ranks(e0.elapsed_time(e1))
     item_stats = ops.stop_timing()
     items_timed_local = sum(c1 - c0 for c0, c1 in chunks[w_items:])
@@ -271,12 +277,16 @@ def run_ours(args, rank, world, local_rank):
         sampler.start()
     l0 = _lib.launch_count()
     ops.start_timing()
+    if args.profile_range == "users":
+        torch.cuda.profiler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for s in range(args.steps):
         scores, idx = ranker(hist_batches[s % 3], lengths)
     e1.record()
     barrier()
+    if args.profile_range == "users":
+        torch.cuda.profiler.stop()
     user_ms = max_over_ranks(e0.elapsed_time(e1))
     user_stats = ops.stop_timing()
     clocks = sampler.stop() if rank == 0 else None

@@ -13,9 +13,15 @@ ITEM_CASES = {
     # field masked (all-masked => uniform attention)
     "full": dict(model=_ITEM_FULL, heads=16, seed=0, attn_std=0.02,
                  input=dict(batch=3, num_fields=14, dim=1024, seed=1, presence=0.6, all_masked_row=2)),
-    # sharper attention (larger q/k weights) so that softmax is far from uniform
+    # sharper attention (larger q/k weights) so that softmax is far from uniform; over 12 layers a bf16
+    # rounding that flips an attention winner is amplified, so this case is bounded by 1.5x the error
+    # of the bf16 precision model on the same input (oracle/bf16_precision_model.py)
     "sharp": dict(model=_ITEM_FULL, heads=16, seed=3, attn_std=0.08,
                   input=dict(batch=2, num_fields=14, dim=1024, seed=4, presence=0.8)),
+    # the same sharp weights, 2 layers (one with cross-attention): errors cannot compound, so the
+    # standard tolerance applies even though softmax is near one-hot
+    "sharp2": dict(model=dict(_ITEM_FULL, layers=2), heads=16, seed=3, attn_std=0.08,
+                   input=dict(batch=2, num_fields=14, dim=1024, seed=4, presence=0.8)),
     # small generic-dims model: 4 heads x 64, 6 fields
     "small": dict(model=_ITEM_SMALL, heads=4, seed=5, attn_std=0.1,
                   input=dict(batch=5, num_fields=6, dim=256, seed=6, clip_field=2, presence=0.7,

@@ -65,3 +65,21 @@ def test_all_masked_item_is_uniform_attention():
     out_open = O.item_qformer_forward(sd, x, torch.ones(1, 6), num_heads=4)["query_outputs"]
     assert torch.isfinite(out_masked).all()
     assert (out_masked - out_open).abs().max() <= 1e-5
+
+
+def test_bf16_precision_model_brackets_the_tolerances():
+    """The CPU precision model (bf16 rounding at the kernels' storage points) meets the standard bar on
+    the reference-like and 2-layer sharp cases, and shows that the 12-layer sharp case is chaotic in
+    bf16 (which is why tests/test_modules_gpu.py bounds that case relative to this model)."""
+    from oracle import bf16_precision_model as P
+    stats = {}
+    for name in ("sharp2", "small", "sharp"):
+        c = ITEM_CASES[name]
+        sd = synth.item_qformer_state_dict(**c["model"], seed=c["seed"], attn_std=c["attn_std"])
+        x, mask = synth.item_fields(**c["input"])
+        g = np.load(os.path.join(GOLDEN, f"item_{name}.npz"))["query_outputs"]
+        stats[name] = P.error_stats(P.item_query_outputs(sd, x, mask, num_heads=c["heads"]), torch.as_tensor(g))
+    for name in ("sharp2", "small"):
+        mx, mean, cos = stats[name]
+        assert mx <= 0.15 and mean <= 0.02 and cos >= 0.9995, (name, stats[name])
+    assert stats["sharp"][0] > 0.15  # documents the amplification; not a bound on the kernels

@@ -1,0 +1,44 @@
+#!/bin/bash
+# One gpurun call: GPU tests, full bench, ncu launch lists and full captures of the top kernels.
+# Usage (from the repo root on the GPU box): bash tools/gpu_round.sh [tests] [bench] [launches] [ncu]
+set -u
+mkdir -p gpurun_out
+what="${*:-tests bench launches ncu}"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
+for w in $what; do
+case $w in
+tests)
+  timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+  timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
+  ;;
+bench)
+  timeout 900 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; echo "bench rc=$?" >> gpurun_out/bench_full.err
+  ;;
+launches)
+  # small pool so the run is short; every launch of one timed user step / two item chunks (cold-cache, serialised)
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+      --log-file gpurun_out/launches_users.csv \
+      python bench.py --steps 1 --warmup 1 --pool-items 131072 --users-per-gpu 1024 --no-cpu-baseline --profile-range users \
+      > gpurun_out/launches_users.out 2>&1
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+      --log-file gpurun_out/launches_items.csv \
+      python bench.py --steps 1 --warmup 1 --pool-items 12288 --users-per-gpu 128 --no-cpu-baseline --profile-range items \
+      > gpurun_out/launches_items.out 2>&1
+  ;;
+ncu)
+  for k in gemm_bf16 attention_kernel score_filter topk_select; do
+    timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:$k -c 4 \
+        -f -o gpurun_out/prof_users_$k \
+        python bench.py --steps 1 --warmup 1 --pool-items 131072 --users-per-gpu 1024 --no-cpu-baseline --profile-range users \
+        > gpurun_out/prof_users_$k.out 2>&1
+  done
+  for k in gemm_bf16 attention_kernel; do
+    timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:$k -s 8 -c 6 \
+        -f -o gpurun_out/prof_items_$k \
+        python bench.py --steps 1 --warmup 1 --pool-items 12288 --users-per-gpu 128 --no-cpu-baseline --profile-range items \
+        > gpurun_out/prof_items_$k.out 2>&1
+  done
+  ;;
+esac
+done
+ls -la gpurun_out
