@@ -49,7 +49,9 @@ int64_t unirec_launch_count(void);
  * training/user_qformer_training.py:38-43.  tcgen05/TMEM/TMA kernel.
  * A, W bf16; bias fp32 or NULL; residual bf16 (epilogue 2), residual row = row % res_row_mod when
  * res_row_mod > 0 (batch-invariant residual).  K % 64 == 0, N % 8 == 0.
- * block_n: 0 = auto, 128 or 256.  max_ctas: 0 = one per SM. */
+ * block_n: 0 = auto; 128 or 256 = single-CTA kernel with that tile width; 2 = CTA-pair kernel
+ * (tcgen05 cta_group::2, 256 x 256 tile per SM pair, TMA-store epilogue; needs bf16 out, N % 256 == 0,
+ * res_row_mod == 0).  max_ctas: 0 = one per SM. */
 int unirec_linear_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                        const void* residual, int64_t ldr, int64_t res_row_mod,
                        void* out, int64_t ldo, int out_fp32,

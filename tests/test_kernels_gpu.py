@@ -74,6 +74,51 @@ def test_linear_strided_views_and_many_tiles():
     torch.testing.assert_close(out2.float(), ref, rtol=1e-2, atol=2e-2)
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (128, 256, 128), (300, 512, 1024), (2048, 1024, 1024),
+                                   (1000, 4096, 1024), (777, 1024, 4096), (40000, 1024, 1024), (19, 768, 192)])
+def test_linear_cta_pair_kernel(M, N, K):
+    """tcgen05 cta_group::2 kernel (block_n=2): 256 x 256 tile per SM pair, TMA-store epilogue, residual via TMA.
+    bf16 output: error = fp32 summation order + one bf16 rounding (2^-9 relative)."""
+    from unirec_b200 import ops
+    a = _randn(M, K, seed=21, dtype=torch.bfloat16)
+    w = _randn(N, K, seed=22, scale=0.05, dtype=torch.bfloat16)
+    b = _randn(N, seed=23, scale=0.5)
+    res = _randn(M, N, seed=24, dtype=torch.bfloat16)
+    lin = a.float() @ w.float().t() + b
+    out = ops.linear(a, w, b, block_n=2)
+    torch.testing.assert_close(out.float(), lin, rtol=1e-2, atol=2e-2)
+    out = ops.linear(a, w, None, block_n=2)
+    torch.testing.assert_close(out.float(), lin - b, rtol=1e-2, atol=2e-2)
+    out = ops.linear(a, w, b, epilogue=ops.EPI_BIAS_GELU, block_n=2)
+    torch.testing.assert_close(out.float(), F.gelu(lin), rtol=1e-2, atol=2e-2)
+    out = ops.linear(a, w, b, epilogue=ops.EPI_BIAS_RESIDUAL, residual=res, block_n=2)
+    torch.testing.assert_close(out.float(), lin + res.float(), rtol=1e-2, atol=3e-2)
+    # identical to the single-CTA kernel up to summation order inside the tensor core (same K order: exact)
+    out1 = ops.linear(a, w, b, block_n=256)
+    assert float((ops.linear(a, w, b, block_n=2).float() - out1.float()).abs().max()) <= 2e-2
+
+
+def test_linear_cta_pair_strided_and_few_clusters():
+    from unirec_b200 import ops
+    M, N, K = 20000, 2048, 1024
+    big_a = _randn(M, 2 * K, seed=8, dtype=torch.bfloat16)
+    a = big_a[:, K:]
+    w = _randn(N, K, seed=9, scale=0.05, dtype=torch.bfloat16)
+    res_big = _randn(M, 2 * N, seed=10, dtype=torch.bfloat16)
+    res = res_big[:, N:]
+    big_out = torch.zeros(M, 3 * N, device=_dev(), dtype=torch.bfloat16)
+    ops.linear(a, w, None, out=big_out[:, N:2 * N], block_n=2, epilogue=ops.EPI_BIAS_RESIDUAL, residual=res)
+    ref = a.float() @ w.float().t() + res.float()
+    torch.testing.assert_close(big_out[:, N:2 * N].float(), ref, rtol=1e-2, atol=3e-2)
+    assert float(big_out[:, :N].abs().max()) == 0.0 and float(big_out[:, 2 * N:].abs().max()) == 0.0
+    out2 = ops.linear(a, w, None, block_n=2, max_ctas=6)     # 3 clusters: every pair loops over many tiles
+    torch.testing.assert_close(out2.float(), a.float() @ w.float().t(), rtol=1e-2, atol=2e-2)
+    with pytest.raises(RuntimeError):
+        ops.linear(a, w[:1000], None, block_n=2)             # N % 256 != 0
+    with pytest.raises(RuntimeError):
+        ops.linear(a, w, None, block_n=2, out_dtype=torch.float32)
+
+
 def test_linear_rejects_bad_arguments():
     from unirec_b200 import ops
     a = _randn(64, 100, dtype=torch.bfloat16)  # K not a multiple of 64

@@ -56,7 +56,7 @@ def test_scoring_golden_case():
 
 
 @pytest.mark.parametrize("B,N,k", [(1, 300, 100), (130, 5000, 100), (64, 70001, 100), (300, 40960, 128), (5, 50, 100),
-                                   (17, 4096, 1)])
+                                   (17, 4096, 1), (3, 32768, 100), (2, 32769, 7), (40, 150001, 100)])
 def test_score_topk_random(B, N, k):
     from unirec_b200 import ops
     g = torch.Generator().manual_seed(B * 31 + N)
@@ -82,6 +82,25 @@ def test_score_topk_adversarial_order_and_ties():
     s, i = ops.score_topk(u.to(DEV), C.to(DEV), 100)
     _assert_topk_matches(s, i, u, C, 100)
     assert float(s[0, 0]) == pytest.approx(float(s[0, 99]), abs=TOL)   # all 100 winners are the tied copies
+
+
+def test_score_topk_adversarial_sample():
+    """Large pool (sampled start threshold).  The sampled candidate tiles (every 17th tile of 256 rows for
+    N = 140000) hold only candidates that are bad for user 0, every other tile is good: the sampled threshold
+    is useless for that user, ~all candidates pass the filter and the exact list-compaction path must keep
+    the result right.  User 1 sees the opposite (sample = the best candidates: threshold is the true one)."""
+    from unirec_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    N, D, k = 140000, 64, 100
+    u = torch.randn(3, D, generator=g)
+    C = torch.randn(N, D, generator=g)
+    tile = torch.arange(N) // 256
+    sampled = (tile % 17 == 0) & (tile // 17 < 32)
+    C[sampled] = -u[0] + 0.3 * C[sampled]
+    C[~sampled] = 0.5 * u[0] + C[~sampled]
+    u, C = u.to(torch.bfloat16), C.to(torch.bfloat16)
+    s, i = ops.score_topk(u.to(DEV), C.to(DEV), k)
+    _assert_topk_matches(s, i, u, C, k)
 
 
 def test_topk_merge_matches_global_topk():

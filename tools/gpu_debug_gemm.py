@@ -45,27 +45,26 @@ M, N, K = 131072, 1024, 1024
 a = torch.randn(M, K, device=dev).to(torch.bfloat16)
 w = (torch.randn(N, K, device=dev) * 0.05).to(torch.bfloat16)
 b = torch.randn(N, device=dev)
-for bn in (128, 256):
-    for (n, k, epi) in [(1024, 1024, 0), (4096, 1024, 1), (3072, 1024, 0)]:
+for bn in (128, 256, 2):
+    for (n, k, epi) in [(1024, 1024, 0), (4096, 1024, 1), (3072, 1024, 0), (1024, 1024, 2), (1024, 4096, 2), (8192, 1024, 0)]:
         w = (torch.randn(n, k, device=dev) * 0.05).to(torch.bfloat16)
         b = torch.randn(n, device=dev)
         out = torch.empty(M, n, device=dev, dtype=torch.bfloat16)
+        a = torch.randn(M, k, device=dev).to(torch.bfloat16)
+        res = torch.randn(M, n, device=dev).to(torch.bfloat16) if epi == 2 else None
         for _ in range(3):
-            ops.linear(a, w, b, block_n=bn, out=out, epilogue=epi)
+            ops.linear(a, w, b, block_n=bn, out=out, epilogue=epi, residual=res)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(10):
-            ops.linear(a, w, b, block_n=bn, out=out, epilogue=epi)
+            ops.linear(a, w, b, block_n=bn, out=out, epilogue=epi, residual=res)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         print(f"timing M={M} N={n} K={k} bn={bn} epi={epi}: {ms:.3f} ms  {2*M*n*k/ms/1e9:.1f} TFLOP/s", flush=True)
-        t0 = time.time()
-        for _ in range(10):
-            torch.matmul(a, w.t())
-        torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a = torch.randn(M, 1024, device=dev).to(torch.bfloat16)
 w = (torch.randn(4096, 1024, device=dev) * 0.05).to(torch.bfloat16)
 for _ in range(3): torch.matmul(a, w.t())
 e0.record()

@@ -1,0 +1,420 @@
+// Projection GEMM, CTA-pair version (sm_100a):
+//     out[M,N] (bf16) = epilogue( A[M,K] (bf16, row-major) x W[N,K]^T (bf16, row-major = nn.Linear.weight) )
+//
+// A thread-block cluster of two CTAs (one SM pair) owns a 256 x 256 output tile.  Each CTA stages ITS 128
+// rows of A and ITS 128 rows of W per 64-wide K block (TMA, 128-byte swizzle, 5-stage ring); the leader CTA
+// issues tcgen05.mma.cta_group::2 (UMMA 256 x 256 x 16), which reads A/W from both CTAs' shared memory and
+// writes each CTA's 128 accumulator rows into that CTA's TMEM - so every operand byte is fetched from L2 once
+// per pair and read from shared memory once per pair (2/3 of the L2->SM traffic and half of the W smem reads
+// of the single-CTA 128 x 256 kernel in gemm_tcgen05.cu).
+//
+// The epilogue never touches global memory with per-thread loads/stores: the residual tile is brought into
+// shared memory by TMA while the tile's MMAs run, the epilogue warps do tcgen05.ld -> bias / erf-GELU /
+// +residual -> bf16 IN PLACE in that shared tile, and a dedicated warp writes it back with TMA bulk stores
+// (full 128-byte lines, asynchronous).  The C tile is handled as four 64-column slabs so that loads, epilogue
+// math and stores of neighbouring slabs/tiles overlap.
+//
+// Warp roles per CTA (384 threads):
+//     warp 0      TMA producer (A and W k-blocks; signals the LEADER's full barrier)
+//     warp 1      UMMA issuer (leader CTA only; tcgen05.commit multicast releases both CTAs' smem slots)
+//     warp 2      TMEM allocator (cta_group::2, both CTAs)
+//     warp 3      C mover: TMA store of finished slabs, TMA load of the next tile's residual slabs
+//     warps 4-11  epilogue (TMEM lane quadrant = warp % 4, column half = (warp - 4) / 4)
+//
+// Replaces the same reference lines as gemm_tcgen05.cu (every nn.Linear of the path: models/qformer.py:185-198,
+// :286, :359-360, :372; heads models/qformer_utils.py:50,53, training/user_qformer_training.py:38-43).
+#include "common.cuh"
+#include "umma_pipe.cuh"
+
+namespace unirec {
+
+enum : int { G2_EPI_BIAS = 0, G2_EPI_BIAS_GELU = 1, G2_EPI_BIAS_RESIDUAL = 2 };
+
+constexpr int G2_TILE_M = 256;              // per cluster; 128 per CTA
+constexpr int G2_TILE_N = 256;
+constexpr int G2_BLOCK_K = 64;
+constexpr int G2_STAGES = 5;
+constexpr int G2_A_BYTES = 128 * G2_BLOCK_K * 2;          // this CTA's 128 rows of A
+constexpr int G2_B_BYTES = 128 * G2_BLOCK_K * 2;          // this CTA's 128 rows of W
+constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;   // 32 KB
+constexpr int G2_SLABS = 4;                               // 64-column slabs of this CTA's 128 x 256 C tile
+constexpr int G2_SLAB_BYTES = 128 * 64 * 2;               // 16 KB
+constexpr int G2_THREADS = 384;
+constexpr int G2_EPI_WARPS = 8;
+constexpr int G2_BARRIER_BYTES = 512;
+constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + G2_SLABS * G2_SLAB_BYTES + 1024 + G2_BARRIER_BYTES;
+constexpr int G2_TMEM_COLS = 512;                         // two 256-column accumulator stages
+static_assert(G2_SMEM_BYTES <= 232448, "shared memory budget exceeded");
+
+struct Gemm2Params {
+    int M, N, K;
+    const float* bias;      // [N] fp32 or nullptr
+    int num_m_blocks, num_n_blocks;
+};
+
+// ---- PTX specific to the CTA-pair pipeline -------------------------------------------------------
+UNIREC_DEVICE void tma_load_2d_cg2(const CUtensorMap* map, uint32_t bar_cluster_addr, void* smem_dst, int32_t c0,
+                                   int32_t c1, uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1),
+        "l"(hint)
+        : "memory");
+}
+UNIREC_DEVICE void tma_store_2d(const CUtensorMap* map, const void* smem_src, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+UNIREC_DEVICE void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+UNIREC_DEVICE void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+UNIREC_DEVICE void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+UNIREC_DEVICE void tmem_alloc_cg2(uint32_t* smem_result, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+                 "r"(ncols)
+                 : "memory");
+}
+UNIREC_DEVICE void tmem_relinquish_cg2() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+UNIREC_DEVICE void tmem_dealloc_cg2(uint32_t tmem_addr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_addr), "r"(ncols) : "memory");
+}
+UNIREC_DEVICE void umma_bf16_ss_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                    uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Arrive (once all previously issued MMAs of this thread completed) on the barrier at the same shared-memory
+// offset in every CTA of cta_mask.
+UNIREC_DEVICE void umma_commit_cg2_mc(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask)
+                 : "memory");
+}
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                     const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
+                     const Gemm2Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = cluster_ctarank();
+    const bool is_leader = cta_rank == 0;
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + G2_STAGES * G2_A_BYTES;
+    uint8_t* smem_c = smem + G2_STAGES * G2_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + G2_SLABS * G2_SLAB_BYTES);
+    uint64_t* full_bar = bars;                                   // [STAGES]  used in the leader
+    uint64_t* empty_bar = bars + G2_STAGES;                      // [STAGES]  one per CTA
+    uint64_t* tmem_full_bar = bars + 2 * G2_STAGES;              // [2]       one per CTA
+    uint64_t* tmem_empty_bar = bars + 2 * G2_STAGES + 2;         // [2]       used in the leader
+    uint64_t* slab_ready_bar = bars + 2 * G2_STAGES + 4;         // [SLABS]   buffer free / residual landed
+    uint64_t* slab_written_bar = bars + 2 * G2_STAGES + 4 + G2_SLABS;   // [SLABS] epilogue done with the slab
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * G2_STAGES + 4 + 2 * G2_SLABS);
+
+    if (warp_idx == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        tma_prefetch_desc(&tmap_out);
+        if constexpr (MODE == G2_EPI_BIAS_RESIDUAL) tma_prefetch_desc(&tmap_res);
+    }
+    if (warp_idx == 1 && lane == 0) {
+        for (int i = 0; i < G2_STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full_bar[i], 1);
+            mbar_init(&tmem_empty_bar[i], 2 * G2_EPI_WARPS);   // one arrival per epilogue warp of both CTAs
+        }
+        for (int i = 0; i < G2_SLABS; ++i) {
+            mbar_init(&slab_ready_bar[i], 1);
+            mbar_init(&slab_written_bar[i], G2_EPI_WARPS / 2);  // the four warps that share the slab's column half
+        }
+        fence_mbar_init();
+    }
+    if (warp_idx == 2) {
+        tmem_alloc_cg2(tmem_ptr_smem, G2_TMEM_COLS);
+        tmem_relinquish_cg2();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int num_kb = p.K / G2_BLOCK_K;
+    const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+
+    if (warp_idx == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            const int m_blk = tile / p.num_n_blocks;
+            const int n_blk = tile % p.num_n_blocks;
+            const int m_coord = m_blk * G2_TILE_M + static_cast<int>(cta_rank) * 128;
+            const int n_coord = n_blk * G2_TILE_N + static_cast<int>(cta_rank) * 128;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (lane == 0) {
+                    const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                    if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
+                    tma_load_2d_cg2(&tmap_a, full_leader, smem_a + stage * G2_A_BYTES, kb * G2_BLOCK_K, m_coord,
+                                    kCacheEvictNormal);
+                    tma_load_2d_cg2(&tmap_b, full_leader, smem_b + stage * G2_B_BYTES, kb * G2_BLOCK_K, n_coord,
+                                    kCacheEvictNormal);
+                }
+                __syncwarp();
+                if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ===================== UMMA issuer (leader CTA only) =====================
+        if (is_leader) {
+            constexpr uint32_t idesc = umma_idesc_bf16(G2_TILE_M, G2_TILE_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t iter = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++iter) {
+                const uint32_t as = iter & 1u;
+                const uint32_t aphase = (iter >> 1) & 1u;
+                mbar_wait_cluster(&tmem_empty_bar[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * G2_TILE_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t a_addr = smem_u32(smem_a + stage * G2_A_BYTES);
+                        const uint32_t b_addr = smem_u32(smem_b + stage * G2_B_BYTES);
+#pragma unroll
+                        for (int k = 0; k < G2_BLOCK_K / 16; ++k) {
+                            const uint64_t da = umma_smem_desc_sw128(a_addr + k * 32);
+                            const uint64_t db = umma_smem_desc_sw128(b_addr + k * 32);
+                            umma_bf16_ss_cg2(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit_cg2_mc(&empty_bar[stage], 0x3);                       // both CTAs' smem slots
+                        if (kb == num_kb - 1) umma_commit_cg2_mc(&tmem_full_bar[as], 0x3);  // both CTAs' epilogues
+                    }
+                    __syncwarp();
+                    if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp_idx == 3) {
+        // ===================== C mover (both CTAs) =====================
+        // Slab order 0,2,1,3: the two epilogue column halves finish slabs (0,2) first, then (1,3).
+        int prev_m = 0, prev_n = 0;
+        uint32_t iter = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++iter) {
+            const int m_blk = tile / p.num_n_blocks;
+            const int n_blk = tile % p.num_n_blocks;
+            const int m_coord = m_blk * G2_TILE_M + static_cast<int>(cta_rank) * 128;
+            const int n_coord = n_blk * G2_TILE_N;
+#pragma unroll 1
+            for (int si = 0; si < G2_SLABS; ++si) {
+                const int slab = ((si & 1) << 1) | (si >> 1);
+                if (iter > 0) {
+                    mbar_wait(&slab_written_bar[slab], (iter - 1) & 1u);
+                    if (lane == 0) {
+                        tma_store_2d(&tmap_out, smem_c + slab * G2_SLAB_BYTES, prev_n + slab * 64, prev_m);
+                        bulk_commit_group();
+                        bulk_wait_group_read0();     // the slab buffer may be overwritten from here on
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) {
+                    if constexpr (MODE == G2_EPI_BIAS_RESIDUAL) {
+                        mbar_arrive_expect_tx(&slab_ready_bar[slab], G2_SLAB_BYTES);
+                        tma_load_2d(&tmap_res, &slab_ready_bar[slab], smem_c + slab * G2_SLAB_BYTES, n_coord + slab * 64,
+                                    m_coord);
+                    } else {
+                        mbar_arrive(&slab_ready_bar[slab]);
+                    }
+                }
+                __syncwarp();
+            }
+            prev_m = m_coord;
+            prev_n = n_coord;
+        }
+        if (iter > 0) {
+#pragma unroll 1
+            for (int si = 0; si < G2_SLABS; ++si) {
+                const int slab = ((si & 1) << 1) | (si >> 1);
+                mbar_wait(&slab_written_bar[slab], (iter - 1) & 1u);
+                if (lane == 0) {
+                    tma_store_2d(&tmap_out, smem_c + slab * G2_SLAB_BYTES, prev_n + slab * 64, prev_m);
+                    bulk_commit_group();
+                }
+                __syncwarp();
+            }
+            if (lane == 0) bulk_wait_group0();       // global writes complete before the CTA may exit
+            __syncwarp();
+        }
+    } else if (warp_idx >= 4) {
+        // ===================== epilogue (both CTAs) =====================
+        const int q = warp_idx & 3;              // TMEM lane quadrant this warp may access
+        const int half = (warp_idx - 4) >> 2;    // column half: slabs {0,1} or {2,3}
+        const int r = q * 32 + lane;             // row inside this CTA's 128-row tile
+        const uint32_t tmem_empty_leader0 = mapa_u32(smem_u32(&tmem_empty_bar[0]), 0);
+        uint32_t iter = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++iter) {
+            const int n_blk = tile % p.num_n_blocks;
+            const uint32_t as = iter & 1u;
+            const uint32_t aphase = (iter >> 1) & 1u;
+            mbar_wait(&tmem_full_bar[as], aphase);
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + as * G2_TILE_N + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+            for (int s = 0; s < 2; ++s) {
+                const int slab = half * 2 + s;
+                uint8_t* slab_smem = smem_c + slab * G2_SLAB_BYTES;
+                mbar_wait(&slab_ready_bar[slab], iter & 1u);
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int col_in_tile = slab * 64 + c * 32;
+                    const int n0 = n_blk * G2_TILE_N + col_in_tile;
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_acc + col_in_tile, v);
+                    uint4 res[4];
+                    if constexpr (MODE == G2_EPI_BIAS_RESIDUAL) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            res[j] = *reinterpret_cast<const uint4*>(slab_smem + swz128(r, c * 4 + j));
+                    }
+                    tmem_ld_wait();
+                    if (s == 1 && c == 1) {
+                        // every TMEM read of this accumulator stage is in registers: hand it back to the issuer
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(tmem_empty_leader0 + as * 8);
+                    }
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    if (p.bias != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j * 4));
+                            f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+                        }
+                    }
+                    if constexpr (MODE == G2_EPI_BIAS_GELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+                    }
+                    if constexpr (MODE == G2_EPI_BIAS_RESIDUAL) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t w[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                f[8 * j + 2 * t] += bf16_lo(w[t]);
+                                f[8 * j + 2 * t + 1] += bf16_hi(w[t]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4*>(slab_smem + swz128(r, c * 4 + j)) =
+                            make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                                       pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+                }
+                fence_proxy_async_smem();        // generic-proxy smem writes -> visible to the TMA store
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&slab_written_bar[slab]);
+            }
+        }
+    }
+
+    // ---- teardown: nobody may exit (or free TMEM) while the pair still uses this CTA's smem / barriers
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp_idx == 2) {
+        tc_fence_after();
+        tmem_dealloc_cg2(tmem_base, G2_TMEM_COLS);
+    }
+}
+
+template <int MODE>
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
+                        const Gemm2Params& p, int max_ctas, cudaStream_t stream) {
+    auto kern = gemm_bf16_cg2_kernel<MODE>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES);
+        if (e != cudaSuccess) {
+            set_last_error("cudaFuncSetAttribute(smem=%d): %s", G2_SMEM_BYTES, cudaGetErrorString(e));
+            return UNIREC_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    const int tiles = p.num_m_blocks * p.num_n_blocks;
+    int clusters = num_sms() / 2;
+    if (max_ctas > 0 && clusters > max_ctas / 2) clusters = max_ctas / 2 > 0 ? max_ctas / 2 : 1;
+    if (clusters > tiles) clusters = tiles;
+    kern<<<2 * clusters, G2_THREADS, G2_SMEM_BYTES, stream>>>(ta, tb, to, tr, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_last_error("gemm (cta pair) launch failed: %s", cudaGetErrorString(e));
+        return UNIREC_ERR_CUDA;
+    }
+    return UNIREC_OK;
+}
+
+// Shapes the CTA-pair kernel accepts (the caller falls back to the single-CTA kernel otherwise).
+bool gemm_cg2_supported(long long M, long long N, long long K, int out_fp32, int res_row_mod, long long lda,
+                        long long ldw, long long ldo, long long ldr, int epilogue) {
+    (void)M;
+    if (out_fp32 || res_row_mod > 0) return false;
+    if (N % G2_TILE_N != 0 || K % G2_BLOCK_K != 0) return false;
+    if (lda % 8 != 0 || ldw % 8 != 0 || ldo % 8 != 0) return false;
+    if (epilogue == G2_EPI_BIAS_RESIDUAL && ldr % 8 != 0) return false;
+    return true;
+}
+
+int gemm_bf16_cg2(const void* A, long long lda, const void* W, long long ldw, const float* bias, const void* residual,
+                  long long ldr, void* out, long long ldo, long long M, long long N, long long K, int epilogue,
+                  int max_ctas, cudaStream_t stream) {
+    Gemm2Params p;
+    p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
+    p.bias = bias;
+    p.num_m_blocks = static_cast<int>((M + G2_TILE_M - 1) / G2_TILE_M);
+    p.num_n_blocks = static_cast<int>(N / G2_TILE_N);
+    CUtensorMap ta, tb, to, tr;
+    int rc = make_tmap_bf16_2d(&ta, A, M, K, lda, 128);
+    if (rc != UNIREC_OK) return rc;
+    rc = make_tmap_bf16_2d(&tb, W, N, K, ldw, 128);
+    if (rc != UNIREC_OK) return rc;
+    rc = make_tmap_bf16_2d(&to, out, M, N, ldo, 128);
+    if (rc != UNIREC_OK) return rc;
+    if (epilogue == G2_EPI_BIAS_RESIDUAL) {
+        rc = make_tmap_bf16_2d(&tr, residual, M, N, ldr, 128);
+        if (rc != UNIREC_OK) return rc;
+    } else {
+        tr = to;
+    }
+    switch (epilogue) {
+        case G2_EPI_BIAS: return launch_gemm2<G2_EPI_BIAS>(ta, tb, to, tr, p, max_ctas, stream);
+        case G2_EPI_BIAS_GELU: return launch_gemm2<G2_EPI_BIAS_GELU>(ta, tb, to, tr, p, max_ctas, stream);
+        case G2_EPI_BIAS_RESIDUAL: return launch_gemm2<G2_EPI_BIAS_RESIDUAL>(ta, tb, to, tr, p, max_ctas, stream);
+        default: set_last_error("gemm_bf16: unknown epilogue %d", epilogue); return UNIREC_ERR_BAD_ARG;
+    }
+}
+
+}  // namespace unirec

@@ -247,6 +247,13 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     return UNIREC_OK;
 }
 
+// CTA-pair kernel (gemm_cg2.cu)
+bool gemm_cg2_supported(long long M, long long N, long long K, int out_fp32, int res_row_mod, long long lda,
+                        long long ldw, long long ldo, long long ldr, int epilogue);
+int gemm_bf16_cg2(const void* A, long long lda, const void* W, long long ldw, const float* bias, const void* residual,
+                  long long ldr, void* out, long long ldo, long long M, long long N, long long K, int epilogue,
+                  int max_ctas, cudaStream_t stream);
+
 int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias, const void* residual,
               long long ldr, int res_row_mod, void* out, long long ldo, int out_fp32, long long M, long long N,
               long long K, int epilogue, int block_n, int max_ctas, cudaStream_t stream) {
@@ -270,6 +277,23 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const 
         set_last_error("gemm_bf16: bias must be 16-byte aligned");
         return UNIREC_ERR_BAD_ARG;
     }
+    if (epilogue == EPI_BIAS_RESIDUAL && (reinterpret_cast<uintptr_t>(residual) & 15)) {
+        set_last_error("gemm_bf16: residual must be 16-byte aligned");
+        return UNIREC_ERR_BAD_ARG;
+    }
+    // block_n: 0 = auto, 128 / 256 = single-CTA kernel with that tile width, 2 = CTA-pair kernel (256 x 256 per pair)
+    const bool cg2_ok = gemm_cg2_supported(M, N, K, out_fp32, res_row_mod, lda, ldw, ldo, ldr, epilogue);
+    if (block_n == 2 && !cg2_ok) {
+        set_last_error("gemm_bf16: the CTA-pair kernel needs bf16 output, N%%256==0, K%%64==0, no residual row broadcast");
+        return UNIREC_ERR_BAD_ARG;
+    }
+    if (block_n == 0 && cg2_ok) {
+        // the pair kernel whenever its 256 x 256 tiles give every SM pair at least one tile
+        const long long tiles = ((M + 255) / 256) * (N / 256);
+        if (tiles >= num_sms() / 2) block_n = 2;
+    }
+    if (block_n == 2)
+        return gemm_bf16_cg2(A, lda, W, ldw, bias, residual, ldr, out, ldo, M, N, K, epilogue, max_ctas, stream);
     if (block_n == 0) {
         // 256-wide tiles when they fill the machine for >= 2 waves, else 128-wide for more parallelism
         const long long tiles256 = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + 255) / 256);
@@ -277,7 +301,7 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const 
         if (N <= 128) block_n = 128;
     }
     if (block_n != 128 && block_n != 256) {
-        set_last_error("gemm_bf16: block_n must be 0, 128 or 256");
+        set_last_error("gemm_bf16: block_n must be 0, 2, 128 or 256");
         return UNIREC_ERR_BAD_ARG;
     }
     GemmParams p;
