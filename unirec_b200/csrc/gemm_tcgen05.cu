@@ -131,7 +131,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 }
                 if constexpr (MODE == EPI_BIAS_GELU) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+                    for (int j = 0; j < 32; j += 2) gelu_erf_x2(f[j], f[j + 1]);
                 }
                 if constexpr (MODE == EPI_BIAS_RESIDUAL) {
 #pragma unroll
