@@ -8,8 +8,12 @@
 //   item cross-attention  32 queries x 14 field keys    (KT = 16, one tile)
 //   user self-attention   64 queries x 64 keys          (KT = 64, one tile)
 //   user cross-attention  64 queries x <= 1600 keys     (KT = 64, key-tiled online softmax)
-// One CTA per (batch, head); each warp owns 16 query rows.  Q, K and V tiles are staged in shared
-// memory with cp.async (16-byte chunks, XOR swizzle), the two small matmuls run on mma.sync
+// Persistent CTAs: each CTA walks a strided list of (batch, head) work items and, inside an item, the key
+// tiles, as ONE flat sequence of K/V tile loads through a 3-deep cp.async ring - the loads of the next two
+// tiles (which may already belong to the next work item, together with its Q tile) are in flight while the
+// current tile is computed, so there is no load bubble between work items (an item-side work item is a
+// single 4-12 KB tile) and one __syncthreads per tile.  Each warp owns 16 query rows.  Q, K and V tiles are
+// staged in shared memory with cp.async (16-byte chunks, XOR swizzle), the two small matmuls run on mma.sync
 // m16n8k16 (bf16 in, fp32 accumulate) from ldmatrix fragments, softmax statistics are fp32 with
 // quad shuffles, and the context is written head-merged ([B*Q, H] row-major) through shared memory
 // so that global stores are 128-byte row segments.  The kernel is HBM-bound by design: algorithmic
@@ -21,6 +25,7 @@
 // degenerates to uniform attention over all nk keys (not NaN, not zero) - exactly the fp32
 // behaviour of the reference, where score + finfo.min == finfo.min for every key.
 #include "common.cuh"
+#include "umma_pipe.cuh"
 
 namespace unirec {
 
@@ -37,84 +42,95 @@ struct AttnParams {
 
 constexpr float kMaskedLog2 = -1.0e30f;  // stands in for finfo.min (see header comment)
 
+constexpr int ATT_STAGES = 3;
+
 template <int KT>
 __global__ void __launch_bounds__(128)
-attention_kernel(const AttnParams p) {
+attention_kernel(const AttnParams p, int num_items) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int b = blockIdx.x / p.num_heads;
-    const int h = blockIdx.x % p.num_heads;
     const int nq_pad = nwarps * 16;
 
-    uint8_t* sQ = smem;                               // nq_pad rows x 128 B
-    uint8_t* sK = sQ + nq_pad * 128;                  // 2 x KT rows x 128 B
-    uint8_t* sV = sK + 2 * KT * 128;                  // 2 x KT rows x 128 B
-    float* sM = reinterpret_cast<float*>(sV + 2 * KT * 128);  // 2 x KT additive mask (log2 domain)
+    uint8_t* sQ = smem;                                         // ATT_STAGES x nq_pad rows x 128 B
+    uint8_t* sK = sQ + ATT_STAGES * nq_pad * 128;               // ATT_STAGES x KT rows x 128 B
+    uint8_t* sV = sK + ATT_STAGES * KT * 128;                   // ATT_STAGES x KT rows x 128 B
+    float* sM = reinterpret_cast<float*>(sV + ATT_STAGES * KT * 128);   // ATT_STAGES x KT additive mask (log2 domain)
 
-    const __nv_bfloat16* qbase = p.q + (static_cast<long long>(b) * p.q_batch_rows) * p.ldq + h * 64;
-    const __nv_bfloat16* kbase = p.k + (static_cast<long long>(b) * p.kv_batch_rows) * p.ldk + h * 64;
-    const __nv_bfloat16* vbase = p.v + (static_cast<long long>(b) * p.kv_batch_rows) * p.ldv + h * 64;
-    const float* mbase = p.key_mask ? p.key_mask + static_cast<long long>(b) * p.nk : nullptr;
+    const int ntiles = (p.nk + KT - 1) / KT;                    // key tiles per work item
+    const int my_items = (num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                         static_cast<int>(gridDim.x);
+    const int total = my_items * ntiles;                        // flat tile count of this CTA
 
-    auto load_kv_tile = [&](int tile, int buf) {
-        const int base = tile * KT;
-        for (int i = threadIdx.x; i < KT * 8; i += blockDim.x) {
-            const int r = i >> 3, c = i & 7;
-            const int key = base + r;
-            const bool ok = key < p.nk;
-            const long long kr = ok ? key : (p.nk - 1);
-            cp_async_16(smem_u32(sK + buf * KT * 128) + swz128(r, c), kbase + kr * p.ldk + c * 8, ok);
-            cp_async_16(smem_u32(sV + buf * KT * 128) + swz128(r, c), vbase + kr * p.ldv + c * 8, ok);
+    // issue the loads of flat tile g (and the item's Q tile when it is the item's first key tile)
+    auto issue = [&](int g) {
+        if (g < total) {
+            const int it = g / ntiles, tile = g - it * ntiles;
+            const int w = blockIdx.x + it * gridDim.x;
+            const int b = w / p.num_heads, h = w - b * p.num_heads;
+            const int buf = g % ATT_STAGES;
+            const __nv_bfloat16* kbase = p.k + (static_cast<long long>(b) * p.kv_batch_rows) * p.ldk + h * 64;
+            const __nv_bfloat16* vbase = p.v + (static_cast<long long>(b) * p.kv_batch_rows) * p.ldv + h * 64;
+            const float* mbase = p.key_mask ? p.key_mask + static_cast<long long>(b) * p.nk : nullptr;
+            if (tile == 0) {
+                const __nv_bfloat16* qbase = p.q + (static_cast<long long>(b) * p.q_batch_rows) * p.ldq + h * 64;
+                const uint32_t qdst = smem_u32(sQ + (it % ATT_STAGES) * nq_pad * 128);
+                for (int i = threadIdx.x; i < nq_pad * 8; i += blockDim.x) {
+                    const int r = i >> 3, c = i & 7;
+                    const bool ok = r < p.nq;
+                    const long long qr = ok ? r : (p.nq - 1);
+                    cp_async_16(qdst + swz128(r, c), qbase + qr * p.ldq + c * 8, ok);
+                }
+            }
+            const int base = tile * KT;
+            const uint32_t kdst = smem_u32(sK + buf * KT * 128), vdst = smem_u32(sV + buf * KT * 128);
+            for (int i = threadIdx.x; i < KT * 8; i += blockDim.x) {
+                const int r = i >> 3, c = i & 7;
+                const int key = base + r;
+                const bool ok = key < p.nk;
+                const long long kr = ok ? key : (p.nk - 1);
+                cp_async_16(kdst + swz128(r, c), kbase + kr * p.ldk + c * 8, ok);
+                cp_async_16(vdst + swz128(r, c), vbase + kr * p.ldv + c * 8, ok);
+            }
+            for (int i = threadIdx.x; i < KT; i += blockDim.x) {
+                const int key = base + i;
+                float m = -INFINITY;  // padding beyond nk: excluded
+                if (key < p.nk) m = (mbase != nullptr && mbase[key] == 0.f) ? kMaskedLog2 : 0.f;
+                sM[buf * KT + i] = m;
+            }
         }
-        for (int i = threadIdx.x; i < KT; i += blockDim.x) {
-            const int key = base + i;
-            float m = -INFINITY;  // padding beyond nk: excluded
-            if (key < p.nk) m = (mbase != nullptr && mbase[key] == 0.f) ? kMaskedLog2 : 0.f;
-            sM[buf * KT + i] = m;
-        }
+        cp_async_commit();   // always commit (possibly empty) so that group counting stays uniform
     };
 
-    // ---- prologue: Q tile + first K/V tile
-    for (int i = threadIdx.x; i < nq_pad * 8; i += blockDim.x) {
-        const int r = i >> 3, c = i & 7;
-        const bool ok = r < p.nq;
-        const long long qr = ok ? r : (p.nq - 1);
-        cp_async_16(smem_u32(sQ) + swz128(r, c), qbase + qr * p.ldq + c * 8, ok);
-    }
-    load_kv_tile(0, 0);
-    cp_async_commit();
+#pragma unroll
+    for (int g = 0; g < ATT_STAGES - 1; ++g) issue(g);
 
-    const int ntiles = (p.nk + KT - 1) / KT;
-    const int g = lane >> 2, t = lane & 3;
-
+    const int g4 = lane >> 2, t = lane & 3;
     uint32_t qf[4][4];
     float o[8][4];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
-    float m_run[2] = {-INFINITY, -INFINITY};
-    float l_run[2] = {0.f, 0.f};
+    float m_run[2], l_run[2];
 
-    for (int tile = 0; tile < ntiles; ++tile) {
-        const int buf = tile & 1;
-        if (tile + 1 < ntiles) {
-            load_kv_tile(tile + 1, buf ^ 1);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads();
+    for (int g = 0; g < total; ++g) {
+        const int it = g / ntiles, tile = g - it * ntiles;
+        const int buf = g % ATT_STAGES;
+        cp_async_wait<ATT_STAGES - 2>();   // flat tile g has landed (this thread's part)
+        __syncthreads();                   // ... everyone's part; and everyone is done with flat tile g-1
+        issue(g + ATT_STAGES - 1);         // refills the buffer of flat tile g-1
 
+        uint8_t* sQi = sQ + (it % ATT_STAGES) * nq_pad * 128;
         if (tile == 0) {
-            // Q fragments (A operand, 16 rows x 64 dims = 4 k-steps) stay in registers for all tiles
+            // Q fragments (A operand, 16 rows x 64 dims = 4 k-steps) stay in registers for the whole item
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
                 const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
                 const int c = kk * 2 + (lane >> 4);
-                ldmatrix_x4(smem_u32(sQ) + swz128(r, c), qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3]);
+                ldmatrix_x4(smem_u32(sQi) + swz128(r, c), qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3]);
             }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+            m_run[0] = m_run[1] = -INFINITY;
+            l_run[0] = l_run[1] = 0.f;
         }
 
         // ---- S = Q K^T  (16 x KT per warp)
@@ -140,12 +156,12 @@ attention_kernel(const AttnParams p) {
         float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
         for (int j = 0; j < KT / 8; ++j) {
-            const float m0 = mt[8 * j + 2 * t], m1 = mt[8 * j + 2 * t + 1];
+            const float2 m01 = *reinterpret_cast<const float2*>(mt + 8 * j + 2 * t);
             // masked keys: the score is absorbed by the huge constant exactly as in the fp32 reference
-            s[j][0] = (m0 == 0.f) ? s[j][0] * p.scale_log2 : m0;
-            s[j][1] = (m1 == 0.f) ? s[j][1] * p.scale_log2 : m1;
-            s[j][2] = (m0 == 0.f) ? s[j][2] * p.scale_log2 : m0;
-            s[j][3] = (m1 == 0.f) ? s[j][3] * p.scale_log2 : m1;
+            s[j][0] = (m01.x == 0.f) ? s[j][0] * p.scale_log2 : m01.x;
+            s[j][1] = (m01.y == 0.f) ? s[j][1] * p.scale_log2 : m01.y;
+            s[j][2] = (m01.x == 0.f) ? s[j][2] * p.scale_log2 : m01.x;
+            s[j][3] = (m01.y == 0.f) ? s[j][3] * p.scale_log2 : m01.y;
             mx[0] = fmaxf(mx[0], fmaxf(s[j][0], s[j][1]));
             mx[1] = fmaxf(mx[1], fmaxf(s[j][2], s[j][3]));
         }
@@ -155,23 +171,25 @@ attention_kernel(const AttnParams p) {
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
             const float m_new = fmaxf(m_run[r], mx[r]);   // finite: key 0 of tile 0 always exists
-            alpha[r] = exp2f(m_run[r] - m_new);           // first tile: exp2(-inf) = 0
+            alpha[r] = ex2_approx(m_run[r] - m_new);      // first tile: ex2(-inf) = 0
             m_run[r] = m_new;
             l_run[r] *= alpha[r];
         }
 #pragma unroll
         for (int j = 0; j < KT / 8; ++j) {
-            s[j][0] = exp2f(s[j][0] - m_run[0]);
-            s[j][1] = exp2f(s[j][1] - m_run[0]);
-            s[j][2] = exp2f(s[j][2] - m_run[1]);
-            s[j][3] = exp2f(s[j][3] - m_run[1]);
+            s[j][0] = ex2_approx(s[j][0] - m_run[0]);
+            s[j][1] = ex2_approx(s[j][1] - m_run[0]);
+            s[j][2] = ex2_approx(s[j][2] - m_run[1]);
+            s[j][3] = ex2_approx(s[j][3] - m_run[1]);
             l_run[0] += s[j][0] + s[j][1];
             l_run[1] += s[j][2] + s[j][3];
         }
+        if (tile > 0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            o[j][0] *= alpha[0]; o[j][1] *= alpha[0];
-            o[j][2] *= alpha[1]; o[j][3] *= alpha[1];
+            for (int j = 0; j < 8; ++j) {
+                o[j][0] *= alpha[0]; o[j][1] *= alpha[0];
+                o[j][2] *= alpha[1]; o[j][3] *= alpha[1];
+            }
         }
 
         // ---- O += P V
@@ -193,33 +211,47 @@ attention_kernel(const AttnParams p) {
                 mma_bf16_16816(o[2 * jj + 1], a, b2, b3);
             }
         }
-        __syncthreads();  // everyone done with buffer `buf` before it is refilled two tiles later
-    }
 
-    // ---- normalise and write the context tile through shared memory (reuses this warp's Q rows)
+        if (tile == ntiles - 1) {
+            // ---- normalise and write the context tile through shared memory (this warp's own Q rows of the
+            //      item's Q buffer: nobody else reads them, and the buffer is only refilled two items later)
+            const int w = blockIdx.x + it * gridDim.x;
+            const int b = w / p.num_heads, h = w - b * p.num_heads;
+            float inv[2];
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
-        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
-        l_run[r] = 1.0f / l_run[r];
-    }
-    __syncwarp();
+            for (int r = 0; r < 2; ++r) {
+                float l = l_run[r];
+                l += __shfl_xor_sync(0xffffffffu, l, 1);
+                l += __shfl_xor_sync(0xffffffffu, l, 2);
+                inv[r] = 1.0f / l;
+            }
+            __syncwarp();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int r0 = warp * 16 + g;
-        *reinterpret_cast<uint32_t*>(sQ + swz128(r0, j) + 4 * t) = pack_bf16(o[j][0] * l_run[0], o[j][1] * l_run[0]);
-        *reinterpret_cast<uint32_t*>(sQ + swz128(r0 + 8, j) + 4 * t) =
-            pack_bf16(o[j][2] * l_run[1], o[j][3] * l_run[1]);
-    }
-    __syncwarp();
-    __nv_bfloat16* obase = p.out + (static_cast<long long>(b) * p.nq) * p.ldo + h * 64;
-    for (int i = lane; i < 16 * 8; i += 32) {
-        const int r = warp * 16 + (i >> 3), c = i & 7;
-        if (r < p.nq) {
-            const uint4 val = *reinterpret_cast<const uint4*>(sQ + swz128(r, c));
-            *reinterpret_cast<uint4*>(obase + static_cast<long long>(r) * p.ldo + c * 8) = val;
+            for (int j = 0; j < 8; ++j) {
+                const int r0 = warp * 16 + g4;
+                *reinterpret_cast<uint32_t*>(sQi + swz128(r0, j) + 4 * t) = pack_bf16(o[j][0] * inv[0], o[j][1] * inv[0]);
+                *reinterpret_cast<uint32_t*>(sQi + swz128(r0 + 8, j) + 4 * t) =
+                    pack_bf16(o[j][2] * inv[1], o[j][3] * inv[1]);
+            }
+            __syncwarp();
+            __nv_bfloat16* obase = p.out + (static_cast<long long>(b) * p.nq) * p.ldo + h * 64;
+            for (int i = lane; i < 16 * 8; i += 32) {
+                const int r = warp * 16 + (i >> 3), c = i & 7;
+                if (r < p.nq) {
+                    const uint4 val = *reinterpret_cast<const uint4*>(sQi + swz128(r, c));
+                    *reinterpret_cast<uint4*>(obase + static_cast<long long>(r) * p.ldo + c * 8) = val;
+                }
+            }
         }
     }
+    cp_async_wait<0>();
+}
+
+template <class K>
+static int attention_ctas_per_sm(K kern, int threads, size_t smem) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem) != cudaSuccess || n < 1) n = 1;
+    return n;
 }
 
 int attention(const void* q, long long ldq, long long q_batch_rows, const void* k, long long ldk, const void* v,
@@ -247,12 +279,32 @@ int attention(const void* q, long long ldq, long long q_batch_rows, const void* 
     p.scale_log2 = scale * 1.4426950408889634f;
     const int nwarps = static_cast<int>((nq + 15) / 16);
     const int threads = nwarps * 32;
-    const unsigned grid = static_cast<unsigned>(batch * num_heads);
+    const int num_items = static_cast<int>(batch * num_heads);
     const int kt = nk <= 16 ? 16 : (nk <= 32 ? 32 : 64);
-    const size_t smem = static_cast<size_t>(nwarps) * 16 * 128 + 4 * static_cast<size_t>(kt) * 128 + 2 * kt * sizeof(float);
-    if (kt == 16) attention_kernel<16><<<grid, threads, smem, stream>>>(p);
-    else if (kt == 32) attention_kernel<32><<<grid, threads, smem, stream>>>(p);
-    else attention_kernel<64><<<grid, threads, smem, stream>>>(p);
+    const size_t smem = static_cast<size_t>(ATT_STAGES) *
+                        (static_cast<size_t>(nwarps) * 16 * 128 + 2 * static_cast<size_t>(kt) * 128 + kt * sizeof(float));
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e1 = cudaFuncSetAttribute(attention_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaError_t e2 = cudaFuncSetAttribute(attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaError_t e3 = cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+            set_last_error("attention: cudaFuncSetAttribute failed");
+            return UNIREC_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    const int sms = num_sms() > 0 ? num_sms() : 148;
+#define UNIREC_ATT(KT_)                                                                                      \
+    do {                                                                                                     \
+        long long grid = static_cast<long long>(sms) * attention_ctas_per_sm(attention_kernel<KT_>, threads, smem); \
+        if (grid > num_items) grid = num_items;                                                              \
+        attention_kernel<KT_><<<static_cast<unsigned>(grid), threads, smem, stream>>>(p, num_items);          \
+    } while (0)
+    if (kt == 16) UNIREC_ATT(16);
+    else if (kt == 32) UNIREC_ATT(32);
+    else UNIREC_ATT(64);
+#undef UNIREC_ATT
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_last_error("attention launch: %s", cudaGetErrorString(e));

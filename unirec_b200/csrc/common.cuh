@@ -100,6 +100,12 @@ UNIREC_DEVICE float gelu_erf(float x) {
     return y;
 }
 
+UNIREC_DEVICE float ex2_approx(float x) {   // MUFU.EX2: 2 ulp, ex2(-inf) = 0
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 UNIREC_DEVICE float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
