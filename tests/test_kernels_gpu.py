@@ -162,7 +162,7 @@ def _ref_attention(q, k, v, mask, heads):
 
 
 @pytest.mark.parametrize("nq,nk,heads", [(32, 32, 16), (32, 14, 16), (64, 64, 16), (64, 160, 16), (64, 1600, 4),
-                                         (32, 6, 4), (64, 97, 4)])
+                                         (32, 6, 4), (64, 97, 4), (64, 128, 2), (40, 300, 6), (64, 129, 2)])
 def test_attention(nq, nk, heads):
     from unirec_b200 import ops
     B = 5
@@ -185,6 +185,38 @@ def test_attention(nq, nk, heads):
     if True:
         uniform = v[1].float().mean(dim=0, keepdim=True).expand(nq, hd)
         torch.testing.assert_close(out[1].float(), uniform, rtol=2e-2, atol=2e-2)
+
+
+def test_attention_long_keys_growing_scores_and_strided_kv():
+    """tcgen05 path (nk > 64): K/V as column slices of a wide [rows, 8*H] buffer (the user model's kv_all layout),
+    many work items per CTA, and scores that grow tile after tile so that the lazily raised running max and the
+    rescale of the TMEM accumulator are exercised (each key tile beats the previous by > 2^8)."""
+    from unirec_b200 import ops
+    B, nq, nk, heads = 40, 64, 700, 16
+    hd = heads * 64
+    g = torch.Generator().manual_seed(60)
+    q = torch.randn(B, nq, hd, generator=g)
+    k = torch.randn(B, nk, hd, generator=g) * 0.3
+    # add a component along the mean query direction of each head that grows with the key index
+    qdir = q.view(B, nq, heads, 64).mean(dim=1)                                  # [B, heads, 64]
+    qdir = qdir / qdir.norm(dim=-1, keepdim=True)
+    ramp = (torch.arange(nk).float() / 128.0).floor() * 3.0                      # +3 per 128-key tile
+    k = k + (ramp[None, :, None, None] * qdir[:, None, :, :]).reshape(B, nk, hd)
+    v = torch.randn(B, nk, hd, generator=g)
+    q, k, v = q.to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16)
+    wide = torch.zeros(B * nk, 8 * hd, dtype=torch.bfloat16)
+    wide[:, 2 * hd:3 * hd] = k.view(B * nk, hd)
+    wide[:, 3 * hd:4 * hd] = v.view(B * nk, hd)
+    wide = wide.to(_dev())
+    mask = torch.ones(B, nk)
+    mask[3, 500:] = 0.0
+    mask[4, :650] = 0.0
+    mask = mask.to(_dev())
+    out = ops.attention(q.to(_dev()).view(B * nq, hd), wide[:, 2 * hd:3 * hd], wide[:, 3 * hd:4 * hd], batch=B,
+                        num_heads=heads, nq=nq, nk=nk, key_mask=mask).view(B, nq, hd)
+    ref = _ref_attention(q.to(_dev()), k.to(_dev()), v.to(_dev()), mask, heads)
+    assert torch.isfinite(out).all()
+    torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)
 
 
 def test_attention_fused_qkv_layout_and_broadcast_queries():

@@ -27,6 +27,8 @@
 #include "common.cuh"
 #include "umma_pipe.cuh"
 
+#include <cstdlib>
+
 namespace unirec {
 
 struct AttnParams {
@@ -254,6 +256,23 @@ static int attention_ctas_per_sm(K kern, int threads, size_t smem) {
     return n;
 }
 
+// tcgen05 kernel for long key sequences (attention_tc.cu)
+bool attention_tc_supported(long long num_heads, long long nq, long long nk, long long head_dim, long long ldk,
+                            long long ldv, long long kv_batch_rows);
+int attention_tc(const void* q, long long ldq, long long q_batch_rows, const void* k, long long ldk, const void* v,
+                 long long ldv, long long kv_batch_rows, const float* key_mask, void* out, long long ldo, long long batch,
+                 long long num_heads, long long nq, long long nk, float scale, cudaStream_t stream);
+
+static bool attention_tc_enabled() {
+    // UNIREC_ATTENTION_TC=0 forces the mma.sync kernel for every shape (A/B measurements and tests)
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("UNIREC_ATTENTION_TC");
+        on = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+
 int attention(const void* q, long long ldq, long long q_batch_rows, const void* k, long long ldk, const void* v,
               long long ldv, long long kv_batch_rows, const float* key_mask, void* out, long long ldo, long long batch,
               long long num_heads, long long nq, long long nk, long long head_dim, float scale, cudaStream_t stream) {
@@ -268,6 +287,9 @@ int attention(const void* q, long long ldq, long long q_batch_rows, const void* 
                        head_dim, nq);
         return UNIREC_ERR_BAD_ARG;
     }
+    if (attention_tc_enabled() && attention_tc_supported(num_heads, nq, nk, head_dim, ldk, ldv, kv_batch_rows))
+        return attention_tc(q, ldq, q_batch_rows, k, ldk, v, ldv, kv_batch_rows, key_mask, out, ldo, batch, num_heads, nq,
+                            nk, scale, stream);
     AttnParams p;
     p.q = reinterpret_cast<const __nv_bfloat16*>(q); p.ldq = ldq; p.q_batch_rows = q_batch_rows;
     p.k = reinterpret_cast<const __nv_bfloat16*>(k); p.ldk = ldk;

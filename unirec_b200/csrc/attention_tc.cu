@@ -1,0 +1,455 @@
+// Long-key cross-attention on the 5th-generation tensor cores (sm_100a), head_dim = 64, <= 64 queries.
+//
+//   ctx[b, q, h*64:(h+1)*64] = softmax_k( Q[b,q,h,:] . K[b,k,h,:] * scale + mask[b,k] ) @ V[b,k,h,:]
+//
+// Used for the user Q-Former's cross-attention (64 queries x up to 1600 keys per user and head;
+// models/qformer.py:185-188, 205, 244-268 with encoder_hidden_states = the user sequence).  At 64 flop per K/V
+// byte this shape is compute-limited on mma.sync (attention.cu reaches 43 % of HBM bandwidth); here both small
+// matmuls run on tcgen05 with accumulators in TMEM and the CUDA cores only do the softmax.
+//
+// One work item = (batch element, PAIR of adjacent heads).  Two heads are stacked so that every UMMA has M = 128
+// (TMEM lane = accumulator row = one softmax thread):
+//     S[128 x 128 keys] = Q2[128 x 128] . Kt[128 keys x 128]^T,   Q2 = [[Q_h, 0], [0, Q_h+1]]  (block diagonal)
+//     O[128 x 128]     += P[128 x 128 keys] . Vt[128 keys x 128]   (useful blocks: rows 0-63 x cols 0-63 = head h,
+//                                                                    rows 64-127 x cols 64-127 = head h+1)
+// where Kt / Vt are 128 consecutive keys x the 128 contiguous columns of the two heads (one 256-byte segment per
+// key and matrix, fetched by TMA as two 64-column slabs, 128-byte swizzle).  Kt is the K-major B operand of the
+// first MMA; Vt is used in place as the MN-major B operand of the second (no transpose anywhere).
+//
+// Warp roles (192 threads, one persistent CTA per SM):
+//     warps 0-3  softmax: thread r owns row r.  tcgen05.ld S -> scale + additive mask -> row max -> ex2 -> row sum,
+//                P (bf16) -> shared memory (K-major, swizzled) for the second MMA.  The running max is only
+//                raised when a tile exceeds it by more than 2^8 (exact: O and the row sum are accumulated against the
+//                same reference value), so O in TMEM is almost never rescaled.  Also builds Q2 for the NEXT item.
+//     warp 4     TMA producer: K and V tiles through two 2-stage rings
+//     warp 5     TMEM allocator + UMMA issuer; issue order S(g+1), PV(g) so that the softmax of tile g overlaps
+//                the first MMA of tile g+1 (two S accumulators in TMEM) - across work items too
+// Mask semantics are those of attention.cu: key_mask == 0 adds -1e30 (log2 domain), keys beyond nk are excluded
+// (-inf), a row whose keys are all masked comes out uniform over the nk keys.
+#include "common.cuh"
+#include "umma_pipe.cuh"
+
+namespace unirec {
+
+constexpr int AT_KT = 128;                       // keys per tile
+constexpr int AT_SLAB = 128 * 64 * 2;            // [128 rows][64 bf16] = 16 KB
+constexpr int AT_TILE = 2 * AT_SLAB;             // 32 KB: Q2, a K tile, a V tile, P
+constexpr int AT_THREADS = 192;
+constexpr int AT_SMEM_BYTES = 2 * AT_TILE /*Q2 x2*/ + 2 * AT_TILE /*K x2*/ + 2 * AT_TILE /*V x2*/ + AT_TILE /*P*/ +
+                              2 * AT_KT * 4 /*mask*/ + 32 /*flags*/ + 1024 /*align*/ + 256 /*barriers*/;
+static_assert(AT_SMEM_BYTES <= 232448, "shared memory budget exceeded");
+constexpr float AT_MASKED = -1.0e30f;
+constexpr float AT_LAZY = 8.0f;                  // raise the running max only when exceeded by 2^8
+
+struct AttnTcParams {
+    const __nv_bfloat16* q; long long ldq; long long q_batch_rows;
+    const float* key_mask;                       // [B, nk] or nullptr
+    __nv_bfloat16* out; long long ldo;
+    int num_heads, nq, nk, kv_batch_rows;
+    float scale_log2;
+    int num_items;                               // batch * num_heads / 2
+};
+
+// K-major SW128 descriptor is umma_smem_desc_sw128 (common.cuh).  MN-major SW128: the tile is
+// [K rows of 128 B][64 MN elements], 8-row groups 1024 B apart (SBO), 64-element MN blocks lbo_bytes apart (LBO).
+UNIREC_DEVICE uint64_t umma_smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>(1024u >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_bmn(uint32_t m, uint32_t n) {
+    return umma_idesc_bf16(m, n) | (1u << 16);   // B operand MN-major
+}
+
+UNIREC_DEVICE void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
+                    const AttnTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ2 = smem;                          // [2][2 slabs]
+    uint8_t* sK = smem + 2 * AT_TILE;             // [2][2 slabs]
+    uint8_t* sV = smem + 4 * AT_TILE;             // [2][2 slabs]
+    uint8_t* sP = smem + 6 * AT_TILE;             // [2 slabs]
+    float* sMask = reinterpret_cast<float*>(smem + 7 * AT_TILE);   // [2][128]
+    int* sPlain = reinterpret_cast<int*>(smem + 7 * AT_TILE + 2 * AT_KT * 4);   // [2][4] per-warp "tile has no masked key"
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * AT_TILE + 2 * AT_KT * 4 + 32);
+    uint64_t* k_full = bars;            // [2]
+    uint64_t* k_empty = bars + 2;       // [2]
+    uint64_t* v_full = bars + 4;        // [2]
+    uint64_t* v_empty = bars + 6;       // [2]
+    uint64_t* q_ready = bars + 8;       // [2]  softmax warps -> issuer
+    uint64_t* q_free = bars + 10;       // [2]  issuer (commit) -> softmax warps
+    uint64_t* s_full = bars + 12;       // [2]  issuer (commit) -> softmax warps
+    uint64_t* s_free = bars + 14;       // [2]  softmax warps -> issuer
+    uint64_t* p_ready = bars + 16;      // softmax warps -> issuer
+    uint64_t* pv_done = bars + 17;      // issuer (commit) -> softmax warps
+    uint64_t* o_free = bars + 18;       // softmax warps -> issuer (O of the finished item has been read)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 19);
+
+    const int T = (p.nk + AT_KT - 1) / AT_KT;
+    const int my_items = (p.num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                         static_cast<int>(gridDim.x);
+    const int G = my_items * T;
+    const int pairs = p.num_heads >> 1;
+
+    if (warp_idx == 4 && lane == 0) {
+        tma_prefetch_desc(&tmap_k);
+        tma_prefetch_desc(&tmap_v);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+            mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+            mbar_init(&q_ready[i], 4); mbar_init(&q_free[i], 1);
+            mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4);
+        }
+        mbar_init(p_ready, 4);
+        mbar_init(pv_done, 1);
+        mbar_init(o_free, 4);
+        fence_mbar_init();
+    }
+    if (warp_idx == 5) {
+        tmem_alloc(tmem_ptr_smem, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t tmem_o = tmem_base + 256;
+
+    if (warp_idx == 4) {
+        // ===================== TMA producer =====================
+        for (int g = 0; g < G; ++g) {
+            const int it = g / T, t = g - it * T;
+            const int w = blockIdx.x + it * gridDim.x;
+            const int b = w / pairs, hp = w - b * pairs;
+            const int slot = g & 1;
+            const uint32_t ph = (g >> 1) & 1;
+            const int row = b * p.kv_batch_rows + t * AT_KT;
+            const int col = hp * 128;
+            mbar_wait(&k_empty[slot], ph ^ 1);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&k_full[slot], AT_TILE);
+                tma_load_2d(&tmap_k, &k_full[slot], sK + slot * AT_TILE, col, row);
+                tma_load_2d(&tmap_k, &k_full[slot], sK + slot * AT_TILE + AT_SLAB, col + 64, row);
+            }
+            __syncwarp();
+            mbar_wait(&v_empty[slot], ph ^ 1);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&v_full[slot], AT_TILE);
+                tma_load_2d(&tmap_v, &v_full[slot], sV + slot * AT_TILE, col, row);
+                tma_load_2d(&tmap_v, &v_full[slot], sV + slot * AT_TILE + AT_SLAB, col + 64, row);
+            }
+            __syncwarp();
+        }
+    } else if (warp_idx == 5) {
+        // ===================== UMMA issuer =====================
+        constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
+        constexpr uint32_t idesc_pv = umma_idesc_bf16_bmn(128, 128);
+        auto issue_s = [&](int g) {
+            const int it = g / T, t = g - it * T;
+            const int slot = g & 1;
+            const uint32_t ph = (g >> 1) & 1;
+            if (t == 0) mbar_wait(&q_ready[it & 1], (it >> 1) & 1);
+            mbar_wait(&k_full[slot], ph);
+            mbar_wait(&s_free[slot], ph ^ 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t a_addr = smem_u32(sQ2 + (it & 1) * AT_TILE);
+                const uint32_t b_addr = smem_u32(sK + slot * AT_TILE);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint32_t off = (ks >> 2) * AT_SLAB + (ks & 3) * 32;
+                    umma_bf16_ss(tmem_base + slot * 128, umma_smem_desc_sw128(a_addr + off),
+                                 umma_smem_desc_sw128(b_addr + off), idesc_s, ks != 0 ? 1u : 0u);
+                }
+                umma_commit(&k_empty[slot]);
+                umma_commit(&s_full[slot]);
+                if (t == T - 1) umma_commit(&q_free[it & 1]);
+            }
+            __syncwarp();
+        };
+        auto issue_pv = [&](int g) {
+            const int it = g / T, t = g - it * T;
+            const int slot = g & 1;
+            const uint32_t ph = (g >> 1) & 1;
+            mbar_wait(&v_full[slot], ph);
+            mbar_wait(p_ready, g & 1);
+            if (t == 0 && it > 0) mbar_wait(o_free, (it - 1) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t a_addr = smem_u32(sP);
+                const uint32_t b_addr = smem_u32(sV + slot * AT_TILE);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint32_t a_off = (ks >> 2) * AT_SLAB + (ks & 3) * 32;     // 16 keys = 32 B along K
+                    const uint32_t b_off = ks * 16 * 128;                            // 16 key rows of 128 B
+                    umma_bf16_ss(tmem_o, umma_smem_desc_sw128(a_addr + a_off),
+                                 umma_smem_desc_mn_sw128(b_addr + b_off, AT_SLAB), idesc_pv, (t | ks) != 0 ? 1u : 0u);
+                }
+                umma_commit(&v_empty[slot]);
+                umma_commit(pv_done);
+            }
+            __syncwarp();
+        };
+        if (G > 0) issue_s(0);
+        for (int g = 0; g < G; ++g) {
+            if (g + 1 < G) issue_s(g + 1);
+            issue_pv(g);
+        }
+    } else {
+        // ===================== softmax warps (thread r = accumulator row r) =====================
+        const int r = threadIdx.x;                 // 0..127
+        const int hsel = r >> 6;                   // 0: head 2*hp, 1: head 2*hp + 1
+        const int qrow = r & 63;
+        const uint32_t lane_field = static_cast<uint32_t>(warp_idx * 32) << 16;
+
+        // Q2 rows: slab `hsel` holds this row's 64 query values, the other slab is zero
+        auto load_q = [&](int it, uint4 (&qv)[8]) {
+            const int w = blockIdx.x + it * gridDim.x;
+            const int b = w / pairs, hp = w - b * pairs;
+            const __nv_bfloat16* src = p.q + (static_cast<long long>(b) * p.q_batch_rows + qrow) * p.ldq +
+                                       (2 * hp + hsel) * 64;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                qv[c] = (qrow < p.nq) ? __ldg(reinterpret_cast<const uint4*>(src) + c) : make_uint4(0, 0, 0, 0);
+        };
+        auto store_q = [&](int it, const uint4 (&qv)[8]) {
+            uint8_t* base = sQ2 + (it & 1) * AT_TILE;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                *reinterpret_cast<uint4*>(base + hsel * AT_SLAB + swz128(r, c)) = qv[c];
+                *reinterpret_cast<uint4*>(base + (hsel ^ 1) * AT_SLAB + swz128(r, c)) = make_uint4(0, 0, 0, 0);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&q_ready[it & 1]);
+        };
+
+        uint4 qv[8];
+        if (my_items > 0) {
+            load_q(0, qv);
+            store_q(0, qv);
+        }
+        float m_used = -INFINITY, l_run = 0.f;
+        for (int g = 0; g < G; ++g) {
+            const int it = g / T, t = g - it * T;
+            const int w = blockIdx.x + it * gridDim.x;
+            const int b = w / pairs, hp = w - b * pairs;
+            const int slot = g & 1;
+            const uint32_t ph = (g >> 1) & 1;
+            if (t == 0) {
+                m_used = -INFINITY;
+                l_run = 0.f;
+                if (it + 1 < my_items) load_q(it + 1, qv);    // in flight during this tile's softmax
+            }
+            // ---- additive mask of this key tile -> smem (one key per thread); `plain` = no key of the tile is
+            //      masked or out of range (the common case), then the mask is not touched again
+            {
+                const int key = t * AT_KT + r;
+                float mv = -INFINITY;
+                if (key < p.nk)
+                    mv = (p.key_mask != nullptr && __ldg(p.key_mask + static_cast<long long>(b) * p.nk + key) == 0.f)
+                             ? AT_MASKED : 0.f;
+                sMask[slot * AT_KT + r] = mv;
+                const bool warp_plain = __all_sync(0xffffffffu, mv == 0.f);
+                if (lane == 0) sPlain[slot * 4 + warp_idx] = warp_plain ? 1 : 0;
+            }
+            named_bar_sync(1, 128);
+            const float* mt = sMask + slot * AT_KT;
+            const bool plain = (sPlain[slot * 4] & sPlain[slot * 4 + 1] & sPlain[slot * 4 + 2] & sPlain[slot * 4 + 3]) != 0;
+
+            mbar_wait(&s_full[slot], ph);
+            tc_fence_after();
+            const uint32_t tmem_s = tmem_base + slot * 128 + lane_field;
+
+            // ---- the whole S row (128 fp32) into registers, then hand the accumulator back to the issuer
+            uint32_t sv[4][32];
+            tmem_ld_32x32(tmem_s, sv[0]);
+            tmem_ld_32x32(tmem_s + 32, sv[1]);
+            tmem_ld_32x32(tmem_s + 64, sv[2]);
+            tmem_ld_32x32(tmem_s + 96, sv[3]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[slot]);
+
+            // ---- x = scale * s (+ mask); row maximum.  Plain tiles keep raw s and fold the scale into the ex2 FFMA.
+            float mx = -INFINITY;
+            float xs = p.scale_log2;           // multiplier applied inside the exponent
+            if (plain) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(sv[c][j]));
+                mx *= p.scale_log2;            // scale > 0: max commutes with the scaling
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 m4 = *reinterpret_cast<const float4*>(mt + c * 32 + j);
+                        const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float x = (mm[e] == 0.f) ? __uint_as_float(sv[c][j + e]) * p.scale_log2 : mm[e];
+                            sv[c][j + e] = __float_as_uint(x);
+                            mx = fmaxf(mx, x);
+                        }
+                    }
+                }
+                xs = 1.0f;
+            }
+            // ---- lazy running max: rescale only when this tile exceeds the reference by more than 2^8
+            const bool raise = mx > m_used + AT_LAZY;      // first tile: m_used = -inf -> true (mx is finite or -1e30)
+            float alpha = 1.0f;
+            if (raise) {
+                alpha = ex2_approx(m_used - mx);           // first tile: 0
+                m_used = mx;
+                l_run *= alpha;
+            }
+            if (g > 0) {
+                // PV(g-1) must be complete before P is overwritten and before O is rescaled
+                mbar_wait(pv_done, (g - 1) & 1);
+                tc_fence_after();
+            }
+            if (t > 0 && __any_sync(0xffffffffu, raise)) {
+                const uint32_t tmem_orow = tmem_o + lane_field + hsel * 64;
+#pragma unroll 1
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_orow + c * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
+                    tmem_st_32x32(tmem_orow + c * 32, v);
+                }
+                tmem_st_wait();
+            }
+            // ---- p = 2^(x - m_used) -> bf16 -> P tile in shared memory; row sum
+            const float neg_m = -m_used;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float psum = 0.f;
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(sv[c][j]), xs, neg_m));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(sv[c][j + 1]), xs, neg_m));
+                    psum += p0 + p1;
+                    pk[j >> 1] = pack_bf16(p0, p1);
+                }
+                l_run += psum;
+                uint8_t* prow = sP + (c >> 1) * AT_SLAB;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4*>(prow + swz128(r, (c & 1) * 4 + j)) =
+                        make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            }
+            tc_fence_before();               // orders the O rescale (tcgen05.st) before the issuer's next MMA
+            fence_proxy_async_smem();        // P writes -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_ready);
+
+            if (t == 0 && it + 1 < my_items) {
+                // Q2 of the next item (its buffer was last read by item it-1, long finished)
+                if (it >= 1) mbar_wait(&q_free[(it + 1) & 1], ((it - 1) >> 1) & 1);
+                store_q(it + 1, qv);
+            }
+            if (t == T - 1) {
+                // ---- finalize: O / l -> bf16 -> global (this row's head: 64 contiguous columns = 128 B)
+                mbar_wait(pv_done, g & 1);
+                tc_fence_after();
+                const float inv = 1.0f / l_run;
+                const uint32_t tmem_orow = tmem_o + lane_field + hsel * 64;
+                __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.nq + qrow) * p.ldo + (2 * hp + hsel) * 64;
+#pragma unroll 1
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_orow + c * 32, v);
+                    tmem_ld_wait();
+                    if (c == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(o_free);
+                    }
+                    if (qrow < p.nq) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<uint4*>(dst + c * 32 + j * 8) = make_uint4(
+                                pack_bf16(__uint_as_float(v[8 * j]) * inv, __uint_as_float(v[8 * j + 1]) * inv),
+                                pack_bf16(__uint_as_float(v[8 * j + 2]) * inv, __uint_as_float(v[8 * j + 3]) * inv),
+                                pack_bf16(__uint_as_float(v[8 * j + 4]) * inv, __uint_as_float(v[8 * j + 5]) * inv),
+                                pack_bf16(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv));
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp_idx == 5) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+bool attention_tc_supported(long long num_heads, long long nq, long long nk, long long head_dim, long long ldk,
+                            long long ldv, long long kv_batch_rows) {
+    return head_dim == 64 && nq <= 64 && (num_heads % 2) == 0 && nk > 64 && ldk % 8 == 0 && ldv % 8 == 0 &&
+           kv_batch_rows >= nk;
+}
+
+int attention_tc(const void* q, long long ldq, long long q_batch_rows, const void* k, long long ldk, const void* v,
+                 long long ldv, long long kv_batch_rows, const float* key_mask, void* out, long long ldo, long long batch,
+                 long long num_heads, long long nq, long long nk, float scale, cudaStream_t stream) {
+    if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(k) & 15) ||
+        (reinterpret_cast<uintptr_t>(v) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || ldq % 8 != 0 || ldo % 8 != 0 ||
+        batch * kv_batch_rows > 2147483647LL) {
+        set_last_error("attention (tcgen05): pointers must be 16-byte aligned, row strides multiples of 8");
+        return UNIREC_ERR_BAD_ARG;
+    }
+    AttnTcParams p;
+    p.q = reinterpret_cast<const __nv_bfloat16*>(q); p.ldq = ldq; p.q_batch_rows = q_batch_rows;
+    p.key_mask = key_mask;
+    p.out = reinterpret_cast<__nv_bfloat16*>(out); p.ldo = ldo;
+    p.num_heads = static_cast<int>(num_heads); p.nq = static_cast<int>(nq); p.nk = static_cast<int>(nk);
+    p.kv_batch_rows = static_cast<int>(kv_batch_rows);
+    p.scale_log2 = scale * 1.4426950408889634f;
+    p.num_items = static_cast<int>(batch * (num_heads / 2));
+    CUtensorMap tk, tv;
+    int rc = make_tmap_bf16_2d(&tk, k, batch * kv_batch_rows, num_heads * 64, ldk, AT_KT);
+    if (rc != UNIREC_OK) return rc;
+    rc = make_tmap_bf16_2d(&tv, v, batch * kv_batch_rows, num_heads * 64, ldv, AT_KT);
+    if (rc != UNIREC_OK) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
+        if (e != cudaSuccess) {
+            set_last_error("attention (tcgen05): cudaFuncSetAttribute(%d): %s", AT_SMEM_BYTES, cudaGetErrorString(e));
+            return UNIREC_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    int grid = num_sms() > 0 ? num_sms() : 148;
+    if (grid > p.num_items) grid = p.num_items;
+    attention_tc_kernel<<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tk, tv, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_last_error("attention (tcgen05) launch: %s", cudaGetErrorString(e));
+        return UNIREC_ERR_CUDA;
+    }
+    return UNIREC_OK;
+}
+
+}  // namespace unirec
