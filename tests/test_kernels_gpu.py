@@ -147,6 +147,22 @@ def test_layernorm(H, in_dtype):
     torch.testing.assert_close(out_b, ref_b, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("H", [256, 1024])
+def test_layernorm_streaming_fast_path(H):
+    """bf16 in, no residual, >= 4096 rows: persistent kernel with register prefetch of the next row."""
+    from unirec_b200 import ops
+    rows = 5003
+    wide = _randn(rows, H + 64, seed=14, scale=2.0, dtype=torch.bfloat16)
+    x = wide[:, :H]                                   # strided rows
+    g = _randn(H, seed=15, scale=0.1) + 1.0
+    b = _randn(H, seed=16, scale=0.1)
+    ref = F.layer_norm(x.float(), (H,), g, b, 1e-12)
+    out = ops.layernorm(x, g, b, 1e-12, out_dtype=torch.float32)
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5)
+    out_b = ops.layernorm(x, g, b, 1e-12)
+    torch.testing.assert_close(out_b.float(), ref, rtol=1e-2, atol=2e-2)
+
+
 # ------------------------------------------------------------------------------------- attention
 def _ref_attention(q, k, v, mask, heads):
     B, nq, hd = q.shape

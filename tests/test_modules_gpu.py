@@ -129,6 +129,39 @@ def test_item_qformer_against_oracle_larger_batch():
                mean_tol=0.02, cos_tol=0.999)
 
 
+def test_full_size_models_at_bench_settings_against_oracle():
+    """Reference-sized models at batch sizes large enough that every projection takes the production kernels
+    (CTA-pair tcgen05 GEMM with the TMA-store epilogue, tcgen05 cross-attention for the 1600-key user sequence)
+    and with the bench.py settings (bf16 pre-LayerNorm buffers, bf16 outputs); oracle = fp32 on the host CPU."""
+    from oracle import qformer_oracle as O
+    from unirec_b200.modules import QFormerForItemRepresentation, UserQFormer
+    c = ITEM_CASES["full"]
+    mk = c["model"]
+    sd = synth.item_qformer_state_dict(**mk, seed=41, attn_std=0.03)
+    model = QFormerForItemRepresentation(num_fields=mk["num_fields"])
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).eval()
+    model.prelayernorm_dtype = torch.bfloat16
+    B = 160          # M = 5120 query rows: 20 x 4 tiles of 256 x 256 >= 74 SM pairs for every GEMM of the layer
+    x, mask = synth.item_fields(batch=B, num_fields=14, dim=1024, seed=42, clip_field=7, presence=0.8, all_masked_row=5)
+    tok = model.encode_query_tokens(x.to(DEV), mask.to(DEV))
+    sub = torch.arange(0, B, 8)                      # oracle on 20 of the 160 items (items are independent)
+    ref = O.item_qformer_forward(sd, x[sub], mask[sub], num_heads=c["heads"])["query_outputs"]
+    _check("item[full,B=160,bench settings].query_outputs", tok[sub.to(DEV)], ref)
+
+    cu = USER_CASES["full"]
+    mu = cu["model"]
+    usd = synth.user_qformer_state_dict(**mu, seed=43, attn_std=0.03)
+    um = UserQFormer()
+    um.load_state_dict(usd, strict=True)
+    um = um.to(DEV).eval()
+    um.prelayernorm_dtype = torch.bfloat16
+    xs, ms = synth.user_sequences(batch=6, max_items=50, tokens_per_item=32, dim=1024, seed=44, ragged=True)
+    out = um(xs.to(torch.bfloat16).to(DEV), ms.to(DEV))
+    refu = O.user_qformer_forward(usd, xs.to(torch.bfloat16).float(), ms, num_heads=cu["heads"], num_item_tokens_to_predict=32)
+    _check("user[full,B=6,S=1600,bench settings]", out, refu, max_tol=0.1, mean_tol=0.015, cos_tol=0.9995)
+
+
 def test_train_mode_with_dropout_is_refused():
     from unirec_b200.modules import QFormerForItemRepresentation
     m = QFormerForItemRepresentation(hidden_size=256, num_hidden_layers=2, num_attention_heads=4,

@@ -90,6 +90,89 @@ layernorm_kernel(const void* __restrict__ x_, long long ldx, int in_row_mod, con
     }
 }
 
+// Fast path for the layer outputs of the encoder (bf16 in, no residual, no row broadcast): persistent warps, the
+// NEXT row's 16-byte loads are issued before the current row is reduced and normalised, and the row is kept
+// packed (bf16 pairs) in registers, so that each SM keeps ~128 KB of loads in flight without a bubble between
+// the load and the store phase of a row.
+template <int MAX_VEC>
+__global__ void __launch_bounds__(256)
+layernorm_bf16_stream_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+                             const float* __restrict__ beta, float eps, void* __restrict__ out_, long long ldo,
+                             int out_fp32, int rows, int H) {
+    const int lane = threadIdx.x & 31;
+    const int warps_total = (gridDim.x * blockDim.x) >> 5;
+    int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nvec = H / 8;
+    uint4 cur[MAX_VEC], nxt[MAX_VEC];
+    auto load = [&](int r, uint4 (&dst)[MAX_VEC]) {
+#pragma unroll
+        for (int i = 0; i < MAX_VEC; ++i) {
+            const int vi = lane + i * 32;
+            dst[i] = (vi < nvec) ? __ldg(reinterpret_cast<const uint4*>(x + static_cast<long long>(r) * ldx) + vi)
+                                 : make_uint4(0, 0, 0, 0);
+        }
+    };
+    if (row < rows) load(row, cur);
+    const float inv_h = 1.0f / static_cast<float>(H);
+    while (row < rows) {
+        const int next = row + warps_total;
+        if (next < rows) load(next, nxt);
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAX_VEC; ++i) {
+            const uint32_t w[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sum += bf16_lo(w[j]) + bf16_hi(w[j]);     // padding lanes hold zeros
+        }
+        const float mean = warp_sum(sum) * inv_h;
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAX_VEC; ++i) {
+            if (lane + i * 32 < nvec) {
+                const uint32_t w[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float d0 = bf16_lo(w[j]) - mean, d1 = bf16_hi(w[j]) - mean;
+                    sq = fmaf(d0, d0, sq);
+                    sq = fmaf(d1, d1, sq);
+                }
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(sq) * inv_h + eps);
+#pragma unroll
+        for (int i = 0; i < MAX_VEC; ++i) {
+            const int vi = lane + i * 32;
+            if (vi < nvec) {
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8) + 1);
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8) + 1);
+                const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                const uint32_t w[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
+                float y[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    y[2 * j] = (bf16_lo(w[j]) - mean) * rstd * g[2 * j] + b[2 * j];
+                    y[2 * j + 1] = (bf16_hi(w[j]) - mean) * rstd * g[2 * j + 1] + b[2 * j + 1];
+                }
+                if (out_fp32) {
+                    float* o = reinterpret_cast<float*>(out_) + static_cast<long long>(row) * ldo + vi * 8;
+                    *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+                    *(reinterpret_cast<float4*>(o) + 1) = make_float4(y[4], y[5], y[6], y[7]);
+                } else {
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_) + static_cast<long long>(row) * ldo + vi * 8;
+                    *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]),
+                                                              pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < MAX_VEC; ++i) cur[i] = nxt[i];
+        row = next;
+    }
+}
+
 int layernorm(const void* x, int x_fp32, long long ldx, int in_row_mod, const void* residual, long long ldres,
               const float* gamma, const float* beta, float eps, void* out, int out_fp32, long long ldo,
               long long rows, long long H, cudaStream_t stream) {
@@ -101,6 +184,35 @@ int layernorm(const void* x, int x_fp32, long long ldx, int in_row_mod, const vo
     const int threads = 256;
     const long long blocks = (rows * 32 + threads - 1) / threads;
     const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(residual);
+    if (!x_fp32 && res == nullptr && in_row_mod == 0 && H <= 1024 && rows >= 4096) {
+        // streaming fast path: persistent grid, 4 CTAs of 8 warps per SM
+        static int per_sm_1 = 0, per_sm_4 = 0, sms = 0;
+        if (sms == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_1, layernorm_bf16_stream_kernel<1>, threads, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_4, layernorm_bf16_stream_kernel<4>, threads, 0);
+            if (per_sm_1 < 1) per_sm_1 = 1;
+            if (per_sm_4 < 1) per_sm_4 = 1;
+            if (sms < 1) sms = 148;
+        }
+        long long grid = static_cast<long long>(sms) * (H <= 256 ? per_sm_1 : per_sm_4);
+        if (grid > blocks) grid = blocks;
+        const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+        if (H <= 256)
+            layernorm_bf16_stream_kernel<1><<<static_cast<unsigned>(grid), threads, 0, stream>>>(xb, ldx, gamma, beta, eps, out, ldo,
+                                                                                              out_fp32, (int)rows, (int)H);
+        else
+            layernorm_bf16_stream_kernel<4><<<static_cast<unsigned>(grid), threads, 0, stream>>>(xb, ldx, gamma, beta, eps, out, ldo,
+                                                                                              out_fp32, (int)rows, (int)H);
+        cudaError_t e2 = cudaGetLastError();
+        if (e2 != cudaSuccess) {
+            set_last_error("layernorm launch: %s", cudaGetErrorString(e2));
+            return UNIREC_ERR_CUDA;
+        }
+        return UNIREC_OK;
+    }
 #define UNIREC_LN(MV)                                                                                      \
     if (x_fp32)                                                                                            \
         layernorm_kernel<true, MV><<<blocks, threads, 0, stream>>>(x, ldx, in_row_mod, res, ldres, gamma, beta, eps, \
