@@ -117,6 +117,43 @@ int unirec_score_topk(const void* users, int64_t ldu, const float* user_inv,
 int unirec_topk_merge(const float* in_scores, const int64_t* in_idx, int64_t G, int64_t B, int64_t k,
                       float* out_scores, int64_t* out_idx, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Backward pass of the item Q-Former training step (training/item_qformer_training.py:129,
+ * loss.backward(); dropout disabled).  Gradients of activations are bf16, of parameters fp32.
+ * ------------------------------------------------------------------------------------------- */
+
+/* out[M,N] (+)= sum_k A(m,k) B(n,k), bf16 operands, fp32 accumulation (tcgen05).  Per operand:
+ *   a_mn = 0: A stored [M, K] row-major;  a_mn = 1: A stored [K, M] row-major
+ *   b_mn = 0: B stored [N, K] row-major;  b_mn = 1: B stored [K, N] row-major
+ * dgrad of y = x W^T:  dx = gemm(A = dy, a_mn 0, B = W [N,K_in], b_mn 1);  wgrad: dW = gemm(A = dy [rows,N], a_mn 1,
+ * B = x [rows,K_in], b_mn 1, accumulate 1).  accumulate = 1 needs fp32 out and adds with fp32 atomics; the
+ * contraction is then split over ksplit CTAs per tile (0 = auto).  K % 8 == 0, N % 8 == 0, 16-byte aligned rows. */
+int unirec_gemm_general(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn,
+                        void* out, int64_t ldo, int out_fp32, int accumulate,
+                        int64_t M, int64_t N, int64_t K, int ksplit, void* stream);
+
+/* out = gelu_erf(z) / dz = da * gelu_erf'(z), bf16, n % 8 == 0 (models/qformer.py:360 with the pre-activation kept). */
+int unirec_gelu_forward(const void* z, void* out, int64_t n, void* stream);
+int unirec_gelu_backward(const void* z, const void* da, void* dz, int64_t n, void* stream);
+
+/* out[n] += sum_rows x[row, n]  (bias gradients); x bf16 [rows, N] row stride ld, out fp32 [N] (atomic accumulate). */
+int unirec_colsum(const void* x, int64_t ld, int64_t rows, int64_t N, float* out, void* stream);
+
+/* LayerNorm backward over the last dim H <= 1024: x = the LayerNorm INPUT (bf16), dy (+ optional dy2) = gradient of
+ * its output, dx bf16, dgamma / dbeta fp32 [H] atomically accumulated (models/qformer.py:104, :288, :374). */
+int unirec_layernorm_backward(const void* x, int64_t ldx, const void* dy, int64_t lddy, const void* dy2, int64_t lddy2,
+                              const float* gamma, float eps, void* dx, int64_t lddx, float* dgamma, float* dbeta,
+                              int64_t rows, int64_t H, void* stream);
+
+/* Backward of unirec_attention for nq <= 64 and nk <= 64 (item self- and cross-attention): dq/dk/dv bf16 with the
+ * layouts of q/k/v (row strides lddq/lddk/lddv); probabilities are recomputed from q, k and key_mask. */
+int unirec_attention_backward(const void* q, int64_t ldq, int64_t q_batch_rows,
+                              const void* k, int64_t ldk, const void* v, int64_t ldv, int64_t kv_batch_rows,
+                              const float* key_mask, const void* dout, int64_t lddo,
+                              void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                              int64_t batch, int64_t num_heads, int64_t nq, int64_t nk, int64_t head_dim,
+                              float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,16 @@ _SIGNATURES = {
     "unirec_score_topk": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64,
                                   c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "unirec_topk_merge": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "unirec_gemm_general": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int,
+                                    c_int64, c_int64, c_int64, c_int, c_void_p]),
+    "unirec_gelu_forward": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "unirec_gelu_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "unirec_colsum": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "unirec_layernorm_backward": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_float,
+                                          c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    "unirec_attention_backward": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64,
+                                          c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                                          c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

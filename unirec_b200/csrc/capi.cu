@@ -27,6 +27,21 @@ int attention(const void* q, long long ldq, long long q_batch_rows, const void* 
               long long ldv, long long kv_batch_rows, const float* key_mask, void* out, long long ldo, long long batch,
               long long num_heads, long long nq, long long nk, long long head_dim, float scale, cudaStream_t stream);
 
+int gemm_bf16_general(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, void* out,
+                      long long ldo, int out_fp32, int accumulate, long long M, long long N, long long K, int ksplit,
+                      cudaStream_t stream);
+int gelu_forward(const void* z, void* out, long long n, cudaStream_t stream);
+int gelu_backward(const void* z, const void* da, void* dz, long long n, cudaStream_t stream);
+int colsum(const void* x, long long ld, long long rows, long long N, float* out, cudaStream_t stream);
+int layernorm_backward(const void* x, long long ldx, const void* dy, long long lddy, const void* dy2, long long lddy2,
+                       const float* gamma, float eps, void* dx, long long lddx, float* dgamma, float* dbeta,
+                       long long rows, long long H, cudaStream_t stream);
+int attention_backward(const void* q, long long ldq, long long q_batch_rows, const void* k, long long ldk, const void* v,
+                       long long ldv, long long kv_batch_rows, const float* key_mask, const void* dout, long long lddo,
+                       void* dq, long long lddq, void* dk, long long lddk, void* dv, long long lddv, long long batch,
+                       long long num_heads, long long nq, long long nk, long long head_dim, float scale,
+                       cudaStream_t stream);
+
 std::atomic<long long> g_launch_count{0};
 }  // namespace unirec
 
@@ -90,6 +105,40 @@ int unirec_build_user_sequence(const void* table, int64_t num_items, const int64
 int unirec_inv_l2_norm(const void* x, int x_fp32, int64_t ldx, float* inv, int64_t rows, int64_t D, float eps,
                        void* stream) {
     COUNTED(inv_l2_norm(x, x_fp32, ldx, inv, rows, D, eps, static_cast<cudaStream_t>(stream)));
+}
+
+int unirec_gemm_general(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* out,
+                        int64_t ldo, int out_fp32, int accumulate, int64_t M, int64_t N, int64_t K, int ksplit,
+                        void* stream) {
+    COUNTED(gemm_bf16_general(A, lda, a_mn, B, ldb, b_mn, out, ldo, out_fp32, accumulate, M, N, K, ksplit,
+                              static_cast<cudaStream_t>(stream)));
+}
+
+int unirec_gelu_forward(const void* z, void* out, int64_t n, void* stream) {
+    COUNTED(gelu_forward(z, out, n, static_cast<cudaStream_t>(stream)));
+}
+
+int unirec_gelu_backward(const void* z, const void* da, void* dz, int64_t n, void* stream) {
+    COUNTED(gelu_backward(z, da, dz, n, static_cast<cudaStream_t>(stream)));
+}
+
+int unirec_colsum(const void* x, int64_t ld, int64_t rows, int64_t N, float* out, void* stream) {
+    COUNTED(colsum(x, ld, rows, N, out, static_cast<cudaStream_t>(stream)));
+}
+
+int unirec_layernorm_backward(const void* x, int64_t ldx, const void* dy, int64_t lddy, const void* dy2, int64_t lddy2,
+                              const float* gamma, float eps, void* dx, int64_t lddx, float* dgamma, float* dbeta,
+                              int64_t rows, int64_t H, void* stream) {
+    COUNTED(layernorm_backward(x, ldx, dy, lddy, dy2, lddy2, gamma, eps, dx, lddx, dgamma, dbeta, rows, H,
+                               static_cast<cudaStream_t>(stream)));
+}
+
+int unirec_attention_backward(const void* q, int64_t ldq, int64_t q_batch_rows, const void* k, int64_t ldk, const void* v,
+                              int64_t ldv, int64_t kv_batch_rows, const float* key_mask, const void* dout, int64_t lddo,
+                              void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t batch,
+                              int64_t num_heads, int64_t nq, int64_t nk, int64_t head_dim, float scale, void* stream) {
+    COUNTED(attention_backward(q, ldq, q_batch_rows, k, ldk, v, ldv, kv_batch_rows, key_mask, dout, lddo, dq, lddq, dk, lddk,
+                               dv, lddv, batch, num_heads, nq, nk, head_dim, scale, static_cast<cudaStream_t>(stream)));
 }
 
 }  // extern "C"

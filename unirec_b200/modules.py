@@ -247,8 +247,8 @@ class QFormerBackbone(nn.Module):
 def _check_inference_mode(module: nn.Module, dropout: float):
     if module.training and dropout > 0.0:
         raise NotImplementedError(
-            "unirec_b200: the CUDA forward implements eval-mode semantics (dropout = identity); call .eval() "
-            "or construct with dropout=0.0.  Train-mode dropout and the backward kernels are not built yet.")
+            "unirec_b200: the CUDA path implements dropout = identity; call .eval(), or construct the module with "
+            "dropout=0.0 to train (forward + backward kernels; unirec_b200/training.py).")
 
 
 class QFormerForItemRepresentation(nn.Module):
@@ -299,9 +299,30 @@ class QFormerForItemRepresentation(nn.Module):
         return self.qformer.encode(self.query_embeddings, field_embeddings, attention_mask, out_dtype,
                                    self.prelayernorm_dtype)
 
-    @torch.no_grad()
+    def _forward_train(self, field_embeddings, attention_mask):
+        """Differentiable forward (models/qformer_utils.py:37-60 under autograd): backbone = BackboneTrainFn,
+        heads = LinearFn (tcgen05 fwd / dgrad / wgrad), the 32 -> num_fields projection in torch (0.9 GFLOP/1024 items)."""
+        from .training import BackboneTrainFn, LinearFn
+        bb = self.qformer
+        qo = BackboneTrainFn.apply(bb, field_embeddings, attention_mask, self.query_embeddings, *bb._live_params())
+        B, Q, H = qo.shape
+        qo16 = qo.to(torch.bfloat16)
+        rep = LinearFn.apply(qo16.mean(dim=1).to(torch.bfloat16), self.item_representation_head.weight,
+                             self.item_representation_head.bias).float()
+        rec = LinearFn.apply(qo16.reshape(B * Q, H), self.reconstruction_head.weight,
+                             self.reconstruction_head.bias).view(B, Q, -1).float()
+        fields = torch.nn.functional.linear(rec.transpose(1, 2), self.field_projection.weight,
+                                            self.field_projection.bias).transpose(1, 2)
+        return {"query_outputs": qo, "item_representation": rep, "reconstructed_fields": fields}
+
     def forward(self, field_embeddings: torch.Tensor, attention_mask: torch.Tensor = None) -> Dict[str, torch.Tensor]:
         _check_inference_mode(self, self.config.hidden_dropout_prob)
+        if self.training and torch.is_grad_enabled():
+            return self._forward_train(field_embeddings, attention_mask)
+        with torch.no_grad():
+            return self._forward_eval(field_embeddings, attention_mask)
+
+    def _forward_eval(self, field_embeddings: torch.Tensor, attention_mask: torch.Tensor = None) -> Dict[str, torch.Tensor]:
         od = self.output_dtype
         query_outputs = self.qformer.encode(self.query_embeddings, field_embeddings, attention_mask, od,
                                             self.prelayernorm_dtype)

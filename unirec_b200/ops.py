@@ -287,3 +287,113 @@ def topk_merge(scores: torch.Tensor, idx: torch.Tensor) -> Tuple[torch.Tensor, t
                                        _stream())
     _lib.check(rc, "unirec_topk_merge")
     return out_s, out_i
+
+
+# ------------------------------------------------------------------------------------------------
+# Backward-pass ops of the item Q-Former training step (C ABI: "Backward pass" block of the header)
+# ------------------------------------------------------------------------------------------------
+def gemm_general(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool, b_mn: bool, M: int, N: int, K: int,
+                 out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16,
+                 accumulate: bool = False, ksplit: int = 0) -> torch.Tensor:
+    """out[M,N] (+)= sum_k A(m,k) B(n,k).  a is stored [M,K] (a_mn False) or [K,M] (a_mn True); b is stored
+    [N,K] (b_mn False) or [K,N] (b_mn True); 2-D row views with contiguous last dim."""
+    _req(a, torch.bfloat16, "gemm_general.a")
+    _req(b, torch.bfloat16, "gemm_general.b")
+    if a.dim() != 2 or b.dim() != 2:
+        raise RuntimeError("gemm_general: operands must be 2-D row views")
+    if tuple(a.shape) != ((K, M) if a_mn else (M, K)) or tuple(b.shape) != ((K, N) if b_mn else (N, K)):
+        raise RuntimeError(f"gemm_general: operand shapes {tuple(a.shape)}, {tuple(b.shape)} do not match M={M} N={N} K={K}")
+    if out is None:
+        if accumulate:
+            raise RuntimeError("gemm_general: accumulate needs an existing fp32 out tensor")
+        out = torch.empty(M, N, device=a.device, dtype=out_dtype)
+    if out.dim() != 2 or tuple(out.shape) != (M, N) or out.stride(1) != 1:
+        raise RuntimeError("gemm_general: out must be a 2-D [M, N] row view")
+    if out.dtype not in (torch.bfloat16, torch.float32) or (accumulate and out.dtype != torch.float32):
+        raise RuntimeError("gemm_general: out must be bf16 or fp32 (fp32 when accumulating)")
+    with _Timed("gemm", 2.0 * M * N * K):
+        rc = _lib.load().unirec_gemm_general(a.data_ptr(), a.stride(0), 1 if a_mn else 0, b.data_ptr(), b.stride(0),
+                                             1 if b_mn else 0, out.data_ptr(), out.stride(0),
+                                             1 if out.dtype == torch.float32 else 0, 1 if accumulate else 0, M, N, K,
+                                             ksplit, _stream())
+    _lib.check(rc, "unirec_gemm_general")
+    return out
+
+
+def linear_dgrad(dy: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """dx[M, K_in] = dy[M, N] @ weight[N, K_in]  (weight bf16 as stored by nn.Linear)."""
+    M, N = dy.shape
+    return gemm_general(dy, weight, a_mn=False, b_mn=True, M=M, N=weight.shape[1], K=N)
+
+
+def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor) -> torch.Tensor:
+    """dw[N, K_in] += dy[rows, N]^T @ x[rows, K_in]  (dw fp32, accumulated with atomics; zero it first)."""
+    rows, N = dy.shape
+    return gemm_general(dy, x, a_mn=True, b_mn=True, M=N, N=x.shape[1], K=rows, out=dw, accumulate=True)
+
+
+def gelu(z: torch.Tensor) -> torch.Tensor:
+    _req(z, torch.bfloat16, "gelu.z")
+    z = z.contiguous()
+    out = torch.empty_like(z)
+    rc = _lib.load().unirec_gelu_forward(z.data_ptr(), out.data_ptr(), z.numel(), _stream())
+    _lib.check(rc, "unirec_gelu_forward")
+    return out
+
+
+def gelu_backward(z: torch.Tensor, da: torch.Tensor) -> torch.Tensor:
+    _req(z, torch.bfloat16, "gelu_backward.z")
+    _req(da, torch.bfloat16, "gelu_backward.da")
+    if not (z.is_contiguous() and da.is_contiguous()) or z.shape != da.shape:
+        raise RuntimeError("gelu_backward: z and da must be contiguous and of the same shape")
+    dz = torch.empty_like(z)
+    rc = _lib.load().unirec_gelu_backward(z.data_ptr(), da.data_ptr(), dz.data_ptr(), z.numel(), _stream())
+    _lib.check(rc, "unirec_gelu_backward")
+    return dz
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[n] += sum_rows x[row, n]; x bf16 2-D row view, out fp32 [N]."""
+    _req(x, torch.bfloat16, "colsum.x")
+    _req(out, torch.float32, "colsum.out")
+    rows, N = x.shape
+    rc = _lib.load().unirec_colsum(x.data_ptr(), x.stride(0), rows, N, out.data_ptr(), _stream())
+    _lib.check(rc, "unirec_colsum")
+    return out
+
+
+def layernorm_backward(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, eps: float, dgamma: torch.Tensor,
+                       dbeta: torch.Tensor, dy2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x = LayerNorm input (bf16 [rows, H]), dy (+ dy2) = gradient of its output; returns dx bf16 and accumulates
+    dgamma / dbeta (fp32 [H])."""
+    for t_, n in ((x, "x"), (dy, "dy")):
+        _req(t_, torch.bfloat16, f"layernorm_backward.{n}")
+    rows, H, ldx = _rows2d(x, "layernorm_backward.x")
+    _, _, lddy = _rows2d(dy, "layernorm_backward.dy")
+    lddy2 = 0
+    if dy2 is not None:
+        _req(dy2, torch.bfloat16, "layernorm_backward.dy2")
+        _, _, lddy2 = _rows2d(dy2, "layernorm_backward.dy2")
+    dx = torch.empty(rows, H, device=x.device, dtype=torch.bfloat16)
+    rc = _lib.load().unirec_layernorm_backward(x.data_ptr(), ldx, dy.data_ptr(), lddy, _ptr(dy2), lddy2, gamma.data_ptr(),
+                                               float(eps), dx.data_ptr(), H, dgamma.data_ptr(), dbeta.data_ptr(), rows, H,
+                                               _stream())
+    _lib.check(rc, "unirec_layernorm_backward")
+    return dx
+
+
+def attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, dout: torch.Tensor, dq: torch.Tensor,
+                       dk: torch.Tensor, dv: torch.Tensor, *, batch: int, num_heads: int, nq: int, nk: int,
+                       key_mask: Optional[torch.Tensor] = None):
+    """Backward of `attention` for nq, nk <= 64; dq/dk/dv are preallocated bf16 row views (written in place)."""
+    for t_, n in ((q, "q"), (k, "k"), (v, "v"), (dout, "dout"), (dq, "dq"), (dk, "dk"), (dv, "dv")):
+        _req(t_, torch.bfloat16, f"attention_backward.{n}")
+        if t_.dim() != 2:
+            raise RuntimeError("attention_backward: tensors must be 2-D row views")
+    if key_mask is not None:
+        _req(key_mask, torch.float32, "attention_backward.key_mask")
+    rc = _lib.load().unirec_attention_backward(q.data_ptr(), q.stride(0), nq, k.data_ptr(), k.stride(0), v.data_ptr(),
+                                               v.stride(0), nk, _ptr(key_mask), dout.data_ptr(), dout.stride(0),
+                                               dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(),
+                                               dv.stride(0), batch, num_heads, nq, nk, 64, 0.125, _stream())
+    _lib.check(rc, "unirec_attention_backward")

@@ -1,0 +1,237 @@
+"""Training path of the item Q-Former (BASELINE config 2: forward + backward, data-parallel gradient all-reduce).
+
+Reference step (training/item_qformer_training.py:117-131): out = model(fields, mask); loss = QFormerLoss(...);
+loss.backward(); optimizer.step().  Here the backbone (99.4 % of the FLOPs) is ONE torch.autograd.Function whose
+forward runs the fused sm_100a kernels and keeps the bf16 activations, and whose backward is written out by hand
+on the backward kernels of the C ABI: tcgen05 dgrad / wgrad GEMMs that read nn.Linear weights and activations in
+place (MN-major operands, no transposes), fp32 split-K accumulation of weight gradients, LayerNorm / erf-GELU /
+small-tile attention backward kernels.  Heads are `LinearFn` (same GEMM kernels).  Loss, optimizer (AdamW) and the
+NCCL all-reduce stay in PyTorch.
+
+Dropout: the CUDA path implements dropout = identity.  `model.train()` is accepted only with dropout = 0.0
+(parity of a random mask is undefined anyway); construct the module with dropout=0.0 for training.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional
+
+import torch
+
+from . import ops
+
+
+def _f32(t):
+    return t.detach().float().contiguous()
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b on the tcgen05 GEMM; x bf16 [M, K], W / b fp32 parameters; y bf16."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        w16 = weight.detach().to(torch.bfloat16).contiguous()
+        ctx.save_for_backward(x, w16)
+        ctx.has_bias = bias is not None
+        return ops.linear(x, w16, None if bias is None else _f32(bias))
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w16 = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = ops.linear_dgrad(dy, w16) if ctx.needs_input_grad[0] else None
+        dw = torch.zeros(w16.shape, device=dy.device, dtype=torch.float32)
+        ops.linear_wgrad(dy, x, dw)
+        db = None
+        if ctx.has_bias:
+            db = torch.zeros(w16.shape[0], device=dy.device, dtype=torch.float32)
+            ops.colsum(dy, db)
+        return dx, dw, db
+
+
+class BackboneTrainFn(torch.autograd.Function):
+    """last_hidden_state = BertModel(query_embeds=queries, encoder_hidden_states=enc, ...) with hand-written
+    backward (models/qformer.py:804-972 under autograd).  Inputs after `mask` are the live parameters in the order
+    of QFormerBackbone._live_params(); gradients are returned in the same order."""
+
+    @staticmethod
+    def forward(ctx, backbone, enc, mask, query_embeddings, *params):
+        cfg = backbone.config
+        B, S, E = enc.shape
+        H, heads = cfg.hidden_size, cfg.num_attention_heads
+        Q = query_embeddings.shape[1]
+        pk = backbone.packed()
+        enc2 = ops.cast_bf16(enc.contiguous()).view(B * S, E)
+        m = None if mask is None else mask.to(device=enc.device, dtype=torch.float32).contiguous()
+        kv_all = ops.linear(enc2, pk["w_kv_all"], pk["b_kv_all"]) if pk["w_kv_all"] is not None else None
+        q0 = query_embeddings.detach().reshape(Q, H).float().contiguous()
+        h = ops.layernorm(q0, pk["emb_g"], pk["emb_b"], cfg.layer_norm_eps, rows=B * Q, in_row_mod=Q)
+        tape = []
+        for L in pk["layers"]:
+            t = {"h_in": h}
+            qkv = ops.linear(h, L["w_qkv"], L["b_qkv"])
+            ctxt = ops.attention(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], batch=B, num_heads=heads, nq=Q, nk=Q)
+            pre1 = ops.linear(ctxt, L["w_o"], L["b_o"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=h)
+            h = ops.layernorm(pre1, L["ln1_g"], L["ln1_b"], cfg.layer_norm_eps)
+            t.update(qkv=qkv, ctx=ctxt, pre1=pre1, h1=h)
+            if L["cross"]:
+                qc = ops.linear(h, L["w_qc"], L["b_qc"])
+                off = L["kv_slot"] * 2 * H
+                ctxc = ops.attention(qc, kv_all[:, off:off + H], kv_all[:, off + H:off + 2 * H], batch=B, num_heads=heads,
+                                     nq=Q, nk=S, key_mask=m)
+                pre2 = ops.linear(ctxc, L["w_oc"], L["b_oc"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=h)
+                h = ops.layernorm(pre2, L["ln2_g"], L["ln2_b"], cfg.layer_norm_eps)
+                t.update(qc=qc, ctxc=ctxc, pre2=pre2, h2=h)
+            z = ops.linear(h, L["w_1"], L["b_1"])
+            a = ops.gelu(z)
+            pre3 = ops.linear(a, L["w_2"], L["b_2"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=h)
+            h = ops.layernorm(pre3, L["ln3_g"], L["ln3_b"], cfg.layer_norm_eps)
+            t.update(z=z, a=a, pre3=pre3)
+            tape.append(t)
+        ctx.backbone, ctx.tape, ctx.kv_all, ctx.enc2, ctx.mask = backbone, tape, kv_all, enc2, m
+        ctx.dims = (B, S, Q, H, heads)
+        ctx.q0 = q0
+        return h.view(B, Q, H).float()
+
+    @staticmethod
+    def backward(ctx, d_out):
+        bb = ctx.backbone
+        cfg = bb.config
+        pk = bb.packed()
+        B, S, Q, H, heads = ctx.dims
+        I = cfg.intermediate_size
+        dev = d_out.device
+        eps = cfg.layer_norm_eps
+        M = B * Q
+        on_ready: Optional[Callable[[int, List[torch.Tensor]], None]] = getattr(bb, "grad_ready_hook", None)
+
+        def zeros(*shape):
+            return torch.zeros(*shape, device=dev, dtype=torch.float32)
+
+        def lin_bwd(dy, x, w16, need_dx=True):
+            dw = zeros(*w16.shape)
+            ops.linear_wgrad(dy, x, dw)
+            db = zeros(w16.shape[0])
+            ops.colsum(dy, db)
+            return (ops.linear_dgrad(dy, w16) if need_dx else None), dw, db
+
+        n_cross = sum(1 for L in pk["layers"] if L["cross"])
+        d_kv_all = torch.zeros(B * S, 2 * H * n_cross, device=dev, dtype=torch.bfloat16) if n_cross else None
+        dy = d_out.reshape(M, H).to(torch.bfloat16).contiguous()
+        dy2 = None
+        layer_grads = [None] * len(pk["layers"])
+        for li in range(len(pk["layers"]) - 1, -1, -1):
+            L, t = pk["layers"][li], ctx.tape[li]
+            g = {}
+            # ---- query FFN: h_out = LN3(a W2^T + b2 + h_mid), a = gelu(h_mid W1^T + b1)
+            g["ln3_g"], g["ln3_b"] = zeros(H), zeros(H)
+            dpre3 = ops.layernorm_backward(t["pre3"], dy, L["ln3_g"], eps, g["ln3_g"], g["ln3_b"], dy2=dy2)
+            da, g["w_2"], g["b_2"] = lin_bwd(dpre3, t["a"], L["w_2"])
+            dz = ops.gelu_backward(t["z"], da)
+            h_mid = t["h2"] if L["cross"] else t["h1"]
+            dh_mid, g["w_1"], g["b_1"] = lin_bwd(dz, h_mid, L["w_1"])
+            dy, dy2 = dpre3, dh_mid                       # gradient of h_mid = residual branch + FFN branch
+            if L["cross"]:
+                g["ln2_g"], g["ln2_b"] = zeros(H), zeros(H)
+                dpre2 = ops.layernorm_backward(t["pre2"], dy, L["ln2_g"], eps, g["ln2_g"], g["ln2_b"], dy2=dy2)
+                dctxc, g["w_oc"], g["b_oc"] = lin_bwd(dpre2, t["ctxc"], L["w_oc"])
+                off = L["kv_slot"] * 2 * H
+                dqc = torch.empty(M, H, device=dev, dtype=torch.bfloat16)
+                ops.attention_backward(t["qc"], ctx.kv_all[:, off:off + H], ctx.kv_all[:, off + H:off + 2 * H], dctxc, dqc,
+                                       d_kv_all[:, off:off + H], d_kv_all[:, off + H:off + 2 * H], batch=B, num_heads=heads,
+                                       nq=Q, nk=S, key_mask=ctx.mask)
+                dh1, g["w_qc"], g["b_qc"] = lin_bwd(dqc, t["h1"], L["w_qc"])
+                dy, dy2 = dpre2, dh1
+            # ---- self-attention block: h1 = LN1(ctx Wo^T + bo + h_in)
+            g["ln1_g"], g["ln1_b"] = zeros(H), zeros(H)
+            dpre1 = ops.layernorm_backward(t["pre1"], dy, L["ln1_g"], eps, g["ln1_g"], g["ln1_b"], dy2=dy2)
+            dctx, g["w_o"], g["b_o"] = lin_bwd(dpre1, t["ctx"], L["w_o"])
+            qkv = t["qkv"]
+            dqkv = torch.empty(M, 3 * H, device=dev, dtype=torch.bfloat16)
+            ops.attention_backward(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], dctx, dqkv[:, :H], dqkv[:, H:2 * H],
+                                   dqkv[:, 2 * H:], batch=B, num_heads=heads, nq=Q, nk=Q)
+            dh_in, g["w_qkv"], g["b_qkv"] = lin_bwd(dqkv, t["h_in"], L["w_qkv"])
+            dy, dy2 = dpre1, dh_in
+            layer_grads[li] = g
+            ctx.tape[li] = None                           # free this layer's activations
+            if on_ready is not None:
+                on_ready(li, [v for v in g.values()])
+        # ---- cross-attention K/V projection of all layers (one GEMM in the forward pass)
+        g_kv_w = g_kv_b = None
+        if n_cross:
+            _, g_kv_w, g_kv_b = lin_bwd(d_kv_all, ctx.enc2, pk["w_kv_all"], need_dx=False)
+        # ---- query-token LayerNorm (batch-invariant): sum over the batch, then a [Q, H] LayerNorm backward (torch)
+        dh0 = (dy.float() + dy2.float()).view(B, Q, H).sum(dim=0)
+        with torch.enable_grad():
+            q0 = ctx.q0.clone().requires_grad_(True)
+            eg = pk["emb_g"].clone().requires_grad_(True)
+            eb = pk["emb_b"].clone().requires_grad_(True)
+            torch.nn.functional.layer_norm(q0, (H,), eg, eb, eps).backward(dh0)
+        # ---- scatter into the order of _live_params()
+        grads = [eg.grad, eb.grad]
+        for li, L in enumerate(pk["layers"]):
+            g = layer_grads[li]
+            wq, wk, wv = g["w_qkv"][:H], g["w_qkv"][H:2 * H], g["w_qkv"][2 * H:]
+            bq, bk, bv = g["b_qkv"][:H], g["b_qkv"][H:2 * H], g["b_qkv"][2 * H:]
+            grads += [wq, bq, wk, bk, wv, bv, g["w_o"], g["b_o"], g["ln1_g"], g["ln1_b"]]
+            if L["cross"]:
+                off = L["kv_slot"] * 2 * H
+                grads += [g["w_qc"], g["b_qc"], g_kv_w[off:off + H], g_kv_b[off:off + H], g_kv_w[off + H:off + 2 * H],
+                          g_kv_b[off + H:off + 2 * H], g["w_oc"], g["b_oc"], g["ln2_g"], g["ln2_b"]]
+            grads += [g["w_1"], g["b_1"], g["w_2"], g["b_2"], g["ln3_g"], g["ln3_b"]]
+        if on_ready is not None and n_cross:
+            on_ready(-1, [g_kv_w, g_kv_b])
+        d_query = q0.grad.view(1, Q, H)
+        return (None, None, None, d_query) + tuple(grads)
+
+
+def qformer_loss(outputs, field_embeddings, attention_mask, pos_rep=None, neg_rep=None, recon_weight: float = 1.0,
+                 contrastive_weight: float = 0.25, margin: float = 0.5):
+    """QFormerLoss of the reference (training/item_qformer_training.py:41-56): masked MSE summed over the embedding
+    dimension and divided by the number of valid fields, plus contrastive_weight * TripletMarginLoss(margin, p=2)
+    on item_representation when positive / negative representations are given."""
+    rec = outputs["reconstructed_fields"].float()
+    mask = attention_mask.to(rec.dtype)
+    mse = (rec - field_embeddings.float()) ** 2
+    loss = recon_weight * (mse * mask.unsqueeze(-1)).sum() / mask.sum()
+    if pos_rep is not None and neg_rep is not None:
+        loss = loss + contrastive_weight * torch.nn.functional.triplet_margin_loss(
+            outputs["item_representation"].float(), pos_rep.float(), neg_rep.float(), margin=margin, p=2)
+    return loss
+
+
+class GradientAllReducer:
+    """Data-parallel gradient averaging for the training step.  The backbone's backward
+    calls `layer_ready` as soon as a layer's parameter gradients are complete; each call starts an asynchronous
+    NCCL all-reduce (one per tensor list, coalesced through a flat bucket), so communication overlaps the backward
+    of the remaining layers.  `finish()` waits for all of them and averages.  The 132.5 M never-executed parameters
+    (text branch, word / position embeddings) have no gradients and are never communicated."""
+
+    def __init__(self, group=None, bucket_dtype: torch.dtype = torch.float32):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.bucket_dtype = bucket_dtype
+        self.pending = []
+
+    def layer_ready(self, layer_index: int, tensors: List[torch.Tensor]):
+        if self.world == 1 or not tensors:
+            return
+        flat = torch.cat([t.reshape(-1).to(self.bucket_dtype) for t in tensors])
+        work = self.dist.all_reduce(flat, group=self.group, async_op=True)
+        self.pending.append((work, flat, tensors))
+
+    def extra(self, tensors: List[torch.Tensor]):
+        """Gradients produced outside the backbone (heads, query tokens, embedding LayerNorm)."""
+        self.layer_ready(-2, tensors)
+
+    def finish(self):
+        for work, flat, tensors in self.pending:
+            work.wait()
+            flat.div_(self.world)
+            off = 0
+            for t in tensors:
+                n = t.numel()
+                t.copy_(flat[off:off + n].view_as(t))
+                off += n
+        self.pending = []
