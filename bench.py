@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--top-k", type=int, default=100)
     ap.add_argument("--cpu-users", type=int, default=8, help="users in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-batch", type=int, default=1024, help="GLOBAL batch of the cfg-2 training block (0 = skip)")
+    ap.add_argument("--train-steps", type=int, default=4)
     ap.add_argument("--profile-range", default="", choices=["", "items", "users"],
                     help="bracket that timed region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     return ap.parse_args()
@@ -175,6 +177,74 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": value, "unit": "users/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
+
+
+# ------------------------------------------------------------------------------- cfg 2: training block
+def run_train_block(args, rank, world, dev, barrier, max_over_ranks, pk):
+    """BASELINE config 2: item Q-Former training step (fwd + QFormerLoss + bwd + gradient all-reduce + AdamW),
+    global batch args.train_batch split over the ranks (strong scaling), bf16 activations / fp32 master weights,
+    dropout 0 (the CUDA path's dropout is identity).  Returns the "train" block of the JSON line."""
+    import torch
+    from unirec_b200 import _lib, ops
+    from unirec_b200.modules import QFormerForItemRepresentation
+    from unirec_b200.training import GradientAllReducer, qformer_loss
+    Bg = args.train_batch
+    Bl = Bg // world
+    torch.manual_seed(0)
+    with torch.device(dev):
+        model = QFormerForItemRepresentation(num_fields=14, dropout=0.0).train()
+    opt = torch.optim.AdamW([p for p in model.parameters()], lr=1e-4, fused=True)
+    red = GradientAllReducer().attach(model.qformer)
+    head_params = (list(model.item_representation_head.parameters()) + list(model.reconstruction_head.parameters()) +
+                   list(model.field_projection.parameters()))
+    gen = torch.Generator(device=dev).manual_seed(4321 + rank)
+    nb = 3
+    fields = torch.randn(nb, Bl, 14, 1024, device=dev, generator=gen)
+    fields[:, :, 7, 768:] = 0
+    mask = torch.ones(Bl, 14, device=dev)
+    pos = torch.randn(Bl, 1024, device=dev, generator=gen)
+    neg = torch.randn(Bl, 1024, device=dev, generator=gen)
+
+    def step(i):
+        out = model(fields[i % nb], mask)
+        loss = qformer_loss(out, fields[i % nb], mask, pos, neg)
+        loss.backward()
+        red.reduce_params(head_params)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    for i in range(2):
+        step(i)
+    barrier()
+    l0 = _lib.launch_count()
+    ops.start_timing()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.train_steps):
+        loss = step(i)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / args.train_steps
+    stats = ops.stop_timing()
+    launches = (_lib.launch_count() - l0) // args.train_steps
+    gemm = stats.get("gemm")
+    ach = gemm[1] / (gemm[2] * 1e-3) / 1e12 if gemm and gemm[2] > 0 else None
+    items_per_sec = Bg / (ms * 1e-3)
+    del model, opt
+    torch.cuda.empty_cache()
+    return {
+        "metric": "items/sec (item Q-Former training step: fwd + QFormerLoss + bwd + grad all-reduce + AdamW)",
+        "value": items_per_sec, "unit": "items/s", "global_batch": Bg, "per_gpu_batch": Bl, "ms_per_step": ms,
+        "scaling": "strong", "dtype": "bf16 activations, fp32 master weights / gradients", "dropout": 0.0,
+        "final_loss": float(loss), "gpu_launches_per_step": launches,
+        "allreduce_bytes_per_step": red.bytes_reduced // max(args.train_steps + 2, 1),
+        "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                     "frac": (ach / pk["bf16_sustained"]) if ach else None,
+                     "share_of_step": (gemm[2] / (ms * args.train_steps)) if gemm else None,
+                     "end_to_end_frac_of_tensor_peak":
+                         items_per_sec / world * 3 * FLOPS_PER_ITEM / (pk["bf16_sustained"] * 1e12)},
+    }
 
 
 # ------------------------------------------------------------------------------------------------- ours
@@ -371,6 +441,13 @@ def run_ours(args, rank, world, local_rank):
         items_cpu = {"value": 32 / (time.perf_counter() - t0), "unit": "items/s", "cores": cores, "kind": "port",
                      "sample": "32 items (14 fields x 1024), oracle fp32 on torch CPU"}
 
+    # ------------------------------------------------------------------ cfg 2: training step
+    train_block = None
+    if args.train_batch > 0 and args.train_batch % world == 0:
+        del ranker, tokens, tok_local, pooled, fpool
+        torch.cuda.empty_cache()
+        train_block = run_train_block(args, rank, world, dev, barrier, max_over_ranks, pk)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -420,6 +497,7 @@ def run_ours(args, rank, world, local_rank):
                          "attention": roof(item_stats, "attention", pk["hbm"], 1e9)},
             "cpu_baseline": items_cpu,
         },
+        "train": train_block,
     }
     print(json.dumps(out), flush=True)
     if world > 1:

@@ -68,3 +68,62 @@ def test_gather_is_identity_without_process_group():
     s_all, i_all = gather_lists(s, i)
     assert tuple(s_all.shape) == (1, 3, 5) and torch.equal(i_all[0], i)
     assert gather_rows(s) is s
+
+
+def _allreduce_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from unirec_b200.training import GradientAllReducer
+        red = GradientAllReducer()
+        assert red.world == world
+        g = torch.Generator().manual_seed(100 + rank)
+        layers = [[torch.randn(7, 5, generator=g), torch.randn(5, generator=g)] for _ in range(3)]
+        big = torch.randn(12, 4, generator=g)
+        views = [big[:6], big[6:]]                      # gradients handed to autograd as views of a fused buffer
+        keep = [[t.clone() for t in ts] for ts in layers] + [[big.clone()]]
+        for li in (2, 1, 0):                            # backward order
+            red.layer_ready(li, layers[li])
+        red.layer_ready(-1, [big, None])
+        red.finish()
+        assert not red.pending
+        # expected: mean over ranks
+        ok = True
+        for ts, mine in zip(layers + [[big]], keep):
+            for t, m in zip(ts, mine):
+                gathered = [torch.empty_like(m) for _ in range(world)]
+                dist.all_gather(gathered, m)
+                ok = ok and torch.allclose(t, sum(gathered) / world, atol=1e-6)
+        ok = ok and torch.equal(torch.cat(views), big)  # views see the in-place result
+        p = torch.nn.Parameter(torch.zeros(3))
+        p.grad = torch.full((3,), float(rank + 1))
+        red.reduce_params([p, torch.nn.Parameter(torch.zeros(2))])      # second one has no grad: skipped
+        ok = ok and torch.allclose(p.grad, torch.full((3,), (1 + world) / 2))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_all_reducer_world2():
+    """Bucketed asynchronous gradient averaging of the training step (config 2) over gloo."""
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_allreduce_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    results = dict(q.get(timeout=5) for _ in range(world))
+    assert results == {0: True, 1: True}
+
+
+def test_gradient_all_reducer_single_process_is_noop():
+    from unirec_b200.training import GradientAllReducer
+    red = GradientAllReducer()
+    t = torch.ones(4)
+    red.layer_ready(0, [t])
+    red.finish()
+    assert red.world == 1 and torch.equal(t, torch.ones(4))

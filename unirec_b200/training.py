@@ -103,6 +103,7 @@ class BackboneTrainFn(torch.autograd.Function):
         eps = cfg.layer_norm_eps
         M = B * Q
         on_ready: Optional[Callable[[int, List[torch.Tensor]], None]] = getattr(bb, "grad_ready_hook", None)
+        on_finish: Optional[Callable[[], None]] = getattr(bb, "grad_finish_hook", None)
 
         def zeros(*shape):
             return torch.zeros(*shape, device=dev, dtype=torch.float32)
@@ -178,9 +179,11 @@ class BackboneTrainFn(torch.autograd.Function):
                 grads += [g["w_qc"], g["b_qc"], g_kv_w[off:off + H], g_kv_b[off:off + H], g_kv_w[off + H:off + 2 * H],
                           g_kv_b[off + H:off + 2 * H], g["w_oc"], g["b_oc"], g["ln2_g"], g["ln2_b"]]
             grads += [g["w_1"], g["b_1"], g["w_2"], g["b_2"], g["ln3_g"], g["ln3_b"]]
-        if on_ready is not None and n_cross:
-            on_ready(-1, [g_kv_w, g_kv_b])
         d_query = q0.grad.view(1, Q, H)
+        if on_ready is not None:
+            on_ready(-1, ([g_kv_w, g_kv_b] if n_cross else []) + [eg.grad, eb.grad, d_query])
+        if on_finish is not None:
+            on_finish()        # every bucket reduced and written back before autograd sees the gradients
         return (None, None, None, d_query) + tuple(grads)
 
 
@@ -201,29 +204,35 @@ def qformer_loss(outputs, field_embeddings, attention_mask, pos_rep=None, neg_re
 
 class GradientAllReducer:
     """Data-parallel gradient averaging for the training step.  The backbone's backward
-    calls `layer_ready` as soon as a layer's parameter gradients are complete; each call starts an asynchronous
-    NCCL all-reduce (one per tensor list, coalesced through a flat bucket), so communication overlaps the backward
-    of the remaining layers.  `finish()` waits for all of them and averages.  The 132.5 M never-executed parameters
-    (text branch, word / position embeddings) have no gradients and are never communicated."""
+    calls `layer_ready` as soon as a layer's parameter gradients are complete; each call packs them into one flat
+    bucket and starts an asynchronous all-reduce (NCCL on GPUs, gloo in the CPU tests), so communication overlaps
+    the backward of the remaining layers; `finish` (called at the end of the backbone's backward) waits, averages
+    and writes the results back in place.  Head gradients (2.1 M parameters) are reduced after backward with
+    `reduce_params`.  The 132.5 M never-executed parameters (text branch, word / position embeddings) have no
+    gradients and are never communicated."""
 
     def __init__(self, group=None, bucket_dtype: torch.dtype = torch.float32):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self.bucket_dtype = bucket_dtype
         self.pending = []
+        self.bytes_reduced = 0
+
+    def attach(self, backbone):
+        backbone.grad_ready_hook = self.layer_ready
+        backbone.grad_finish_hook = self.finish
+        return self
 
     def layer_ready(self, layer_index: int, tensors: List[torch.Tensor]):
+        tensors = [t for t in tensors if t is not None]
         if self.world == 1 or not tensors:
             return
         flat = torch.cat([t.reshape(-1).to(self.bucket_dtype) for t in tensors])
         work = self.dist.all_reduce(flat, group=self.group, async_op=True)
+        self.bytes_reduced += flat.numel() * flat.element_size()
         self.pending.append((work, flat, tensors))
-
-    def extra(self, tensors: List[torch.Tensor]):
-        """Gradients produced outside the backbone (heads, query tokens, embedding LayerNorm)."""
-        self.layer_ready(-2, tensors)
 
     def finish(self):
         for work, flat, tensors in self.pending:
@@ -235,3 +244,9 @@ class GradientAllReducer:
                 t.copy_(flat[off:off + n].view_as(t))
                 off += n
         self.pending = []
+
+    def reduce_params(self, params):
+        """Synchronous averaging of .grad of parameters whose gradients are produced outside the backbone."""
+        grads = [p.grad for p in params if p.grad is not None]
+        self.layer_ready(-2, grads)
+        self.finish()
