@@ -237,7 +237,7 @@ def run_train_block(args, rank, world, dev, barrier, max_over_ranks, pk):
         "metric": "items/sec (item Q-Former training step: fwd + QFormerLoss + bwd + grad all-reduce + AdamW)",
         "value": items_per_sec, "unit": "items/s", "global_batch": Bg, "per_gpu_batch": Bl, "ms_per_step": ms,
         "scaling": "strong", "dtype": "bf16 activations, fp32 master weights / gradients", "dropout": 0.0,
-        "final_loss": float(loss), "gpu_launches_per_step": launches,
+        "final_loss": float(loss.detach()), "gpu_launches_per_step": launches,
         "allreduce_bytes_per_step": red.bytes_reduced // max(args.train_steps + 2, 1),
         "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                      "frac": (ach / pk["bf16_sustained"]) if ach else None,
@@ -260,7 +260,19 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout at communicator creation; stdout carries exactly one JSON line,
+        # so route fd 1 to stderr while the communicator is created
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         if world > 1:
