@@ -154,6 +154,40 @@ int unirec_attention_backward(const void* q, int64_t ldq, int64_t q_batch_rows,
                               int64_t batch, int64_t num_heads, int64_t nq, int64_t nk, int64_t head_dim,
                               float scale, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Train-mode dropout (nn.Dropout at models/qformer.py:107 embeddings, :258 attention probabilities, :287 attention
+ * output dense, :373 FFN output dense; p = 0.2 item / 0.1 user, models/qformer_utils.py:19,25).  The reference draws
+ * masks from torch's global RNG; here a mask bit is a pure function of (seed, site, element) through Philox4x32-10 so
+ * that forward, backward and the CPU oracle agree bit for bit (definition: unirec_b200/csrc/dropout.cuh, restated in
+ * oracle/dropout_masks.py).  thr16 = round(p * 65536) (0 = off); kept elements are scaled by 65536 / (65536 - thr16).
+ * ------------------------------------------------------------------------------------------- */
+
+/* unirec_attention with dropout on the probabilities (after the softmax, before the product with V). */
+int unirec_attention_dropout(const void* q, int64_t ldq, int64_t q_batch_rows,
+                             const void* k, int64_t ldk, const void* v, int64_t ldv, int64_t kv_batch_rows,
+                             const float* key_mask, void* out, int64_t ldo,
+                             int64_t batch, int64_t num_heads, int64_t nq, int64_t nk, int64_t head_dim,
+                             float scale, uint32_t thr16, uint64_t seed, uint32_t site, void* stream);
+
+/* unirec_attention_backward for a forward pass run with unirec_attention_dropout(thr16, seed, site). */
+int unirec_attention_dropout_backward(const void* q, int64_t ldq, int64_t q_batch_rows,
+                                      const void* k, int64_t ldk, const void* v, int64_t ldv, int64_t kv_batch_rows,
+                                      const float* key_mask, const void* dout, int64_t lddo,
+                                      void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                                      int64_t batch, int64_t num_heads, int64_t nq, int64_t nk, int64_t head_dim,
+                                      float scale, uint32_t thr16, uint64_t seed, uint32_t site, void* stream);
+
+/* out[r,:] = dropout(x[r % x_row_mod or r,:]) + residual[r,:]  (bf16; residual NULL = no residual; H % 8 == 0):
+ * the pre-LayerNorm sum "dropout(dense(x)) + input_tensor" of models/qformer.py:287-288 / :373-374, and the dropped
+ * query embeddings of :107 (x_row_mod = number of query tokens, residual NULL). */
+int unirec_dropout_add(const void* x, int64_t ldx, int64_t x_row_mod, const void* residual, int64_t ldres,
+                       void* out, int64_t ldo, int64_t rows, int64_t H,
+                       uint32_t thr16, uint64_t seed, uint32_t site, void* stream);
+
+/* dx = dy o mask * scale  (gradient of the dropped branch). */
+int unirec_dropout_backward(const void* dy, int64_t lddy, void* dx, int64_t lddx, int64_t rows, int64_t H,
+                            uint32_t thr16, uint64_t seed, uint32_t site, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,11 +39,33 @@ def _split_heads(x, num_heads):
     return x.view(b, s, num_heads, h // num_heads).permute(0, 2, 1, 3)
 
 
+def _drop_rows(x, drop, site):
+    """nn.Dropout on a [B, T, H] hidden state with the CUDA path's counter-based mask (oracle/dropout_masks.py)."""
+    if drop is None:
+        return x
+    from . import dropout_masks as DM
+    thr, seed = drop
+    b, t, h = x.shape
+    keep = torch.from_numpy(DM.keep_mask_rows(seed, site, b * t, h, thr)).view(b, t, h)
+    return x * keep.to(x.dtype) * DM.keep_scale(thr)
+
+
+def _drop_probs(probs, drop, site):
+    if drop is None:
+        return probs
+    from . import dropout_masks as DM
+    thr, seed = drop
+    b, nh, nq, nk = probs.shape
+    keep = torch.from_numpy(DM.keep_mask_attention(seed, site, b, nh, nq, nk, thr))
+    return probs * keep.to(probs.dtype) * DM.keep_scale(thr)
+
+
 def attention_block(sd: Dict[str, torch.Tensor], prefix: str, hidden, kv_source, additive_mask,
-                    num_heads: int):
+                    num_heads: int, drop=None, site_probs: int = 0, site_out: int = 0):
     """BertAttention = BertSelfAttention + BertSelfOutput (models/qformer.py:169-275, 278-289,
     322-346).  `kv_source` is `hidden` for self-attention and encoder_hidden_states for
-    cross-attention (:185-198).  Dropout is identity (eval)."""
+    cross-attention (:185-198).  Dropout is identity (eval) unless `drop = (thr16, seed)` is given
+    (train mode: :258 on the probabilities, :287 on the dense output)."""
     q = _split_heads(_linear(sd, prefix + ".self.query", hidden), num_heads)
     k = _split_heads(_linear(sd, prefix + ".self.key", kv_source), num_heads)
     v = _split_heads(_linear(sd, prefix + ".self.value", kv_source), num_heads)
@@ -52,23 +74,28 @@ def attention_block(sd: Dict[str, torch.Tensor], prefix: str, hidden, kv_source,
     if additive_mask is not None:
         scores = scores + additive_mask                                # :247
     probs = torch.softmax(scores, dim=-1)                              # :250
+    probs = _drop_probs(probs, drop, site_probs)                       # :258
     ctx = torch.matmul(probs, v)                                       # :264
     ctx = ctx.permute(0, 2, 1, 3).contiguous()                         # :266
     ctx = ctx.view(ctx.shape[0], ctx.shape[1], -1)                     # :267-268
-    out = _linear(sd, prefix + ".output.dense", ctx)                   # :286
+    out = _drop_rows(_linear(sd, prefix + ".output.dense", ctx), drop, site_out)   # :286-287
     return _layer_norm(sd, prefix + ".output.LayerNorm", out + hidden, LN_EPS_BERT)  # :288
 
 
 def qformer_backbone(sd: Dict[str, torch.Tensor], prefix: str, query_embeds, encoder_hidden_states,
-                     encoder_attention_mask, num_layers: int, num_heads: int, cross_freq: int):
+                     encoder_attention_mask, num_layers: int, num_heads: int, cross_freq: int, drop=None):
     """BertModel.forward in the only mode the path uses: input_ids=None, query_embeds given,
     is_decoder=False, all-ones query attention mask (models/qformer.py:804-972).
 
     Masks: self-attention (1-m)*-10000 with m == 1 everywhere -> zeros (:785,801);
     cross-attention PreTrainedModel.invert_attention_mask -> (1-m)*finfo(fp32).min (:927-933).
+    `drop = (thr16, seed)`: train-mode dropout with the CUDA path's mask definition (dropout_masks.py).
     """
+    from .dropout_masks import (KIND_CROSS_OUT, KIND_CROSS_PROBS, KIND_FFN_OUT, KIND_SELF_OUT, KIND_SELF_PROBS,
+                                SITE_EMBEDDINGS, site_id)
     dtype = query_embeds.dtype
-    h = _layer_norm(sd, prefix + "embeddings.LayerNorm", query_embeds, LN_EPS_BERT)  # :104-107
+    h = _layer_norm(sd, prefix + "embeddings.LayerNorm", query_embeds, LN_EPS_BERT)  # :104-106
+    h = _drop_rows(h, drop, SITE_EMBEDDINGS)                                         # :107
     b, qn, _ = h.shape
     self_mask = torch.zeros(b, 1, 1, qn, dtype=dtype)
     if encoder_attention_mask is None:
@@ -77,19 +104,22 @@ def qformer_backbone(sd: Dict[str, torch.Tensor], prefix: str, query_embeds, enc
     cross_mask = (1.0 - m) * torch.finfo(dtype).min
     for i in range(num_layers):                                                        # :517
         p = f"{prefix}encoder.layer.{i}."
-        h = attention_block(sd, p + "attention", h, h, self_mask, num_heads)           # :417-424
+        h = attention_block(sd, p + "attention", h, h, self_mask, num_heads, drop,
+                            site_id(i, KIND_SELF_PROBS), site_id(i, KIND_SELF_OUT))    # :417-424
         if i % cross_freq == 0:                                                        # :386-394,432
             h = attention_block(sd, p + "crossattention", h, encoder_hidden_states, cross_mask,
-                                num_heads)                                             # :436-444
+                                num_heads, drop, site_id(i, KIND_CROSS_PROBS),
+                                site_id(i, KIND_CROSS_OUT))                            # :436-444
         inter = F.gelu(_linear(sd, p + "intermediate_query.dense", h))                 # :359-361 (erf GELU)
-        out = _linear(sd, p + "output_query.dense", inter)                             # :372
+        out = _drop_rows(_linear(sd, p + "output_query.dense", inter), drop,
+                         site_id(i, KIND_FFN_OUT))                                     # :372-373
         h = _layer_norm(sd, p + "output_query.LayerNorm", out + h, LN_EPS_BERT)        # :374, 481-484
     return h
 
 
 def item_qformer_forward(sd: Dict[str, torch.Tensor], field_embeddings: torch.Tensor,
                          attention_mask: Optional[torch.Tensor] = None, num_heads: int = 16,
-                         cross_freq: int = 2) -> Dict[str, torch.Tensor]:
+                         cross_freq: int = 2, drop=None) -> Dict[str, torch.Tensor]:
     """QFormerForItemRepresentation.forward (models/qformer_utils.py:37-60)."""
     b = field_embeddings.shape[0]
     num_layers = 1 + max(int(k.split(".")[3]) for k in sd if k.startswith("qformer.encoder.layer."))
@@ -97,7 +127,7 @@ def item_qformer_forward(sd: Dict[str, torch.Tensor], field_embeddings: torch.Te
     if attention_mask is None:
         attention_mask = torch.ones(b, field_embeddings.shape[1])                     # :40-41
     out = qformer_backbone(sd, "qformer.", q, field_embeddings.float(), attention_mask,
-                           num_layers, num_heads, cross_freq)                          # :45-49
+                           num_layers, num_heads, cross_freq, drop)                    # :45-49
     rep = _linear(sd, "item_representation_head", out.mean(dim=1))                     # :50
     rec = _linear(sd, "reconstruction_head", out)                                      # :53
     rec_fields = _linear(sd, "field_projection", rec.transpose(1, 2)).transpose(1, 2)  # :54

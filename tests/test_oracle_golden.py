@@ -83,3 +83,23 @@ def test_bf16_precision_model_brackets_the_tolerances():
         mx, mean, cos = stats[name]
         assert mx <= 0.15 and mean <= 0.02 and cos >= 0.9995, (name, stats[name])
     assert stats["sharp"][0] > 0.15  # documents the amplification; not a bound on the kernels
+
+
+def test_philox_known_answer_vectors_and_mask_rate():
+    """oracle/dropout_masks.py: Philox4x32-10 against the Random123 known-answer vectors; mask keep-rate ~ 1 - p."""
+    import numpy as np
+    from oracle import dropout_masks as DM
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+             (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kats:
+        got = DM.philox4x32_10(*[np.uint32(c) for c in ctr], *key)
+        assert tuple(int(g) for g in got) == want
+    thr = DM.threshold16(0.2)
+    assert thr == 13107 and abs(DM.keep_scale(thr) - 1.25) < 1e-4
+    rows = DM.keep_mask_rows(7, 3, 256, 1024, thr)
+    att = DM.keep_mask_attention(7, 4, 4, 16, 32, 14, thr)
+    assert abs(rows.mean() - 0.8) < 0.005 and abs(att.mean() - 0.8) < 0.01
+    assert not np.array_equal(rows, DM.keep_mask_rows(8, 3, 256, 1024, thr))       # seed matters
+    assert not np.array_equal(rows, DM.keep_mask_rows(7, 5, 256, 1024, thr))       # site matters

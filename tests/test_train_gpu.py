@@ -130,19 +130,103 @@ def test_attention_backward(nq, nk, heads):
         torch.testing.assert_close(dv.float().view(B, nk, hd), vf.grad, rtol=3e-2, atol=3e-2)
 
 
-def _oracle_loss_and_grads(sd, x, mask, heads, weights):
+def test_dropout_rows_match_oracle_masks():
+    """dropout_add / dropout_backward reproduce the CPU restatement of the Philox mask bit for bit."""
+    from oracle import dropout_masks as DM
+    from unirec_b200 import ops
+    rows, H, p = 515, 256, 0.2
+    thr = ops.dropout_threshold(p)
+    seed, site = (1 << 40) + 12345, 19
+    x = _randn(rows, H, seed=30, dtype=torch.bfloat16)
+    res = _randn(rows, H, seed=31, dtype=torch.bfloat16)
+    keep = torch.from_numpy(DM.keep_mask_rows(seed, site, rows, H, thr)).to(DEV)
+    scale = DM.keep_scale(thr)
+    assert 0.77 < float(keep.float().mean()) < 0.83
+    out = ops.dropout_add(x, res, (thr, seed, site))
+    ref = (x.float() * scale * keep + res.float()).to(torch.bfloat16)
+    assert torch.equal(out, ref)
+    out0 = ops.dropout_add(x, None, (thr, seed, site))
+    assert torch.equal(out0, (x.float() * scale * keep).to(torch.bfloat16))
+    dx = ops.dropout_backward(x, (thr, seed, site))
+    assert torch.equal(dx, (x.float() * scale * keep).to(torch.bfloat16))
+    # broadcast input (query embeddings: 32 rows serve every batch element, each with its own mask)
+    q = _randn(32, H, seed=32, dtype=torch.bfloat16)
+    outq = ops.dropout_add(q, None, (thr, seed, 0), rows=rows - 3, x_row_mod=32)
+    keepq = torch.from_numpy(DM.keep_mask_rows(seed, 0, rows - 3, H, thr)).to(DEV)
+    refq = (q.float()[torch.arange(rows - 3, device=DEV) % 32] * scale * keepq).to(torch.bfloat16)
+    assert torch.equal(outq, refq)
+
+
+@pytest.mark.parametrize("nq,nk,heads", [(32, 32, 16), (32, 14, 16), (64, 64, 4), (48, 40, 2)])
+def test_attention_dropout_forward_backward(nq, nk, heads):
+    """Probability dropout inside the attention kernels vs torch autograd with the oracle's mask."""
+    from oracle import dropout_masks as DM
+    from unirec_b200 import ops
+    B, hd, p = 5, heads * 64, 0.2
+    thr, seed, site = ops.dropout_threshold(p), 987654321012345, 1 + 8 * 3 + 2
+    q = _randn(B, nq, hd, seed=40, dtype=torch.bfloat16)
+    k = _randn(B, nk, hd, seed=41, dtype=torch.bfloat16)
+    v = _randn(B, nk, hd, seed=42, dtype=torch.bfloat16)
+    do = _randn(B, nq, hd, seed=43, dtype=torch.bfloat16)
+    mask = (torch.rand(B, nk, generator=torch.Generator().manual_seed(44)) < 0.7).float()
+    mask[:, 0] = 1.0
+    mask = mask.to(DEV)
+    keep = torch.from_numpy(DM.keep_mask_attention(seed, site, B, heads, nq, nk, thr)).to(DEV).float() * DM.keep_scale(thr)
+    qf, kf, vf = (t.float().requires_grad_() for t in (q, k, v))
+    qh = qf.view(B, nq, heads, 64).permute(0, 2, 1, 3)
+    kh = kf.view(B, nk, heads, 64).permute(0, 2, 1, 3)
+    vh = vf.view(B, nk, heads, 64).permute(0, 2, 1, 3)
+    s = qh @ kh.transpose(-1, -2) / 8.0 + (1.0 - mask[:, None, None, :]) * torch.finfo(torch.float32).min
+    ref = ((torch.softmax(s, dim=-1) * keep) @ vh).permute(0, 2, 1, 3).reshape(B, nq, hd)
+    ref.backward(do.float())
+    out = ops.attention(q.view(B * nq, hd), k.view(B * nk, hd), v.view(B * nk, hd), batch=B, num_heads=heads, nq=nq, nk=nk,
+                        key_mask=mask, dropout=(thr, seed, site))
+    torch.testing.assert_close(out.float().view(B, nq, hd), ref.detach(), rtol=2e-2, atol=2e-2)
+    dq = torch.zeros(B * nq, hd, device=DEV, dtype=torch.bfloat16)
+    dk = torch.zeros(B * nk, hd, device=DEV, dtype=torch.bfloat16)
+    dv = torch.zeros(B * nk, hd, device=DEV, dtype=torch.bfloat16)
+    ops.attention_backward(q.view(B * nq, hd), k.view(B * nk, hd), v.view(B * nk, hd), do.view(B * nq, hd), dq, dk, dv,
+                           batch=B, num_heads=heads, nq=nq, nk=nk, key_mask=mask, dropout=(thr, seed, site))
+    torch.testing.assert_close(dq.float().view(B, nq, hd), qf.grad, rtol=3e-2, atol=4e-2)
+    torch.testing.assert_close(dk.float().view(B, nk, hd), kf.grad, rtol=3e-2, atol=4e-2)
+    torch.testing.assert_close(dv.float().view(B, nk, hd), vf.grad, rtol=3e-2, atol=4e-2)
+
+
+def test_attention_dropout_long_keys_forward():
+    """Key-tiled path (nk > 64: several 64-key tiles with the online softmax) with dropout."""
+    from oracle import dropout_masks as DM
+    from unirec_b200 import ops
+    B, heads, nq, nk = 3, 4, 64, 200
+    hd = heads * 64
+    thr, seed, site = ops.dropout_threshold(0.1), 77, 11
+    q = _randn(B, nq, hd, seed=50, dtype=torch.bfloat16)
+    k = _randn(B, nk, hd, seed=51, dtype=torch.bfloat16)
+    v = _randn(B, nk, hd, seed=52, dtype=torch.bfloat16)
+    keep = torch.from_numpy(DM.keep_mask_attention(seed, site, B, heads, nq, nk, thr)).to(DEV).float() * DM.keep_scale(thr)
+    qh = q.float().view(B, nq, heads, 64).permute(0, 2, 1, 3)
+    kh = k.float().view(B, nk, heads, 64).permute(0, 2, 1, 3)
+    vh = v.float().view(B, nk, heads, 64).permute(0, 2, 1, 3)
+    ref = ((torch.softmax(qh @ kh.transpose(-1, -2) / 8.0, dim=-1) * keep) @ vh).permute(0, 2, 1, 3).reshape(B, nq, hd)
+    out = ops.attention(q.view(B * nq, hd), k.view(B * nk, hd), v.view(B * nk, hd), batch=B, num_heads=heads, nq=nq, nk=nk,
+                        dropout=(thr, seed, site))
+    torch.testing.assert_close(out.float().view(B, nq, hd), ref, rtol=2e-2, atol=2e-2)
+
+
+def _oracle_loss_and_grads(sd, x, mask, heads, weights, drop=None):
     """Reference: fp32 autograd through the CPU oracle; loss = sum(outputs * fixed random weights)."""
     from oracle import qformer_oracle as O
     sd = {k: v.clone().float().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
-    out = O.item_qformer_forward(sd, x, mask, num_heads=heads)
+    out = O.item_qformer_forward(sd, x, mask, num_heads=heads, drop=drop)
     loss = sum((out[k] * weights[k]).sum() for k in ("query_outputs", "item_representation", "reconstructed_fields"))
     loss.backward()
     return float(loss), {k: v.grad for k, v in sd.items() if v.requires_grad and v.grad is not None}
 
 
-def test_item_training_step_gradients_match_oracle_autograd():
+@pytest.mark.parametrize("dropout", [0.0, 0.2])
+def test_item_training_step_gradients_match_oracle_autograd(dropout):
     """Small item Q-Former (4 layers, hidden 256): forward + backward through the CUDA training path vs torch
-    autograd through the fp32 oracle on the same weights and inputs."""
+    autograd through the fp32 oracle on the same weights and inputs - with dropout 0 and with the reference's
+    default dropout 0.2 (the oracle regenerates the CUDA path's Philox masks from the same seed)."""
     from tests.golden_cases import ITEM_CASES
     from unirec_b200 import synth
     from unirec_b200.modules import QFormerForItemRepresentation
@@ -152,9 +236,10 @@ def test_item_training_step_gradients_match_oracle_autograd():
     model = QFormerForItemRepresentation(hidden_size=mk["hidden"], num_hidden_layers=mk["layers"],
                                          num_attention_heads=c["heads"], intermediate_size=mk["inter"],
                                          num_query_tokens=mk["num_query"], field_embedding_dim=mk["field_dim"],
-                                         num_fields=mk["num_fields"], dropout=0.0)
+                                         num_fields=mk["num_fields"], dropout=dropout)
     model.load_state_dict(sd, strict=True)
     model = model.to(DEV).train()
+    model.dropout_seed = 20261017
     B = 64
     x, mask = synth.item_fields(batch=B, num_fields=6, dim=256, seed=62, clip_field=2, presence=0.8)
     g = torch.Generator().manual_seed(63)
@@ -164,7 +249,8 @@ def test_item_training_step_gradients_match_oracle_autograd():
     out = model(x.to(DEV), mask.to(DEV))
     loss = sum((out[k].float() * weights[k].to(DEV)).sum() for k in weights)
     loss.backward()
-    ref_loss, ref = _oracle_loss_and_grads(sd, x, mask, c["heads"], weights)
+    assert (model.last_dropout is None) == (dropout == 0.0)
+    ref_loss, ref = _oracle_loss_and_grads(sd, x, mask, c["heads"], weights, drop=model.last_dropout)
     assert abs(float(loss) - ref_loss) <= 0.02 * abs(ref_loss) + 0.05
     checked, bad = 0, []
     for name, prm in model.named_parameters():
@@ -188,3 +274,35 @@ def test_item_training_step_gradients_match_oracle_autograd():
         checked += 1
     assert not bad, bad
     assert checked > 60
+
+
+def test_train_mode_no_grad_forward_uses_dropout_and_eval_does_not():
+    """The reference's step runs the positive / negative forwards under no_grad with the module in train():
+    dropout stays active there (training/item_qformer_training.py:122-125); eval() is deterministic."""
+    from oracle import qformer_oracle as O
+    from tests.golden_cases import ITEM_CASES
+    from unirec_b200 import synth
+    from unirec_b200.modules import QFormerForItemRepresentation
+    c = ITEM_CASES["small"]
+    mk = c["model"]
+    sd = synth.item_qformer_state_dict(**mk, seed=61, attn_std=0.1)
+    model = QFormerForItemRepresentation(hidden_size=mk["hidden"], num_hidden_layers=mk["layers"],
+                                         num_attention_heads=c["heads"], intermediate_size=mk["inter"],
+                                         num_query_tokens=mk["num_query"], field_embedding_dim=mk["field_dim"],
+                                         num_fields=mk["num_fields"], dropout=0.2)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).train()
+    x, mask = synth.item_fields(batch=16, num_fields=6, dim=256, seed=62, clip_field=2, presence=0.8)
+    model.dropout_seed = 5
+    with torch.no_grad():
+        a = model(x.to(DEV), mask.to(DEV))["query_outputs"].float().cpu()
+        drop_a = model.last_dropout
+        b = model(x.to(DEV), mask.to(DEV))["query_outputs"].float().cpu()
+    assert drop_a == (13107, 5) and model.last_dropout == (13107, 6)
+    assert float((a - b).abs().max()) > 0.05                       # different seeds, different masks
+    ref = O.item_qformer_forward(sd, x, mask, num_heads=c["heads"], drop=drop_a)["query_outputs"]
+    assert float((a - ref).abs().mean()) < 0.02 and float(F.cosine_similarity(a.flatten(), ref.flatten(), dim=0)) > 0.999
+    model.eval()
+    e1 = model(x.to(DEV), mask.to(DEV))["query_outputs"]
+    e2 = model(x.to(DEV), mask.to(DEV))["query_outputs"]
+    assert torch.equal(e1, e2)

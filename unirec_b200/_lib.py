@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_int64, c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libunirec_b200.so")
@@ -50,6 +50,17 @@ _SIGNATURES = {
     "unirec_attention_backward": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64,
                                           c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                           c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p]),
+    "unirec_attention_dropout": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64,
+                                         c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_float,
+                                         c_uint32, c_uint64, c_uint32, c_void_p]),
+    "unirec_attention_dropout_backward": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64,
+                                                  c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                                                  c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                                  c_int64, c_float, c_uint32, c_uint64, c_uint32, c_void_p]),
+    "unirec_dropout_add": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64,
+                                   c_uint32, c_uint64, c_uint32, c_void_p]),
+    "unirec_dropout_backward": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_uint32, c_uint64,
+                                        c_uint32, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -25,6 +25,7 @@
 // degenerates to uniform attention over all nk keys (not NaN, not zero) - exactly the fp32
 // behaviour of the reference, where score + finfo.min == finfo.min for every key.
 #include "common.cuh"
+#include "dropout.cuh"
 #include "umma_pipe.cuh"
 
 #include <cstdlib>
@@ -40,13 +41,14 @@ struct AttnParams {
     __nv_bfloat16* out; long long ldo;
     int num_heads, nq, nk;
     float scale_log2;        // softmax scale * log2(e)
+    DropoutParams drop;      // train-mode dropout of the probabilities (models/qformer.py:258); DROP kernels only
 };
 
 constexpr float kMaskedLog2 = -1.0e30f;  // stands in for finfo.min (see header comment)
 
 constexpr int ATT_STAGES = 3;
 
-template <int KT>
+template <int KT, bool DROP>
 __global__ void __launch_bounds__(128)
 attention_kernel(const AttnParams p, int num_items) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -186,6 +188,27 @@ attention_kernel(const AttnParams p, int num_items) {
             l_run[0] += s[j][0] + s[j][1];
             l_run[1] += s[j][2] + s[j][3];
         }
+        if (DROP) {
+            // the row sum above is that of the un-dropped probabilities (softmax first, dropout second, :250-258)
+            const unsigned long long row0 =
+                static_cast<unsigned long long>(blockIdx.x + it * gridDim.x) * p.nq + warp * 16 + g4;
+#pragma unroll
+            for (int kb = 0; kb < (KT + 31) / 32; ++kb) {
+                const uint32_t group = static_cast<uint32_t>(((tile * KT) >> 5) + kb) * 4 + t;
+                const uint32_t k0 = dropout_keep8(p.drop, row0, group);
+                const uint32_t k1 = dropout_keep8(p.drop, row0 + 8, group);
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const int j = kb * 4 + nt;
+                    if (j < KT / 8) {
+                        s[j][0] = ((k0 >> (2 * nt)) & 1u) ? s[j][0] * p.drop.scale : 0.f;
+                        s[j][1] = ((k0 >> (2 * nt + 1)) & 1u) ? s[j][1] * p.drop.scale : 0.f;
+                        s[j][2] = ((k1 >> (2 * nt)) & 1u) ? s[j][2] * p.drop.scale : 0.f;
+                        s[j][3] = ((k1 >> (2 * nt + 1)) & 1u) ? s[j][3] * p.drop.scale : 0.f;
+                    }
+                }
+            }
+        }
         if (tile > 0) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -275,7 +298,8 @@ static bool attention_tc_enabled() {
 
 int attention(const void* q, long long ldq, long long q_batch_rows, const void* k, long long ldk, const void* v,
               long long ldv, long long kv_batch_rows, const float* key_mask, void* out, long long ldo, long long batch,
-              long long num_heads, long long nq, long long nk, long long head_dim, float scale, cudaStream_t stream) {
+              long long num_heads, long long nq, long long nk, long long head_dim, float scale, unsigned drop_thr16,
+              unsigned long long drop_seed, unsigned drop_site, cudaStream_t stream) {
     if (q == nullptr || k == nullptr || v == nullptr || out == nullptr || batch <= 0 || num_heads <= 0 || nq <= 0 ||
         nk <= 0) {
         set_last_error("attention: null pointer or empty shape");
@@ -287,7 +311,11 @@ int attention(const void* q, long long ldq, long long q_batch_rows, const void* 
                        head_dim, nq);
         return UNIREC_ERR_BAD_ARG;
     }
-    if (attention_tc_enabled() && attention_tc_supported(num_heads, nq, nk, head_dim, ldk, ldv, kv_batch_rows))
+    if (drop_thr16 >= 65536u) {
+        set_last_error("attention: dropout probability must be < 1");
+        return UNIREC_ERR_BAD_ARG;
+    }
+    if (drop_thr16 == 0 && attention_tc_enabled() && attention_tc_supported(num_heads, nq, nk, head_dim, ldk, ldv, kv_batch_rows))
         return attention_tc(q, ldq, q_batch_rows, k, ldk, v, ldv, kv_batch_rows, key_mask, out, ldo, batch, num_heads, nq,
                             nk, scale, stream);
     AttnParams p;
@@ -299,33 +327,39 @@ int attention(const void* q, long long ldq, long long q_batch_rows, const void* 
     p.out = reinterpret_cast<__nv_bfloat16*>(out); p.ldo = ldo;
     p.num_heads = static_cast<int>(num_heads); p.nq = static_cast<int>(nq); p.nk = static_cast<int>(nk);
     p.scale_log2 = scale * 1.4426950408889634f;
+    p.drop.thr16 = drop_thr16; p.drop.seed = drop_seed; p.drop.site = drop_site;
+    p.drop.scale = 65536.0f / (65536.0f - static_cast<float>(drop_thr16));
     const int nwarps = static_cast<int>((nq + 15) / 16);
     const int threads = nwarps * 32;
     const int num_items = static_cast<int>(batch * num_heads);
     const int kt = nk <= 16 ? 16 : (nk <= 32 ? 32 : 64);
     const size_t smem = static_cast<size_t>(ATT_STAGES) *
                         (static_cast<size_t>(nwarps) * 16 * 128 + 2 * static_cast<size_t>(kt) * 128 + kt * sizeof(float));
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e1 = cudaFuncSetAttribute(attention_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        cudaError_t e2 = cudaFuncSetAttribute(attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        cudaError_t e3 = cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
-            set_last_error("attention: cudaFuncSetAttribute failed");
-            return UNIREC_ERR_CUDA;
-        }
-        attr_set = true;
-    }
     const int sms = num_sms() > 0 ? num_sms() : 148;
-#define UNIREC_ATT(KT_)                                                                                      \
-    do {                                                                                                     \
-        long long grid = static_cast<long long>(sms) * attention_ctas_per_sm(attention_kernel<KT_>, threads, smem); \
-        if (grid > num_items) grid = num_items;                                                              \
-        attention_kernel<KT_><<<static_cast<unsigned>(grid), threads, smem, stream>>>(p, num_items);          \
+#define UNIREC_ATT(KT_, DROP_)                                                                                     \
+    do {                                                                                                           \
+        static bool attr_set = false;                                                                              \
+        if (!attr_set) {                                                                                           \
+            if (cudaFuncSetAttribute(attention_kernel<KT_, DROP_>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                     100 * 1024) != cudaSuccess) {                                                 \
+                set_last_error("attention: cudaFuncSetAttribute failed");                                          \
+                return UNIREC_ERR_CUDA;                                                                            \
+            }                                                                                                      \
+            attr_set = true;                                                                                       \
+        }                                                                                                          \
+        long long grid = static_cast<long long>(sms) * attention_ctas_per_sm(attention_kernel<KT_, DROP_>, threads, smem); \
+        if (grid > num_items) grid = num_items;                                                                    \
+        attention_kernel<KT_, DROP_><<<static_cast<unsigned>(grid), threads, smem, stream>>>(p, num_items);         \
     } while (0)
-    if (kt == 16) UNIREC_ATT(16);
-    else if (kt == 32) UNIREC_ATT(32);
-    else UNIREC_ATT(64);
+    if (drop_thr16 == 0) {
+        if (kt == 16) UNIREC_ATT(16, false);
+        else if (kt == 32) UNIREC_ATT(32, false);
+        else UNIREC_ATT(64, false);
+    } else {
+        if (kt == 16) UNIREC_ATT(16, true);
+        else if (kt == 32) UNIREC_ATT(32, true);
+        else UNIREC_ATT(64, true);
+    }
 #undef UNIREC_ATT
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -7,6 +7,7 @@
 //                            (nq <= 64, nk <= 64: item self-attention 32 x 32, item cross-attention 32 x 14)
 // Reference semantics: autograd of training/item_qformer_training.py:129 (loss.backward()) with dropout disabled.
 #include "common.cuh"
+#include "dropout.cuh"
 
 namespace unirec {
 
@@ -284,6 +285,7 @@ struct AttnBwdParams {
     __nv_bfloat16* dv; long long lddv;
     int num_heads, nq, nk;
     float scale;
+    DropoutParams drop;      // same (seed, site) as the forward pass; thr16 == 0: no dropout
 };
 
 template <int KT>
@@ -396,9 +398,32 @@ attention_bwd_kernel(const AttnBwdParams p) {
         l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
         l[r] = 1.0f / l[r];
     }
+    // dropout (models/qformer.py:258): O = (P o m) V with m in {0, 1/keep}; dP = (dO V^T) o m, and dV uses P o m
+    float mk[KT / 8][4];
+#pragma unroll
+    for (int j = 0; j < KT / 8; ++j) { mk[j][0] = mk[j][1] = mk[j][2] = mk[j][3] = 1.f; }
+    if (p.drop.thr16 != 0) {
+        const unsigned long long row0 = static_cast<unsigned long long>(blockIdx.x) * p.nq + warp * 16 + g4;
+#pragma unroll
+        for (int kb = 0; kb < (KT + 31) / 32; ++kb) {
+            const uint32_t k0 = dropout_keep8(p.drop, row0, static_cast<uint32_t>(kb * 4 + t));
+            const uint32_t k1 = dropout_keep8(p.drop, row0 + 8, static_cast<uint32_t>(kb * 4 + t));
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int j = kb * 4 + nt;
+                if (j < KT / 8) {
+                    mk[j][0] = ((k0 >> (2 * nt)) & 1u) ? p.drop.scale : 0.f;
+                    mk[j][1] = ((k0 >> (2 * nt + 1)) & 1u) ? p.drop.scale : 0.f;
+                    mk[j][2] = ((k1 >> (2 * nt)) & 1u) ? p.drop.scale : 0.f;
+                    mk[j][3] = ((k1 >> (2 * nt + 1)) & 1u) ? p.drop.scale : 0.f;
+                }
+            }
+        }
+    }
 #pragma unroll
     for (int j = 0; j < KT / 8; ++j) {
         s[j][0] *= l[0]; s[j][1] *= l[0]; s[j][2] *= l[1]; s[j][3] *= l[1];          // P
+        dp[j][0] *= mk[j][0]; dp[j][1] *= mk[j][1]; dp[j][2] *= mk[j][2]; dp[j][3] *= mk[j][3];
         rd[0] += s[j][0] * dp[j][0] + s[j][1] * dp[j][1];
         rd[1] += s[j][2] * dp[j][2] + s[j][3] * dp[j][3];
     }
@@ -413,8 +438,8 @@ attention_bwd_kernel(const AttnBwdParams p) {
         dp[j][2] = s[j][2] * (dp[j][2] - rd[1]) * p.scale; dp[j][3] = s[j][3] * (dp[j][3] - rd[1]) * p.scale;
         const int r0 = warp * 16 + g4;
         const uint32_t off0 = swz128(r0, j) + 4 * t, off1 = swz128(r0 + 8, j) + 4 * t;
-        *reinterpret_cast<uint32_t*>(sP + off0) = pack_bf16(s[j][0], s[j][1]);
-        *reinterpret_cast<uint32_t*>(sP + off1) = pack_bf16(s[j][2], s[j][3]);
+        *reinterpret_cast<uint32_t*>(sP + off0) = pack_bf16(s[j][0] * mk[j][0], s[j][1] * mk[j][1]);   // P o m for dV
+        *reinterpret_cast<uint32_t*>(sP + off1) = pack_bf16(s[j][2] * mk[j][2], s[j][3] * mk[j][3]);
         *reinterpret_cast<uint32_t*>(sdS + off0) = pack_bf16(dp[j][0], dp[j][1]);
         *reinterpret_cast<uint32_t*>(sdS + off1) = pack_bf16(dp[j][2], dp[j][3]);
     }
@@ -500,7 +525,7 @@ int attention_backward(const void* q, long long ldq, long long q_batch_rows, con
                        long long ldv, long long kv_batch_rows, const float* key_mask, const void* dout, long long lddo,
                        void* dq, long long lddq, void* dk, long long lddk, void* dv, long long lddv, long long batch,
                        long long num_heads, long long nq, long long nk, long long head_dim, float scale,
-                       cudaStream_t stream) {
+                       unsigned drop_thr16, unsigned long long drop_seed, unsigned drop_site, cudaStream_t stream) {
     if (q == nullptr || k == nullptr || v == nullptr || dout == nullptr || dq == nullptr || dk == nullptr || dv == nullptr ||
         batch <= 0 || num_heads <= 0 || nq <= 0 || nk <= 0) {
         set_last_error("attention_backward: null pointer or empty shape");
@@ -524,6 +549,9 @@ int attention_backward(const void* q, long long ldq, long long q_batch_rows, con
     p.dv = reinterpret_cast<__nv_bfloat16*>(dv); p.lddv = lddv;
     p.num_heads = (int)num_heads; p.nq = (int)nq; p.nk = (int)nk;
     p.scale = scale;
+    if (drop_thr16 >= 65536u) { set_last_error("attention_backward: dropout probability must be < 1"); return UNIREC_ERR_BAD_ARG; }
+    p.drop.thr16 = drop_thr16; p.drop.seed = drop_seed; p.drop.site = drop_site;
+    p.drop.scale = 65536.0f / (65536.0f - static_cast<float>(drop_thr16));
     const int nwarps = (int)((nq + 15) / 16);
     const int threads = nwarps * 32;
     const unsigned grid = static_cast<unsigned>(batch * num_heads);

@@ -247,8 +247,8 @@ class QFormerBackbone(nn.Module):
 def _check_inference_mode(module: nn.Module, dropout: float):
     if module.training and dropout > 0.0:
         raise NotImplementedError(
-            "unirec_b200: the CUDA path implements dropout = identity; call .eval(), or construct the module with "
-            "dropout=0.0 to train (forward + backward kernels; unirec_b200/training.py).")
+            "unirec_b200: this entry point implements dropout = identity; call .eval() first.  Train-mode dropout is "
+            "implemented for QFormerForItemRepresentation.forward (unirec_b200/training.py).")
 
 
 class QFormerForItemRepresentation(nn.Module):
@@ -275,6 +275,25 @@ class QFormerForItemRepresentation(nn.Module):
         self.prelayernorm_dtype = torch.float32
         self._head_pack = None
         self._head_key = None
+        # train-mode dropout: None = draw a fresh seed per forward call from torch's default CPU generator
+        # (reproducible under torch.manual_seed); an int = use it for the next call, then count up
+        self.dropout_seed: Optional[int] = None
+        self.last_dropout = None                   # (thr16, seed) of the most recent train-mode forward
+
+    def _next_dropout(self):
+        p = float(self.config.hidden_dropout_prob)
+        if p != float(self.config.attention_probs_dropout_prob):
+            raise NotImplementedError("hidden and attention dropout probabilities differ")
+        if p <= 0.0:
+            self.last_dropout = None
+            return None
+        if self.dropout_seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        else:
+            seed = int(self.dropout_seed)
+            self.dropout_seed = seed + 1
+        self.last_dropout = (ops.dropout_threshold(p), seed)
+        return self.last_dropout
 
     def _heads(self):
         ps = [self.item_representation_head.weight, self.item_representation_head.bias,
@@ -299,12 +318,13 @@ class QFormerForItemRepresentation(nn.Module):
         return self.qformer.encode(self.query_embeddings, field_embeddings, attention_mask, out_dtype,
                                    self.prelayernorm_dtype)
 
-    def _forward_train(self, field_embeddings, attention_mask):
+    def _forward_train(self, field_embeddings, attention_mask, drop=None):
         """Differentiable forward (models/qformer_utils.py:37-60 under autograd): backbone = BackboneTrainFn,
-        heads = LinearFn (tcgen05 fwd / dgrad / wgrad), the 32 -> num_fields projection in torch (0.9 GFLOP/1024 items)."""
+        heads = LinearFn (tcgen05 fwd / dgrad / wgrad), the 32 -> num_fields projection in torch (0.9 GFLOP/1024 items).
+        drop = (thr16, seed) or None."""
         from .training import BackboneTrainFn, LinearFn
         bb = self.qformer
-        qo = BackboneTrainFn.apply(bb, field_embeddings, attention_mask, self.query_embeddings, *bb._live_params())
+        qo = BackboneTrainFn.apply(bb, drop, field_embeddings, attention_mask, self.query_embeddings, *bb._live_params())
         B, Q, H = qo.shape
         qo16 = qo.to(torch.bfloat16)
         rep = LinearFn.apply(qo16.mean(dim=1).to(torch.bfloat16), self.item_representation_head.weight,
@@ -316,9 +336,12 @@ class QFormerForItemRepresentation(nn.Module):
         return {"query_outputs": qo, "item_representation": rep, "reconstructed_fields": fields}
 
     def forward(self, field_embeddings: torch.Tensor, attention_mask: torch.Tensor = None) -> Dict[str, torch.Tensor]:
-        _check_inference_mode(self, self.config.hidden_dropout_prob)
-        if self.training and torch.is_grad_enabled():
-            return self._forward_train(field_embeddings, attention_mask)
+        if self.training:
+            # train(): dropout is live in every forward, including the no-grad positive / negative passes of the
+            # reference's step (training/item_qformer_training.py:122-125)
+            drop = self._next_dropout()
+            if torch.is_grad_enabled() or drop is not None:
+                return self._forward_train(field_embeddings, attention_mask, drop)
         with torch.no_grad():
             return self._forward_eval(field_embeddings, attention_mask)
 

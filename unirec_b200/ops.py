@@ -145,9 +145,10 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, batch: int, num_heads: int, nq: int, nk: int,
               key_mask: Optional[torch.Tensor] = None, q_broadcast: bool = False,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, dropout: Optional[Tuple[int, int, int]] = None) -> torch.Tensor:
     """Multi-head attention with head_dim 64.  q/k/v are 2-D row views (possibly column slices of a fused
-    projection buffer): q [batch*nq (or nq if q_broadcast), heads*64], k/v [batch*nk, heads*64]."""
+    projection buffer): q [batch*nq (or nq if q_broadcast), heads*64], k/v [batch*nk, heads*64].
+    dropout = (thr16, seed, site): train-mode dropout of the probabilities (see dropout_threshold)."""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _req(t, torch.bfloat16, f"attention.{n}")
         if t.dim() != 2:
@@ -163,11 +164,52 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, batch: int, 
             raise RuntimeError("attention: key_mask must be contiguous [batch, nk]")
     # algorithmic bytes: Q, K, V read once + context written once (bf16)
     with _Timed("attention", 2.0 * hd * batch * ((1 if q_broadcast else 1) * nq + 2 * nk + nq)):
-        rc = _lib.load().unirec_attention(q.data_ptr(), q.stride(0), 0 if q_broadcast else nq, k.data_ptr(),
-                                          k.stride(0), v.data_ptr(), v.stride(0), nk, _ptr(key_mask), out.data_ptr(),
-                                          out.stride(0), batch, num_heads, nq, nk, 64, 0.125, _stream())
+        if dropout is not None and dropout[0] > 0:
+            rc = _lib.load().unirec_attention_dropout(q.data_ptr(), q.stride(0), 0 if q_broadcast else nq, k.data_ptr(),
+                                                      k.stride(0), v.data_ptr(), v.stride(0), nk, _ptr(key_mask),
+                                                      out.data_ptr(), out.stride(0), batch, num_heads, nq, nk, 64, 0.125,
+                                                      dropout[0], dropout[1], dropout[2], _stream())
+        else:
+            rc = _lib.load().unirec_attention(q.data_ptr(), q.stride(0), 0 if q_broadcast else nq, k.data_ptr(),
+                                              k.stride(0), v.data_ptr(), v.stride(0), nk, _ptr(key_mask), out.data_ptr(),
+                                              out.stride(0), batch, num_heads, nq, nk, 64, 0.125, _stream())
     _lib.check(rc, "unirec_attention")
     return out
+
+
+def dropout_threshold(p: float) -> int:
+    """thr16 = round(p * 65536): an element is dropped iff its 16-bit Philox value is below thr16."""
+    if not 0.0 <= p < 1.0:
+        raise ValueError(f"dropout probability has to be in [0, 1), got {p}")
+    return int(round(p * 65536.0))
+
+
+def dropout_add(x: torch.Tensor, residual: Optional[torch.Tensor], dropout: Tuple[int, int, int], *,
+                rows: Optional[int] = None, x_row_mod: int = 0) -> torch.Tensor:
+    """out = dropout(x) [+ residual]; bf16 [rows, H].  With x_row_mod > 0, x has x_row_mod rows broadcast over `rows`."""
+    _req(x, torch.bfloat16, "dropout_add.x")
+    xr, H, ldx = _rows2d(x, "dropout_add.x")
+    rows = xr if rows is None else rows
+    ldres = 0
+    if residual is not None:
+        _req(residual, torch.bfloat16, "dropout_add.residual")
+        _, _, ldres = _rows2d(residual, "dropout_add.residual")
+    out = torch.empty(rows, H, device=x.device, dtype=torch.bfloat16)
+    rc = _lib.load().unirec_dropout_add(x.data_ptr(), ldx, x_row_mod, _ptr(residual), ldres, out.data_ptr(), H, rows, H,
+                                        dropout[0], dropout[1], dropout[2], _stream())
+    _lib.check(rc, "unirec_dropout_add")
+    return out
+
+
+def dropout_backward(dy: torch.Tensor, dropout: Tuple[int, int, int]) -> torch.Tensor:
+    """dx = dy o mask * scale for the mask of (thr16, seed, site); bf16 [rows, H]."""
+    _req(dy, torch.bfloat16, "dropout_backward.dy")
+    rows, H, lddy = _rows2d(dy, "dropout_backward.dy")
+    dx = torch.empty(rows, H, device=dy.device, dtype=torch.bfloat16)
+    rc = _lib.load().unirec_dropout_backward(dy.data_ptr(), lddy, dx.data_ptr(), H, rows, H, dropout[0], dropout[1],
+                                             dropout[2], _stream())
+    _lib.check(rc, "unirec_dropout_backward")
+    return dx
 
 
 def cast_bf16(x: torch.Tensor) -> torch.Tensor:
@@ -384,7 +426,7 @@ def layernorm_backward(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, e
 
 def attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, dout: torch.Tensor, dq: torch.Tensor,
                        dk: torch.Tensor, dv: torch.Tensor, *, batch: int, num_heads: int, nq: int, nk: int,
-                       key_mask: Optional[torch.Tensor] = None):
+                       key_mask: Optional[torch.Tensor] = None, dropout: Optional[Tuple[int, int, int]] = None):
     """Backward of `attention` for nq, nk <= 64; dq/dk/dv are preallocated bf16 row views (written in place)."""
     for t_, n in ((q, "q"), (k, "k"), (v, "v"), (dout, "dout"), (dq, "dq"), (dk, "dk"), (dv, "dv")):
         _req(t_, torch.bfloat16, f"attention_backward.{n}")
@@ -392,8 +434,9 @@ def attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, dout: 
             raise RuntimeError("attention_backward: tensors must be 2-D row views")
     if key_mask is not None:
         _req(key_mask, torch.float32, "attention_backward.key_mask")
-    rc = _lib.load().unirec_attention_backward(q.data_ptr(), q.stride(0), nq, k.data_ptr(), k.stride(0), v.data_ptr(),
-                                               v.stride(0), nk, _ptr(key_mask), dout.data_ptr(), dout.stride(0),
-                                               dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(),
-                                               dv.stride(0), batch, num_heads, nq, nk, 64, 0.125, _stream())
-    _lib.check(rc, "unirec_attention_backward")
+    thr16, seed, site = dropout if dropout is not None else (0, 0, 0)
+    rc = _lib.load().unirec_attention_dropout_backward(
+        q.data_ptr(), q.stride(0), nq, k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), nk, _ptr(key_mask),
+        dout.data_ptr(), dout.stride(0), dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(),
+        dv.stride(0), batch, num_heads, nq, nk, 64, 0.125, thr16, seed, site, _stream())
+    _lib.check(rc, "unirec_attention_dropout_backward")

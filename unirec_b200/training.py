@@ -8,8 +8,11 @@ place (MN-major operands, no transposes), fp32 split-K accumulation of weight gr
 small-tile attention backward kernels.  Heads are `LinearFn` (same GEMM kernels).  Loss, optimizer (AdamW) and the
 NCCL all-reduce stay in PyTorch.
 
-Dropout: the CUDA path implements dropout = identity.  `model.train()` is accepted only with dropout = 0.0
-(parity of a random mask is undefined anyway); construct the module with dropout=0.0 for training.
+Dropout (train mode, models/qformer.py:107, :258, :287, :373): masks are a pure function of (seed, site, element)
+through Philox4x32-10 (csrc/dropout.cuh), regenerated - never stored - in the backward pass; one fresh seed per forward
+call.  The oracle reproduces the same masks on the CPU (oracle/dropout_masks.py), which is what makes a dropped
+forward / backward comparable at all.  Probability dropout runs inside the attention kernels; the hidden-state sites
+are `dropout_add` (dropout(dense) + residual, one streaming pass) in front of the LayerNorm.
 """
 from __future__ import annotations
 
@@ -53,9 +56,23 @@ class BackboneTrainFn(torch.autograd.Function):
     backward (models/qformer.py:804-972 under autograd).  Inputs after `mask` are the live parameters in the order
     of QFormerBackbone._live_params(); gradients are returned in the same order."""
 
+    SITE_EMBEDDINGS = 0
+    KIND_SELF_PROBS, KIND_SELF_OUT, KIND_CROSS_PROBS, KIND_CROSS_OUT, KIND_FFN_OUT = range(5)
+
     @staticmethod
-    def forward(ctx, backbone, enc, mask, query_embeddings, *params):
+    def forward(ctx, backbone, drop, enc, mask, query_embeddings, *params):
+        """drop = None (dropout off) or (thr16, seed)."""
         cfg = backbone.config
+
+        def site(layer, kind):
+            return None if drop is None else (drop[0], drop[1], 1 + 8 * layer + kind)
+
+        def dense_residual(x, w, b, res, st):
+            # dropout(dense(x)) + res: fused into the GEMM epilogue when there is no dropout
+            if st is None:
+                return ops.linear(x, w, b, epilogue=ops.EPI_BIAS_RESIDUAL, residual=res)
+            return ops.dropout_add(ops.linear(x, w, b), res, st)
+
         B, S, E = enc.shape
         H, heads = cfg.hidden_size, cfg.num_attention_heads
         Q = query_embeddings.shape[1]
@@ -64,32 +81,39 @@ class BackboneTrainFn(torch.autograd.Function):
         m = None if mask is None else mask.to(device=enc.device, dtype=torch.float32).contiguous()
         kv_all = ops.linear(enc2, pk["w_kv_all"], pk["b_kv_all"]) if pk["w_kv_all"] is not None else None
         q0 = query_embeddings.detach().reshape(Q, H).float().contiguous()
-        h = ops.layernorm(q0, pk["emb_g"], pk["emb_b"], cfg.layer_norm_eps, rows=B * Q, in_row_mod=Q)
+        if drop is None:
+            h = ops.layernorm(q0, pk["emb_g"], pk["emb_b"], cfg.layer_norm_eps, rows=B * Q, in_row_mod=Q)
+        else:
+            h = ops.dropout_add(ops.layernorm(q0, pk["emb_g"], pk["emb_b"], cfg.layer_norm_eps), None,
+                                (drop[0], drop[1], BackboneTrainFn.SITE_EMBEDDINGS), rows=B * Q, x_row_mod=Q)
+        K = BackboneTrainFn
         tape = []
-        for L in pk["layers"]:
+        for li, L in enumerate(pk["layers"]):
             t = {"h_in": h}
             qkv = ops.linear(h, L["w_qkv"], L["b_qkv"])
-            ctxt = ops.attention(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], batch=B, num_heads=heads, nq=Q, nk=Q)
-            pre1 = ops.linear(ctxt, L["w_o"], L["b_o"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=h)
+            ctxt = ops.attention(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], batch=B, num_heads=heads, nq=Q, nk=Q,
+                                 dropout=site(li, K.KIND_SELF_PROBS))
+            pre1 = dense_residual(ctxt, L["w_o"], L["b_o"], h, site(li, K.KIND_SELF_OUT))
             h = ops.layernorm(pre1, L["ln1_g"], L["ln1_b"], cfg.layer_norm_eps)
             t.update(qkv=qkv, ctx=ctxt, pre1=pre1, h1=h)
             if L["cross"]:
                 qc = ops.linear(h, L["w_qc"], L["b_qc"])
                 off = L["kv_slot"] * 2 * H
                 ctxc = ops.attention(qc, kv_all[:, off:off + H], kv_all[:, off + H:off + 2 * H], batch=B, num_heads=heads,
-                                     nq=Q, nk=S, key_mask=m)
-                pre2 = ops.linear(ctxc, L["w_oc"], L["b_oc"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=h)
+                                     nq=Q, nk=S, key_mask=m, dropout=site(li, K.KIND_CROSS_PROBS))
+                pre2 = dense_residual(ctxc, L["w_oc"], L["b_oc"], h, site(li, K.KIND_CROSS_OUT))
                 h = ops.layernorm(pre2, L["ln2_g"], L["ln2_b"], cfg.layer_norm_eps)
                 t.update(qc=qc, ctxc=ctxc, pre2=pre2, h2=h)
             z = ops.linear(h, L["w_1"], L["b_1"])
             a = ops.gelu(z)
-            pre3 = ops.linear(a, L["w_2"], L["b_2"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=h)
+            pre3 = dense_residual(a, L["w_2"], L["b_2"], h, site(li, K.KIND_FFN_OUT))
             h = ops.layernorm(pre3, L["ln3_g"], L["ln3_b"], cfg.layer_norm_eps)
             t.update(z=z, a=a, pre3=pre3)
             tape.append(t)
         ctx.backbone, ctx.tape, ctx.kv_all, ctx.enc2, ctx.mask = backbone, tape, kv_all, enc2, m
         ctx.dims = (B, S, Q, H, heads)
         ctx.q0 = q0
+        ctx.drop = drop
         return h.view(B, Q, H).float()
 
     @staticmethod
@@ -104,6 +128,15 @@ class BackboneTrainFn(torch.autograd.Function):
         M = B * Q
         on_ready: Optional[Callable[[int, List[torch.Tensor]], None]] = getattr(bb, "grad_ready_hook", None)
         on_finish: Optional[Callable[[], None]] = getattr(bb, "grad_finish_hook", None)
+        drop = ctx.drop
+        K = BackboneTrainFn
+
+        def site(layer, kind):
+            return None if drop is None else (drop[0], drop[1], 1 + 8 * layer + kind)
+
+        def dense_grad(dpre, st):
+            # gradient of the dense output behind dropout(dense) + residual
+            return dpre if st is None else ops.dropout_backward(dpre, st)
 
         def zeros(*shape):
             return torch.zeros(*shape, device=dev, dtype=torch.float32)
@@ -126,7 +159,7 @@ class BackboneTrainFn(torch.autograd.Function):
             # ---- query FFN: h_out = LN3(a W2^T + b2 + h_mid), a = gelu(h_mid W1^T + b1)
             g["ln3_g"], g["ln3_b"] = zeros(H), zeros(H)
             dpre3 = ops.layernorm_backward(t["pre3"], dy, L["ln3_g"], eps, g["ln3_g"], g["ln3_b"], dy2=dy2)
-            da, g["w_2"], g["b_2"] = lin_bwd(dpre3, t["a"], L["w_2"])
+            da, g["w_2"], g["b_2"] = lin_bwd(dense_grad(dpre3, site(li, K.KIND_FFN_OUT)), t["a"], L["w_2"])
             dz = ops.gelu_backward(t["z"], da)
             h_mid = t["h2"] if L["cross"] else t["h1"]
             dh_mid, g["w_1"], g["b_1"] = lin_bwd(dz, h_mid, L["w_1"])
@@ -134,22 +167,23 @@ class BackboneTrainFn(torch.autograd.Function):
             if L["cross"]:
                 g["ln2_g"], g["ln2_b"] = zeros(H), zeros(H)
                 dpre2 = ops.layernorm_backward(t["pre2"], dy, L["ln2_g"], eps, g["ln2_g"], g["ln2_b"], dy2=dy2)
-                dctxc, g["w_oc"], g["b_oc"] = lin_bwd(dpre2, t["ctxc"], L["w_oc"])
+                dctxc, g["w_oc"], g["b_oc"] = lin_bwd(dense_grad(dpre2, site(li, K.KIND_CROSS_OUT)), t["ctxc"], L["w_oc"])
                 off = L["kv_slot"] * 2 * H
                 dqc = torch.empty(M, H, device=dev, dtype=torch.bfloat16)
                 ops.attention_backward(t["qc"], ctx.kv_all[:, off:off + H], ctx.kv_all[:, off + H:off + 2 * H], dctxc, dqc,
                                        d_kv_all[:, off:off + H], d_kv_all[:, off + H:off + 2 * H], batch=B, num_heads=heads,
-                                       nq=Q, nk=S, key_mask=ctx.mask)
+                                       nq=Q, nk=S, key_mask=ctx.mask, dropout=site(li, K.KIND_CROSS_PROBS))
                 dh1, g["w_qc"], g["b_qc"] = lin_bwd(dqc, t["h1"], L["w_qc"])
                 dy, dy2 = dpre2, dh1
             # ---- self-attention block: h1 = LN1(ctx Wo^T + bo + h_in)
             g["ln1_g"], g["ln1_b"] = zeros(H), zeros(H)
             dpre1 = ops.layernorm_backward(t["pre1"], dy, L["ln1_g"], eps, g["ln1_g"], g["ln1_b"], dy2=dy2)
-            dctx, g["w_o"], g["b_o"] = lin_bwd(dpre1, t["ctx"], L["w_o"])
+            dctx, g["w_o"], g["b_o"] = lin_bwd(dense_grad(dpre1, site(li, K.KIND_SELF_OUT)), t["ctx"], L["w_o"])
             qkv = t["qkv"]
             dqkv = torch.empty(M, 3 * H, device=dev, dtype=torch.bfloat16)
             ops.attention_backward(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], dctx, dqkv[:, :H], dqkv[:, H:2 * H],
-                                   dqkv[:, 2 * H:], batch=B, num_heads=heads, nq=Q, nk=Q)
+                                   dqkv[:, 2 * H:], batch=B, num_heads=heads, nq=Q, nk=Q,
+                                   dropout=site(li, K.KIND_SELF_PROBS))
             dh_in, g["w_qkv"], g["b_qkv"] = lin_bwd(dqkv, t["h_in"], L["w_qkv"])
             dy, dy2 = dpre1, dh_in
             layer_grads[li] = g
@@ -161,7 +195,10 @@ class BackboneTrainFn(torch.autograd.Function):
         if n_cross:
             _, g_kv_w, g_kv_b = lin_bwd(d_kv_all, ctx.enc2, pk["w_kv_all"], need_dx=False)
         # ---- query-token LayerNorm (batch-invariant): sum over the batch, then a [Q, H] LayerNorm backward (torch)
-        dh0 = (dy.float() + dy2.float()).view(B, Q, H).sum(dim=0)
+        dh0 = dy.float() + dy2.float()
+        if drop is not None:
+            dh0 = ops.dropout_backward(dh0.to(torch.bfloat16), (drop[0], drop[1], K.SITE_EMBEDDINGS)).float()
+        dh0 = dh0.view(B, Q, H).sum(dim=0)
         with torch.enable_grad():
             q0 = ctx.q0.clone().requires_grad_(True)
             eg = pk["emb_g"].clone().requires_grad_(True)
@@ -184,7 +221,7 @@ class BackboneTrainFn(torch.autograd.Function):
             on_ready(-1, ([g_kv_w, g_kv_b] if n_cross else []) + [eg.grad, eb.grad, d_query])
         if on_finish is not None:
             on_finish()        # every bucket reduced and written back before autograd sees the gradients
-        return (None, None, None, d_query) + tuple(grads)
+        return (None, None, None, None, d_query) + tuple(grads)
 
 
 def qformer_loss(outputs, field_embeddings, attention_mask, pos_rep=None, neg_rep=None, recon_weight: float = 1.0,
