@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--train-batch", type=int, default=1024, help="GLOBAL batch of the cfg-2 training block (0 = skip)")
     ap.add_argument("--train-steps", type=int, default=4)
+    ap.add_argument("--train-dropout", type=float, default=0.2, help="dropout of the cfg-2 training block "
+                    "(reference default 0.2, models/qformer_utils.py:19)")
     ap.add_argument("--profile-range", default="", choices=["", "items", "users"],
                     help="bracket that timed region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     return ap.parse_args()
@@ -183,7 +185,9 @@ def run_reference(args, rank, world):
 def run_train_block(args, rank, world, dev, barrier, max_over_ranks, pk):
     """BASELINE config 2: item Q-Former training step (fwd + QFormerLoss + bwd + gradient all-reduce + AdamW),
     global batch args.train_batch split over the ranks (strong scaling), bf16 activations / fp32 master weights,
-    dropout 0 (the CUDA path's dropout is identity).  Returns the "train" block of the JSON line."""
+    train-mode dropout args.train_dropout (Philox masks inside the kernels).  Primary step = anchor forward + backward
+    (positive / negative representations given); the "reference_faithful" step adds the two no-grad train-mode
+    forwards of training/item_qformer_training.py:122-125.  Returns the "train" block of the JSON line."""
     import torch
     from unirec_b200 import _lib, ops
     from unirec_b200.modules import QFormerForItemRepresentation
@@ -192,7 +196,8 @@ def run_train_block(args, rank, world, dev, barrier, max_over_ranks, pk):
     Bl = Bg // world
     torch.manual_seed(0)
     with torch.device(dev):
-        model = QFormerForItemRepresentation(num_fields=14, dropout=0.0).train()
+        model = QFormerForItemRepresentation(num_fields=14, dropout=args.train_dropout).train()
+    model.dropout_seed = 1000 + rank * 1_000_003
     opt = torch.optim.AdamW([p for p in model.parameters()], lr=1e-4, fused=True)
     red = GradientAllReducer().attach(model.qformer)
     head_params = (list(model.item_representation_head.parameters()) + list(model.reconstruction_head.parameters()) +
@@ -205,9 +210,14 @@ def run_train_block(args, rank, world, dev, barrier, max_over_ranks, pk):
     pos = torch.randn(Bl, 1024, device=dev, generator=gen)
     neg = torch.randn(Bl, 1024, device=dev, generator=gen)
 
-    def step(i):
+    def step(i, faithful=False):
         out = model(fields[i % nb], mask)
-        loss = qformer_loss(out, fields[i % nb], mask, pos, neg)
+        p_rep, n_rep = pos, neg
+        if faithful:
+            with torch.no_grad():
+                p_rep = model(fields[(i + 1) % nb], mask)["item_representation"]
+                n_rep = model(fields[(i + 2) % nb], mask)["item_representation"]
+        loss = qformer_loss(out, fields[i % nb], mask, p_rep, n_rep)
         loss.backward()
         red.reduce_params(head_params)
         opt.step()
@@ -228,6 +238,15 @@ def run_train_block(args, rank, world, dev, barrier, max_over_ranks, pk):
     ms = max_over_ranks(e0.elapsed_time(e1)) / args.train_steps
     stats = ops.stop_timing()
     launches = (_lib.launch_count() - l0) // args.train_steps
+    step(0, faithful=True)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.train_steps):
+        step(i, faithful=True)
+    f1.record()
+    barrier()
+    ms_faithful = max_over_ranks(f0.elapsed_time(f1)) / args.train_steps
     gemm = stats.get("gemm")
     ach = gemm[1] / (gemm[2] * 1e-3) / 1e12 if gemm and gemm[2] > 0 else None
     items_per_sec = Bg / (ms * 1e-3)
@@ -236,7 +255,10 @@ def run_train_block(args, rank, world, dev, barrier, max_over_ranks, pk):
     return {
         "metric": "items/sec (item Q-Former training step: fwd + QFormerLoss + bwd + grad all-reduce + AdamW)",
         "value": items_per_sec, "unit": "items/s", "global_batch": Bg, "per_gpu_batch": Bl, "ms_per_step": ms,
-        "scaling": "strong", "dtype": "bf16 activations, fp32 master weights / gradients", "dropout": 0.0,
+        "scaling": "strong", "dtype": "bf16 activations, fp32 master weights / gradients",
+        "dropout": args.train_dropout,
+        "reference_faithful_step": {"what": "anchor fwd+bwd + two no-grad train-mode forwards (positive, negative)",
+                                    "ms_per_step": ms_faithful, "items_per_s": Bg / (ms_faithful * 1e-3)},
         "final_loss": float(loss.detach()), "gpu_launches_per_step": launches,
         "allreduce_bytes_per_step": red.bytes_reduced // max(args.train_steps + 2, 1),
         "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
