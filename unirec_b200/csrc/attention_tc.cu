@@ -21,7 +21,9 @@
 //                P (bf16) -> shared memory (K-major, swizzled) for the second MMA.  The running max is only
 //                raised when a tile exceeds it by more than 2^8 (exact: O and the row sum are accumulated against the
 //                same reference value), so O in TMEM is almost never rescaled.  Also builds Q2 for the NEXT item.
-//     warp 4     TMA producer: K and V tiles through two 2-stage rings
+//     warp 4     TMA producer: K tiles through a 3-stage ring, V tiles through a 2-stage ring.  P(g) is written IN PLACE
+//                over K(g) (same 32 KB footprint; K(g) is dead once S(g) has been accumulated), so the K slot is only
+//                released by PV(g) - P is effectively triple-buffered and the softmax of tile g+1 never waits for PV(g)
 //     warp 5     TMEM allocator + UMMA issuer; issue order S(g+1), PV(g) so that the softmax of tile g overlaps
 //                the first MMA of tile g+1 (two S accumulators in TMEM) - across work items too
 // Mask semantics are those of attention.cu: key_mask == 0 adds -1e30 (log2 domain), keys beyond nk are excluded
@@ -35,7 +37,8 @@ constexpr int AT_KT = 128;                       // keys per tile
 constexpr int AT_SLAB = 128 * 64 * 2;            // [128 rows][64 bf16] = 16 KB
 constexpr int AT_TILE = 2 * AT_SLAB;             // 32 KB: Q2, a K tile, a V tile, P
 constexpr int AT_THREADS = 192;
-constexpr int AT_SMEM_BYTES = 2 * AT_TILE /*Q2 x2*/ + 2 * AT_TILE /*K x2*/ + 2 * AT_TILE /*V x2*/ + AT_TILE /*P*/ +
+constexpr int AT_KSTAGES = 3;                    // K ring depth (a K slot is reused as that tile's P)
+constexpr int AT_SMEM_BYTES = 2 * AT_TILE /*Q2 x2*/ + AT_KSTAGES * AT_TILE /*K|P x3*/ + 2 * AT_TILE /*V x2*/ +
                               2 * AT_KT * 4 /*mask*/ + 32 /*flags*/ + 1024 /*align*/ + 256 /*barriers*/;
 static_assert(AT_SMEM_BYTES <= 232448, "shared memory budget exceeded");
 constexpr float AT_MASKED = -1.0e30f;
@@ -77,24 +80,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
     const int lane = threadIdx.x & 31;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ2 = smem;                          // [2][2 slabs]
-    uint8_t* sK = smem + 2 * AT_TILE;             // [2][2 slabs]
-    uint8_t* sV = smem + 4 * AT_TILE;             // [2][2 slabs]
-    uint8_t* sP = smem + 6 * AT_TILE;             // [2 slabs]
+    uint8_t* sK = smem + 2 * AT_TILE;             // [3][2 slabs]  K(g), later P(g)
+    uint8_t* sV = smem + 5 * AT_TILE;             // [2][2 slabs]
     float* sMask = reinterpret_cast<float*>(smem + 7 * AT_TILE);   // [2][128]
     int* sPlain = reinterpret_cast<int*>(smem + 7 * AT_TILE + 2 * AT_KT * 4);   // [2][4] per-warp "tile has no masked key"
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * AT_TILE + 2 * AT_KT * 4 + 32);
-    uint64_t* k_full = bars;            // [2]
-    uint64_t* k_empty = bars + 2;       // [2]
-    uint64_t* v_full = bars + 4;        // [2]
-    uint64_t* v_empty = bars + 6;       // [2]
-    uint64_t* q_ready = bars + 8;       // [2]  softmax warps -> issuer
-    uint64_t* q_free = bars + 10;       // [2]  issuer (commit) -> softmax warps
-    uint64_t* s_full = bars + 12;       // [2]  issuer (commit) -> softmax warps
-    uint64_t* s_free = bars + 14;       // [2]  softmax warps -> issuer
-    uint64_t* p_ready = bars + 16;      // softmax warps -> issuer
-    uint64_t* pv_done = bars + 17;      // issuer (commit) -> softmax warps
-    uint64_t* o_free = bars + 18;       // softmax warps -> issuer (O of the finished item has been read)
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 19);
+    uint64_t* k_full = bars;            // [3]
+    uint64_t* k_empty = bars + 3;       // [3]  issuer (commit after PV: the slot held K, then P)
+    uint64_t* v_full = bars + 6;        // [2]
+    uint64_t* v_empty = bars + 8;       // [2]
+    uint64_t* q_ready = bars + 10;      // [2]  softmax warps -> issuer
+    uint64_t* q_free = bars + 12;       // [2]  issuer (commit) -> softmax warps
+    uint64_t* s_full = bars + 14;       // [2]  issuer (commit) -> softmax warps
+    uint64_t* s_free = bars + 16;       // [2]  softmax warps -> issuer
+    uint64_t* p_ready = bars + 18;      // softmax warps -> issuer
+    uint64_t* pv_done = bars + 19;      // issuer (commit) -> softmax warps
+    uint64_t* o_free = bars + 20;       // softmax warps -> issuer (O of the finished item has been read)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 21);
 
     const int T = (p.nk + AT_KT - 1) / AT_KT;
     const int my_items = (p.num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
@@ -105,8 +107,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
     if (warp_idx == 4 && lane == 0) {
         tma_prefetch_desc(&tmap_k);
         tma_prefetch_desc(&tmap_v);
+        for (int i = 0; i < AT_KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
             mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
             mbar_init(&q_ready[i], 4); mbar_init(&q_free[i], 1);
             mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4);
@@ -134,13 +136,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
             const int b = w / pairs, hp = w - b * pairs;
             const int slot = g & 1;
             const uint32_t ph = (g >> 1) & 1;
+            const int kslot = g % AT_KSTAGES;
+            const uint32_t kph = (g / AT_KSTAGES) & 1;
             const int row = b * p.kv_batch_rows + t * AT_KT;
             const int col = hp * 128;
-            mbar_wait(&k_empty[slot], ph ^ 1);
+            mbar_wait(&k_empty[kslot], kph ^ 1);
             if (lane == 0) {
-                mbar_arrive_expect_tx(&k_full[slot], AT_TILE);
-                tma_load_2d(&tmap_k, &k_full[slot], sK + slot * AT_TILE, col, row);
-                tma_load_2d(&tmap_k, &k_full[slot], sK + slot * AT_TILE + AT_SLAB, col + 64, row);
+                mbar_arrive_expect_tx(&k_full[kslot], AT_TILE);
+                tma_load_2d(&tmap_k, &k_full[kslot], sK + kslot * AT_TILE, col, row);
+                tma_load_2d(&tmap_k, &k_full[kslot], sK + kslot * AT_TILE + AT_SLAB, col + 64, row);
             }
             __syncwarp();
             mbar_wait(&v_empty[slot], ph ^ 1);
@@ -159,20 +163,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
             const int it = g / T, t = g - it * T;
             const int slot = g & 1;
             const uint32_t ph = (g >> 1) & 1;
+            const int kslot = g % AT_KSTAGES;
             if (t == 0) mbar_wait(&q_ready[it & 1], (it >> 1) & 1);
-            mbar_wait(&k_full[slot], ph);
+            mbar_wait(&k_full[kslot], (g / AT_KSTAGES) & 1);
             mbar_wait(&s_free[slot], ph ^ 1);
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t a_addr = smem_u32(sQ2 + (it & 1) * AT_TILE);
-                const uint32_t b_addr = smem_u32(sK + slot * AT_TILE);
+                const uint32_t b_addr = smem_u32(sK + kslot * AT_TILE);
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
                     const uint32_t off = (ks >> 2) * AT_SLAB + (ks & 3) * 32;
                     umma_bf16_ss(tmem_base + slot * 128, umma_smem_desc_sw128(a_addr + off),
                                  umma_smem_desc_sw128(b_addr + off), idesc_s, ks != 0 ? 1u : 0u);
                 }
-                umma_commit(&k_empty[slot]);
                 umma_commit(&s_full[slot]);
                 if (t == T - 1) umma_commit(&q_free[it & 1]);
             }
@@ -187,7 +191,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
             if (t == 0 && it > 0) mbar_wait(o_free, (it - 1) & 1);
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t a_addr = smem_u32(sP);
+                const uint32_t a_addr = smem_u32(sK + (g % AT_KSTAGES) * AT_TILE);   // P(g), written over K(g)
                 const uint32_t b_addr = smem_u32(sV + slot * AT_TILE);
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
@@ -197,6 +201,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
                                  umma_smem_desc_mn_sw128(b_addr + b_off, AT_SLAB), idesc_pv, (t | ks) != 0 ? 1u : 0u);
                 }
                 umma_commit(&v_empty[slot]);
+                umma_commit(&k_empty[g % AT_KSTAGES]);
                 umma_commit(pv_done);
             }
             __syncwarp();
@@ -317,12 +322,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
                 m_used = mx;
                 l_run *= alpha;
             }
-            if (g > 0) {
-                // PV(g-1) must be complete before P is overwritten and before O is rescaled
+            // PV(g-1) only has to be complete before O is rescaled (rare: lazy max).  P(g) goes into K(g)'s slot, which
+            // the tensor core finished reading when s_full[g] completed, so the exponentials below never wait for it.
+            bool pv_seen = (g == 0);
+            if (t > 0 && __any_sync(0xffffffffu, raise)) {
                 mbar_wait(pv_done, (g - 1) & 1);
                 tc_fence_after();
-            }
-            if (t > 0 && __any_sync(0xffffffffu, raise)) {
+                pv_seen = true;
                 const uint32_t tmem_orow = tmem_o + lane_field + hsel * 64;
 #pragma unroll 1
                 for (int c = 0; c < 2; ++c) {
@@ -349,12 +355,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
                     pk[j >> 1] = pack_bf16(p0, p1);
                 }
                 l_run += psum;
-                uint8_t* prow = sP + (c >> 1) * AT_SLAB;
+                uint8_t* prow = sK + (g % AT_KSTAGES) * AT_TILE + (c >> 1) * AT_SLAB;
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     *reinterpret_cast<uint4*>(prow + swz128(r, (c & 1) * 4 + j)) =
                         make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
             }
+            // every phase of pv_done is consumed in order, and phase g-1 before p_ready(g) is signalled: PV(g) cannot be
+            // issued earlier, so the barrier is never more than one phase ahead of this thread's parity bookkeeping
+            if (!pv_seen) mbar_wait(pv_done, (g - 1) & 1);
             tc_fence_before();               // orders the O rescale (tcgen05.st) before the issuer's next MMA
             fence_proxy_async_smem();        // P writes -> visible to the tensor core
             __syncwarp();
