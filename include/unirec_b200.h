@@ -90,10 +90,15 @@ int unirec_field_projection(const void* rec, const float* Wp, const float* bp, v
  * training/user_qformer_training.py:153-161): seq[b, h*Q+q, :] = table[history[b,h], q, :] (+ ctx[b,h,:])
  * + PE[h*Q+q, :] for h < lengths[b], 0 otherwise; mask[b,s] = s < lengths[b]*Q.
  * table bf16 [num_items, Q, D]; history int64 [B, Hmax]; lengths int32 [B]; ctx bf16 [B,Hmax,D] or NULL;
+ * pe_table fp32 [Hmax*Q, D] from unirec_positional_encoding, or NULL (PE evaluated in the kernel: slower, same values);
  * seq bf16 [B, Hmax*Q, D]; mask fp32 [B, Hmax*Q]. */
 int unirec_build_user_sequence(const void* table, int64_t num_items, const int64_t* history,
-                               const int32_t* lengths, const void* ctx, void* seq, float* mask,
+                               const int32_t* lengths, const void* ctx, const float* pe_table, void* seq, float* mask,
                                int64_t B, int64_t Hmax, int64_t Q, int64_t D, void* stream);
+
+/* pe_table[p, 2i] = sin(p * w_i), pe_table[p, 2i+1] = cos(p * w_i), w_i = exp(-(2i) ln(10000) / D)
+ * (PositionalEncoding buffer, models/user_sequence_encoder.py:20-24); fp32 [S, D], D even. */
+int unirec_positional_encoding(float* pe_table, int64_t S, int64_t D, void* stream);
 
 /* inv[r] = 1 / max(||x_r||_2, eps)  (F.normalize, training/train_item_individual_token_joint.py:405-406,412). */
 int unirec_inv_l2_norm(const void* x, int x_fp32, int64_t ldx, float* inv, int64_t rows, int64_t D,

@@ -286,3 +286,8 @@ def test_build_user_sequence_matches_oracle():
         assert torch.equal(mask.cpu(), ref_mask)
         # bf16 output rounding of values up to ~5
         torch.testing.assert_close(seq.cpu().float(), ref_seq, rtol=1e-2, atol=2e-2)
+        # the precomputed PE table and the in-kernel evaluation are the same closed form: identical outputs
+        seq2, mask2 = ops.build_user_sequence(table, history.to(_dev()), lengths.to(_dev()), c, use_pe_table=False)
+        assert torch.equal(seq, seq2) and torch.equal(mask, mask2)
+    pe = ops.positional_encoding_table(Hmax * Q, D, _dev())
+    torch.testing.assert_close(pe.cpu(), O.positional_encoding_table(Hmax * Q, D), rtol=0, atol=2e-4)

@@ -33,8 +33,9 @@ _SIGNATURES = {
     "unirec_mean_tokens": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p]),
     "unirec_field_projection": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64,
                                         c_int64, c_void_p]),
-    "unirec_build_user_sequence": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+    "unirec_build_user_sequence": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    "unirec_positional_encoding": (c_int, [c_void_p, c_int64, c_int64, c_void_p]),
     "unirec_inv_l2_norm": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_int64, c_float, c_void_p]),
     "unirec_score_topk_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
     "unirec_score_topk": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64,

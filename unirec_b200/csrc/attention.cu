@@ -33,13 +33,9 @@
 namespace unirec {
 
 struct AttnParams {
-    const __nv_bfloat16* q; long long ldq; long long q_batch_rows;   // 0 => same queries for every batch
-    const __nv_bfloat16* k; long long ldk;
-    const __nv_bfloat16* v; long long ldv;
-    long long kv_batch_rows;
     const float* key_mask;   // [B, nk] (1 attend / 0 masked) or nullptr
-    __nv_bfloat16* out; long long ldo;
     int num_heads, nq, nk;
+    int q_broadcast;         // 1: the same queries serve every batch element
     float scale_log2;        // softmax scale * log2(e)
     DropoutParams drop;      // train-mode dropout of the probabilities (models/qformer.py:258); DROP kernels only
 };
@@ -48,63 +44,76 @@ constexpr float kMaskedLog2 = -1.0e30f;  // stands in for finfo.min (see header 
 
 constexpr int ATT_STAGES = 3;
 
+// Shared-memory plan (all tiles are 128-byte rows written by TMA with the 128-byte swizzle, 1 KB aligned):
+//   sQ [STAGES][nq_pad]  Q tile of the work item (by item index), one 16-row TMA box per warp
+//   sK, sV [STAGES][KT]  key / value tiles (by flat tile index)
+//   sO [2][nq_pad]       context staging for the per-warp TMA stores (two in flight)
+//   sM [STAGES][KT]      additive mask (log2 domain), full[STAGES] mbarriers
 template <int KT, bool DROP>
 __global__ void __launch_bounds__(128)
-attention_kernel(const AttnParams p, int num_items) {
-    extern __shared__ __align__(128) uint8_t smem[];
+attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
+                 const AttnParams p, int num_items) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int nq_pad = nwarps * 16;
 
-    uint8_t* sQ = smem;                                         // ATT_STAGES x nq_pad rows x 128 B
-    uint8_t* sK = sQ + ATT_STAGES * nq_pad * 128;               // ATT_STAGES x KT rows x 128 B
-    uint8_t* sV = sK + ATT_STAGES * KT * 128;                   // ATT_STAGES x KT rows x 128 B
-    float* sM = reinterpret_cast<float*>(sV + ATT_STAGES * KT * 128);   // ATT_STAGES x KT additive mask (log2 domain)
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + ATT_STAGES * nq_pad * 128;
+    uint8_t* sV = sK + ATT_STAGES * KT * 128;
+    uint8_t* sO = sV + ATT_STAGES * KT * 128;
+    float* sM = reinterpret_cast<float*>(sO + 2 * nq_pad * 128);
+    uint64_t* full = reinterpret_cast<uint64_t*>(sM + ATT_STAGES * KT);
 
     const int ntiles = (p.nk + KT - 1) / KT;                    // key tiles per work item
     const int my_items = (num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                          static_cast<int>(gridDim.x);
     const int total = my_items * ntiles;                        // flat tile count of this CTA
+    // no additive mask at all (self-attention, full last tile): the select in the softmax is skipped
+    const bool plain = (p.key_mask == nullptr) && (p.nk % KT == 0);
 
-    // issue the loads of flat tile g (and the item's Q tile when it is the item's first key tile)
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_k);
+        tma_prefetch_desc(&tmap_v);
+        tma_prefetch_desc(&tmap_o);
+        for (int i = 0; i < ATT_STAGES; ++i) mbar_init(&full[i], nwarps);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    // Loads of flat tile g: warp 0 fetches the K and V tiles, every warp its own 16 query rows when the tile is the
+    // first of a work item; all of them complete on full[g % STAGES] (one arrival per warp).
     auto issue = [&](int g) {
-        if (g < total) {
-            const int it = g / ntiles, tile = g - it * ntiles;
-            const int w = blockIdx.x + it * gridDim.x;
-            const int b = w / p.num_heads, h = w - b * p.num_heads;
-            const int buf = g % ATT_STAGES;
-            const __nv_bfloat16* kbase = p.k + (static_cast<long long>(b) * p.kv_batch_rows) * p.ldk + h * 64;
-            const __nv_bfloat16* vbase = p.v + (static_cast<long long>(b) * p.kv_batch_rows) * p.ldv + h * 64;
+        if (g >= total) return;
+        const int it = g / ntiles, tile = g - it * ntiles;
+        const int w = blockIdx.x + it * gridDim.x;
+        const int b = w / p.num_heads, h = w - b * p.num_heads;
+        const int buf = g % ATT_STAGES;
+        if (!plain) {
             const float* mbase = p.key_mask ? p.key_mask + static_cast<long long>(b) * p.nk : nullptr;
-            if (tile == 0) {
-                const __nv_bfloat16* qbase = p.q + (static_cast<long long>(b) * p.q_batch_rows) * p.ldq + h * 64;
-                const uint32_t qdst = smem_u32(sQ + (it % ATT_STAGES) * nq_pad * 128);
-                for (int i = threadIdx.x; i < nq_pad * 8; i += blockDim.x) {
-                    const int r = i >> 3, c = i & 7;
-                    const bool ok = r < p.nq;
-                    const long long qr = ok ? r : (p.nq - 1);
-                    cp_async_16(qdst + swz128(r, c), qbase + qr * p.ldq + c * 8, ok);
-                }
-            }
-            const int base = tile * KT;
-            const uint32_t kdst = smem_u32(sK + buf * KT * 128), vdst = smem_u32(sV + buf * KT * 128);
-            for (int i = threadIdx.x; i < KT * 8; i += blockDim.x) {
-                const int r = i >> 3, c = i & 7;
-                const int key = base + r;
-                const bool ok = key < p.nk;
-                const long long kr = ok ? key : (p.nk - 1);
-                cp_async_16(kdst + swz128(r, c), kbase + kr * p.ldk + c * 8, ok);
-                cp_async_16(vdst + swz128(r, c), vbase + kr * p.ldv + c * 8, ok);
-            }
             for (int i = threadIdx.x; i < KT; i += blockDim.x) {
-                const int key = base + i;
+                const int key = tile * KT + i;
                 float m = -INFINITY;  // padding beyond nk: excluded
                 if (key < p.nk) m = (mbase != nullptr && mbase[key] == 0.f) ? kMaskedLog2 : 0.f;
                 sM[buf * KT + i] = m;
             }
         }
-        cp_async_commit();   // always commit (possibly empty) so that group counting stays uniform
+        if (lane == 0) {
+            uint32_t bytes = (tile == 0) ? 16u * 128u : 0u;
+            if (warp == 0) bytes += 2u * KT * 128u;
+            mbar_arrive_expect_tx(&full[buf], bytes);
+            if (tile == 0)
+                tma_load_3d(&tmap_q, &full[buf], sQ + ((it % ATT_STAGES) * nq_pad + warp * 16) * 128, h * 64, warp * 16,
+                            p.q_broadcast ? 0 : b);
+            if (warp == 0) {
+                tma_load_3d(&tmap_k, &full[buf], sK + buf * KT * 128, h * 64, tile * KT, b);
+                tma_load_3d(&tmap_v, &full[buf], sV + buf * KT * 128, h * 64, tile * KT, b);
+            }
+        }
     };
 
 #pragma unroll
@@ -118,18 +127,18 @@ attention_kernel(const AttnParams p, int num_items) {
     for (int g = 0; g < total; ++g) {
         const int it = g / ntiles, tile = g - it * ntiles;
         const int buf = g % ATT_STAGES;
-        cp_async_wait<ATT_STAGES - 2>();   // flat tile g has landed (this thread's part)
-        __syncthreads();                   // ... everyone's part; and everyone is done with flat tile g-1
-        issue(g + ATT_STAGES - 1);         // refills the buffer of flat tile g-1
+        __syncthreads();                   // everyone is done with flat tile g-1 (its buffers are refilled below)
+        issue(g + ATT_STAGES - 1);
+        mbar_wait(&full[buf], (g / ATT_STAGES) & 1);   // flat tile g has landed
 
-        uint8_t* sQi = sQ + (it % ATT_STAGES) * nq_pad * 128;
+        const uint32_t sQi = smem_u32(sQ + (it % ATT_STAGES) * nq_pad * 128);
         if (tile == 0) {
             // Q fragments (A operand, 16 rows x 64 dims = 4 k-steps) stay in registers for the whole item
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
                 const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
                 const int c = kk * 2 + (lane >> 4);
-                ldmatrix_x4(smem_u32(sQi) + swz128(r, c), qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3]);
+                ldmatrix_x4(sQi + swz128(r, c), qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3]);
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
@@ -156,18 +165,27 @@ attention_kernel(const AttnParams p, int num_items) {
         }
 
         // ---- scale + mask, online softmax (log2 domain)
-        const float* mt = sM + buf * KT;
         float mx[2] = {-INFINITY, -INFINITY};
+        if (plain) {
 #pragma unroll
-        for (int j = 0; j < KT / 8; ++j) {
-            const float2 m01 = *reinterpret_cast<const float2*>(mt + 8 * j + 2 * t);
-            // masked keys: the score is absorbed by the huge constant exactly as in the fp32 reference
-            s[j][0] = (m01.x == 0.f) ? s[j][0] * p.scale_log2 : m01.x;
-            s[j][1] = (m01.y == 0.f) ? s[j][1] * p.scale_log2 : m01.y;
-            s[j][2] = (m01.x == 0.f) ? s[j][2] * p.scale_log2 : m01.x;
-            s[j][3] = (m01.y == 0.f) ? s[j][3] * p.scale_log2 : m01.y;
-            mx[0] = fmaxf(mx[0], fmaxf(s[j][0], s[j][1]));
-            mx[1] = fmaxf(mx[1], fmaxf(s[j][2], s[j][3]));
+            for (int j = 0; j < KT / 8; ++j) {
+                s[j][0] *= p.scale_log2; s[j][1] *= p.scale_log2; s[j][2] *= p.scale_log2; s[j][3] *= p.scale_log2;
+                mx[0] = fmaxf(mx[0], fmaxf(s[j][0], s[j][1]));
+                mx[1] = fmaxf(mx[1], fmaxf(s[j][2], s[j][3]));
+            }
+        } else {
+            const float* mt = sM + buf * KT;
+#pragma unroll
+            for (int j = 0; j < KT / 8; ++j) {
+                const float2 m01 = *reinterpret_cast<const float2*>(mt + 8 * j + 2 * t);
+                // masked keys: the score is absorbed by the huge constant exactly as in the fp32 reference
+                s[j][0] = (m01.x == 0.f) ? s[j][0] * p.scale_log2 : m01.x;
+                s[j][1] = (m01.y == 0.f) ? s[j][1] * p.scale_log2 : m01.y;
+                s[j][2] = (m01.x == 0.f) ? s[j][2] * p.scale_log2 : m01.x;
+                s[j][3] = (m01.y == 0.f) ? s[j][3] * p.scale_log2 : m01.y;
+                mx[0] = fmaxf(mx[0], fmaxf(s[j][0], s[j][1]));
+                mx[1] = fmaxf(mx[1], fmaxf(s[j][2], s[j][3]));
+            }
         }
         float alpha[2];
 #pragma unroll
@@ -238,8 +256,8 @@ attention_kernel(const AttnParams p, int num_items) {
         }
 
         if (tile == ntiles - 1) {
-            // ---- normalise and write the context tile through shared memory (this warp's own Q rows of the
-            //      item's Q buffer: nobody else reads them, and the buffer is only refilled two items later)
+            // ---- normalise, stage this warp's 16 context rows (swizzled like a TMA tile) and hand them to the TMA
+            //      store engine: head-merged [B*nq, H] output, rows beyond nq are clipped by the tensor map
             const int w = blockIdx.x + it * gridDim.x;
             const int b = w / p.num_heads, h = w - b * p.num_heads;
             float inv[2];
@@ -250,26 +268,23 @@ attention_kernel(const AttnParams p, int num_items) {
                 l += __shfl_xor_sync(0xffffffffu, l, 2);
                 inv[r] = 1.0f / l;
             }
+            uint8_t* so = sO + ((it & 1) * nq_pad + warp * 16) * 128;
+            if (lane == 0) tma_store_wait_read<1>();    // the store issued from this slot two items ago has read it
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int r0 = warp * 16 + g4;
-                *reinterpret_cast<uint32_t*>(sQi + swz128(r0, j) + 4 * t) = pack_bf16(o[j][0] * inv[0], o[j][1] * inv[0]);
-                *reinterpret_cast<uint32_t*>(sQi + swz128(r0 + 8, j) + 4 * t) =
-                    pack_bf16(o[j][2] * inv[1], o[j][3] * inv[1]);
+                *reinterpret_cast<uint32_t*>(so + swz128(g4, j) + 4 * t) = pack_bf16(o[j][0] * inv[0], o[j][1] * inv[0]);
+                *reinterpret_cast<uint32_t*>(so + swz128(g4 + 8, j) + 4 * t) = pack_bf16(o[j][2] * inv[1], o[j][3] * inv[1]);
             }
+            fence_proxy_async_smem();
             __syncwarp();
-            __nv_bfloat16* obase = p.out + (static_cast<long long>(b) * p.nq) * p.ldo + h * 64;
-            for (int i = lane; i < 16 * 8; i += 32) {
-                const int r = warp * 16 + (i >> 3), c = i & 7;
-                if (r < p.nq) {
-                    const uint4 val = *reinterpret_cast<const uint4*>(sQi + swz128(r, c));
-                    *reinterpret_cast<uint4*>(obase + static_cast<long long>(r) * p.ldo + c * 8) = val;
-                }
+            if (lane == 0) {
+                tma_store_3d(&tmap_o, so, h * 64, warp * 16, b);
+                tma_store_commit();
             }
         }
     }
-    cp_async_wait<0>();
+    if (lane == 0) tma_store_wait_all();    // global writes complete before the CTA exits
 }
 
 template <class K>
@@ -318,14 +333,15 @@ int attention(const void* q, long long ldq, long long q_batch_rows, const void* 
     if (drop_thr16 == 0 && attention_tc_enabled() && attention_tc_supported(num_heads, nq, nk, head_dim, ldk, ldv, kv_batch_rows))
         return attention_tc(q, ldq, q_batch_rows, k, ldk, v, ldv, kv_batch_rows, key_mask, out, ldo, batch, num_heads, nq,
                             nk, scale, stream);
+    if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(k) & 15) ||
+        (reinterpret_cast<uintptr_t>(v) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) {
+        set_last_error("attention: q / k / v / out must be 16-byte aligned");
+        return UNIREC_ERR_BAD_ARG;
+    }
     AttnParams p;
-    p.q = reinterpret_cast<const __nv_bfloat16*>(q); p.ldq = ldq; p.q_batch_rows = q_batch_rows;
-    p.k = reinterpret_cast<const __nv_bfloat16*>(k); p.ldk = ldk;
-    p.v = reinterpret_cast<const __nv_bfloat16*>(v); p.ldv = ldv;
-    p.kv_batch_rows = kv_batch_rows;
     p.key_mask = key_mask;
-    p.out = reinterpret_cast<__nv_bfloat16*>(out); p.ldo = ldo;
     p.num_heads = static_cast<int>(num_heads); p.nq = static_cast<int>(nq); p.nk = static_cast<int>(nk);
+    p.q_broadcast = q_batch_rows == 0 ? 1 : 0;
     p.scale_log2 = scale * 1.4426950408889634f;
     p.drop.thr16 = drop_thr16; p.drop.seed = drop_seed; p.drop.site = drop_site;
     p.drop.scale = 65536.0f / (65536.0f - static_cast<float>(drop_thr16));
@@ -333,8 +349,19 @@ int attention(const void* q, long long ldq, long long q_batch_rows, const void* 
     const int threads = nwarps * 32;
     const int num_items = static_cast<int>(batch * num_heads);
     const int kt = nk <= 16 ? 16 : (nk <= 32 ? 32 : 64);
-    const size_t smem = static_cast<size_t>(ATT_STAGES) *
-                        (static_cast<size_t>(nwarps) * 16 * 128 + 2 * static_cast<size_t>(kt) * 128 + kt * sizeof(float));
+    const size_t smem = 1024 + static_cast<size_t>(ATT_STAGES) * (static_cast<size_t>(nwarps) * 16 * 128 +
+                                                                  2 * static_cast<size_t>(kt) * 128 + kt * sizeof(float)) +
+                        2 * static_cast<size_t>(nwarps) * 16 * 128 + ATT_STAGES * sizeof(uint64_t);
+    const long long hd = num_heads * 64;
+    CUtensorMap tq, tk, tv, to;
+    int rc = make_tmap_bf16_3d(&tq, q, q_batch_rows == 0 ? 1 : batch, nq, hd, ldq, q_batch_rows * ldq, 16);
+    if (rc != UNIREC_OK) return rc;
+    rc = make_tmap_bf16_3d(&tk, k, batch, nk, hd, ldk, kv_batch_rows * ldk, kt);
+    if (rc != UNIREC_OK) return rc;
+    rc = make_tmap_bf16_3d(&tv, v, batch, nk, hd, ldv, kv_batch_rows * ldv, kt);
+    if (rc != UNIREC_OK) return rc;
+    rc = make_tmap_bf16_3d(&to, out, batch, nq, hd, ldo, nq * ldo, 16);
+    if (rc != UNIREC_OK) return rc;
     const int sms = num_sms() > 0 ? num_sms() : 148;
 #define UNIREC_ATT(KT_, DROP_)                                                                                     \
     do {                                                                                                           \
@@ -349,7 +376,7 @@ int attention(const void* q, long long ldq, long long q_batch_rows, const void* 
         }                                                                                                          \
         long long grid = static_cast<long long>(sms) * attention_ctas_per_sm(attention_kernel<KT_, DROP_>, threads, smem); \
         if (grid > num_items) grid = num_items;                                                                    \
-        attention_kernel<KT_, DROP_><<<static_cast<unsigned>(grid), threads, smem, stream>>>(p, num_items);         \
+        attention_kernel<KT_, DROP_><<<static_cast<unsigned>(grid), threads, smem, stream>>>(tq, tk, tv, to, p, num_items); \
     } while (0)
     if (drop_thr16 == 0) {
         if (kt == 16) UNIREC_ATT(16, false);

@@ -19,8 +19,9 @@ int mean_tokens(const void* x, long long ldx, long long B, long long T, long lon
 int field_projection(const void* rec, const float* Wp, const float* bp, void* out, int out_fp32, long long B,
                      long long T, long long F, long long E, cudaStream_t stream);
 int build_user_sequence(const void* table, long long num_items, const long long* history, const int* lengths,
-                        const void* ctx, void* seq, float* mask, long long B, long long Hmax, long long Q, long long D,
-                        cudaStream_t stream);
+                        const void* ctx, const float* pe, void* seq, float* mask, long long B, long long Hmax, long long Q,
+                        long long D, cudaStream_t stream);
+int positional_encoding(float* pe, long long S, long long D, cudaStream_t stream);
 int inv_l2_norm(const void* x, int x_fp32, long long ldx, float* inv, long long rows, long long D, float eps,
                 cudaStream_t stream);
 int attention(const void* q, long long ldq, long long q_batch_rows, const void* k, long long ldk, const void* v,
@@ -121,10 +122,14 @@ int unirec_field_projection(const void* rec, const float* Wp, const float* bp, v
 }
 
 int unirec_build_user_sequence(const void* table, int64_t num_items, const int64_t* history, const int32_t* lengths,
-                               const void* ctx, void* seq, float* mask, int64_t B, int64_t Hmax, int64_t Q, int64_t D,
-                               void* stream) {
-    COUNTED(build_user_sequence(table, num_items, reinterpret_cast<const long long*>(history), lengths, ctx, seq, mask,
-                                B, Hmax, Q, D, static_cast<cudaStream_t>(stream)));
+                               const void* ctx, const float* pe_table, void* seq, float* mask, int64_t B, int64_t Hmax,
+                               int64_t Q, int64_t D, void* stream) {
+    COUNTED(build_user_sequence(table, num_items, reinterpret_cast<const long long*>(history), lengths, ctx, pe_table, seq,
+                                mask, B, Hmax, Q, D, static_cast<cudaStream_t>(stream)));
+}
+
+int unirec_positional_encoding(float* pe_table, int64_t S, int64_t D, void* stream) {
+    COUNTED(positional_encoding(pe_table, S, D, static_cast<cudaStream_t>(stream)));
 }
 
 int unirec_inv_l2_norm(const void* x, int x_fp32, int64_t ldx, float* inv, int64_t rows, int64_t D, float eps,

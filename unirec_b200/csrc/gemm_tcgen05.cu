@@ -211,6 +211,31 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long l
     return UNIREC_OK;
 }
 
+// 3-D bf16 [batch, rows, cols]: element (b, r, c) at base + (b * batch_stride + r * ld + c); box = [1, box_rows, 64 cols],
+// 128B swizzle.  Rows >= `rows` of a batch element are out of bounds: zero-filled on load, clipped on store.
+int make_tmap_bf16_3d(CUtensorMap* map, const void* base, long long batch, long long rows, long long cols, long long ld,
+                      long long batch_stride, int box_rows) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (fn == nullptr) {
+        set_last_error("cuTensorMapEncodeTiled driver entry point not available");
+        return UNIREC_ERR_TENSORMAP;
+    }
+    if (batch <= 1) { batch = 1; batch_stride = rows * ld; }
+    cuuint64_t gdim[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batch)};
+    cuuint64_t gstride[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(batch_stride) * 2};
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(BLOCK_K), static_cast<cuuint32_t>(box_rows), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled(3d) failed: CUresult %d (batch=%lld rows=%lld cols=%lld ld=%lld stride=%lld "
+                       "box_rows=%d base=%p)", static_cast<int>(r), batch, rows, cols, ld, batch_stride, box_rows, base);
+        return UNIREC_ERR_TENSORMAP;
+    }
+    return UNIREC_OK;
+}
+
 int num_sms() {
     static int n = 0;
     if (n == 0) {

@@ -411,13 +411,39 @@ int field_projection(const void* rec, const float* Wp, const float* bp, void* ou
 // the right-padding of training/user_qformer_training.py:153-161.  PE is computed in-kernel from
 // the closed form (user_sequence_encoder.py:20-24): pe[p, 2i] = sin(p * w_i), pe[p, 2i+1] = cos(p * w_i),
 // w_i = exp(-(2i) ln(10000) / D).
-// One warp per output row; 16-byte gathers from the item-token table.
+// One warp per output row; 16-byte gathers from the item-token table.  With a precomputed table `pe` ([S, D] fp32,
+// positional_encoding_kernel below - the same closed form evaluated once; 6.5 MB at S = 1600, L2 resident) the kernel
+// is a pure HBM stream; without it the transcendental evaluation makes it issue-bound (ncu: 90 % issue slots).
 // ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+positional_encoding_kernel(float* __restrict__ pe, int S, int D) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // one (position, pair) per thread
+    const int pairs = D / 2;
+    if (i >= static_cast<long long>(S) * pairs) return;
+    const int s = static_cast<int>(i / pairs), j = static_cast<int>(i % pairs);
+    const float w = expf(static_cast<float>(2 * j) * (-9.210340371976184f / static_cast<float>(D)));
+    float sn, cs;
+    sincosf(static_cast<float>(s) * w, &sn, &cs);
+    reinterpret_cast<float2*>(pe)[i] = make_float2(sn, cs);
+}
+
+int positional_encoding(float* pe, long long S, long long D, cudaStream_t stream) {
+    if (pe == nullptr || S <= 0 || D <= 0 || D % 2 != 0) {
+        set_last_error("positional_encoding: bad arguments (S=%lld D=%lld)", S, D);
+        return UNIREC_ERR_BAD_ARG;
+    }
+    const long long n = S * (D / 2);
+    positional_encoding_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(pe, (int)S, (int)D);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_last_error("positional_encoding launch: %s", cudaGetErrorString(e)); return UNIREC_ERR_CUDA; }
+    return UNIREC_OK;
+}
+
 __global__ void __launch_bounds__(256)
 build_user_sequence_kernel(const __nv_bfloat16* __restrict__ table, const long long* __restrict__ history,
                            const int* __restrict__ lengths, const __nv_bfloat16* __restrict__ ctx,
-                           __nv_bfloat16* __restrict__ seq, float* __restrict__ mask, int Hmax, int Q, int D,
-                           long long rows_total) {
+                           const float* __restrict__ pe, __nv_bfloat16* __restrict__ seq, float* __restrict__ mask,
+                           int Hmax, int Q, int D, long long rows_total) {
     const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= rows_total) return;
@@ -445,13 +471,20 @@ build_user_sequence_kernel(const __nv_bfloat16* __restrict__ table, const long l
             x[0] += bf16_lo(c.x); x[1] += bf16_hi(c.x); x[2] += bf16_lo(c.y); x[3] += bf16_hi(c.y);
             x[4] += bf16_lo(c.z); x[5] += bf16_hi(c.z); x[6] += bf16_lo(c.w); x[7] += bf16_hi(c.w);
         }
+        if (pe != nullptr) {
+            const float4 p0 = __ldg(reinterpret_cast<const float4*>(pe + static_cast<long long>(s) * D) + 2 * vi);
+            const float4 p1 = __ldg(reinterpret_cast<const float4*>(pe + static_cast<long long>(s) * D) + 2 * vi + 1);
+            x[0] += p0.x; x[1] += p0.y; x[2] += p0.z; x[3] += p0.w;
+            x[4] += p1.x; x[5] += p1.y; x[6] += p1.z; x[7] += p1.w;
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float w = expf(static_cast<float>(vi * 8 + 2 * j) * neg_ln1e4_over_d);
-            float sn, cs;
-            sincosf(static_cast<float>(s) * w, &sn, &cs);
-            x[2 * j] += sn;
-            x[2 * j + 1] += cs;
+            for (int j = 0; j < 4; ++j) {
+                const float w = expf(static_cast<float>(vi * 8 + 2 * j) * neg_ln1e4_over_d);
+                float sn, cs;
+                sincosf(static_cast<float>(s) * w, &sn, &cs);
+                x[2 * j] += sn;
+                x[2 * j + 1] += cs;
+            }
         }
         reinterpret_cast<uint4*>(o)[vi] =
             make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
@@ -459,8 +492,8 @@ build_user_sequence_kernel(const __nv_bfloat16* __restrict__ table, const long l
 }
 
 int build_user_sequence(const void* table, long long num_items, const long long* history, const int* lengths,
-                        const void* ctx, void* seq, float* mask, long long B, long long Hmax, long long Q, long long D,
-                        cudaStream_t stream) {
+                        const void* ctx, const float* pe, void* seq, float* mask, long long B, long long Hmax, long long Q,
+                        long long D, cudaStream_t stream) {
     (void)num_items;
     if (table == nullptr || history == nullptr || lengths == nullptr || seq == nullptr || mask == nullptr || B <= 0 ||
         Hmax <= 0 || Q <= 0 || D % 8 != 0) {
@@ -470,7 +503,7 @@ int build_user_sequence(const void* table, long long num_items, const long long*
     const long long rows = B * Hmax * Q;
     const long long blocks = (rows * 32 + 255) / 256;
     build_user_sequence_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(table), history, lengths, reinterpret_cast<const __nv_bfloat16*>(ctx),
+        reinterpret_cast<const __nv_bfloat16*>(table), history, lengths, reinterpret_cast<const __nv_bfloat16*>(ctx), pe,
         reinterpret_cast<__nv_bfloat16*>(seq), mask, (int)Hmax, (int)Q, (int)D, rows);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

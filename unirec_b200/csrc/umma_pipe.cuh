@@ -152,6 +152,8 @@ UNIREC_DEVICE void pipe_epilogue_release(Pipe& pipe, uint32_t iter) {
 
 // Host: 2-D bf16 row-major tensor map, box [box_rows, 64 cols], 128-byte swizzle (gemm_tcgen05.cu).
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows);
+int make_tmap_bf16_3d(CUtensorMap* map, const void* base, long long batch, long long rows, long long cols, long long ld,
+                      long long batch_stride, int box_rows);
 int num_sms();
 
 }  // namespace unirec

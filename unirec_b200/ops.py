@@ -252,8 +252,25 @@ def field_projection(rec: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor
     return out
 
 
+_pe_tables = {}
+
+
+def positional_encoding_table(S: int, D: int, device) -> torch.Tensor:
+    """fp32 [S, D] sinusoidal table (models/user_sequence_encoder.py:20-24), built once per (S, D, device) by the
+    CUDA kernel and kept resident (6.5 MB at S = 1600, D = 1024)."""
+    key = (int(S), int(D), torch.device(device))
+    t = _pe_tables.get(key)
+    if t is None:
+        t = torch.empty(S, D, device=device, dtype=torch.float32)
+        rc = _lib.load().unirec_positional_encoding(t.data_ptr(), S, D, _stream())
+        _lib.check(rc, "unirec_positional_encoding")
+        _pe_tables[key] = t
+    return t
+
+
 def build_user_sequence(table: torch.Tensor, history: torch.Tensor, lengths: torch.Tensor,
-                        context: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                        context: Optional[torch.Tensor] = None, use_pe_table: bool = True
+                        ) -> Tuple[torch.Tensor, torch.Tensor]:
     """table bf16 [N, Q, D]; history int64 [B, Hmax]; lengths int32 [B]; context bf16 [B, Hmax, D] or None.
     Returns (seq bf16 [B, Hmax*Q, D], mask fp32 [B, Hmax*Q])."""
     _req(table, torch.bfloat16, "build_user_sequence.table")
@@ -268,8 +285,9 @@ def build_user_sequence(table: torch.Tensor, history: torch.Tensor, lengths: tor
         context = context.contiguous()
     seq = torch.empty(B, Hmax * Q, D, device=table.device, dtype=torch.bfloat16)
     mask = torch.empty(B, Hmax * Q, device=table.device, dtype=torch.float32)
+    pe = positional_encoding_table(Hmax * Q, D, table.device) if use_pe_table else None
     rc = _lib.load().unirec_build_user_sequence(table.data_ptr(), N, history.data_ptr(), lengths.data_ptr(),
-                                                _ptr(context), seq.data_ptr(), mask.data_ptr(), B, Hmax, Q, D,
+                                                _ptr(context), _ptr(pe), seq.data_ptr(), mask.data_ptr(), B, Hmax, Q, D,
                                                 _stream())
     _lib.check(rc, "unirec_build_user_sequence")
     return seq, mask
