@@ -162,10 +162,21 @@ def test_full_size_models_at_bench_settings_against_oracle():
     _check("user[full,B=6,S=1600,bench settings]", out, refu, max_tol=0.1, mean_tol=0.015, cos_tol=0.9995)
 
 
-def test_train_mode_with_dropout_is_refused():
-    from unirec_b200.modules import QFormerForItemRepresentation
+def test_train_mode_dropout_entry_points():
+    """train() with dropout > 0: the item module's forward applies the reference's dropout sites (tests/test_train_gpu.py
+    checks the values); entry points that only implement dropout = identity refuse instead of silently skipping it."""
+    from unirec_b200.modules import QFormerForItemRepresentation, UserQFormer
     m = QFormerForItemRepresentation(hidden_size=256, num_hidden_layers=2, num_attention_heads=4,
                                      intermediate_size=512, field_embedding_dim=256, num_fields=6).to(DEV)
     m.train()
+    x = torch.randn(2, 6, 256, device=DEV)
+    out = m(x)
+    assert out["query_outputs"].shape == (2, 32, 256) and out["query_outputs"].requires_grad
+    assert m.last_dropout is not None and m.last_dropout[0] == 13107
     with pytest.raises(NotImplementedError):
-        m(torch.randn(2, 6, 256, device=DEV))
+        m.encode_query_tokens(x)
+    u = UserQFormer(hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=512,
+                    input_embedding_dim=256, num_item_tokens_to_predict=8).to(DEV)
+    u.train()
+    with pytest.raises(NotImplementedError):
+        u(torch.randn(2, 64, 256, device=DEV), torch.ones(2, 64, device=DEV))

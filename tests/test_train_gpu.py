@@ -251,7 +251,10 @@ def test_item_training_step_gradients_match_oracle_autograd(dropout):
     loss.backward()
     assert (model.last_dropout is None) == (dropout == 0.0)
     ref_loss, ref = _oracle_loss_and_grads(sd, x, mask, c["heads"], weights, drop=model.last_dropout)
-    assert abs(float(loss) - ref_loss) <= 0.02 * abs(ref_loss) + 0.05
+    # the loss is a signed random-weighted sum of ~0.6 M outputs: compare against the scale of its terms
+    term_scale = float(sum((out[k].float().abs() * weights[k].to(DEV).abs()).sum() for k in weights))
+    loss_err = abs(float(loss) - ref_loss)
+    print(f"loss {float(loss):.4f} vs oracle {ref_loss:.4f} (sum |terms| = {term_scale:.1f})")
     checked, bad = 0, []
     for name, prm in model.named_parameters():
         if name not in ref:
@@ -274,6 +277,7 @@ def test_item_training_step_gradients_match_oracle_autograd(dropout):
         checked += 1
     assert not bad, bad
     assert checked > 60
+    assert loss_err <= 2e-4 * term_scale + 0.02 * abs(ref_loss), (float(loss), ref_loss, term_scale)
 
 
 def test_train_mode_no_grad_forward_uses_dropout_and_eval_does_not():

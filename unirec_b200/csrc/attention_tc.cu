@@ -246,10 +246,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
             store_q(0, qv);
         }
         float m_used = -INFINITY, l_run = 0.f;
-        for (int g = 0; g < G; ++g) {
-            const int it = g / T, t = g - it * T;
-            const int w = blockIdx.x + it * gridDim.x;
-            const int b = w / pairs, hp = w - b * pairs;
+        // key_mask value of this thread's key in tile (item it_, tile t_), fetched one tile AHEAD: ncu showed the
+        // load's latency (long scoreboard) on the critical path of every tile when it was issued at the tile's start
+        auto mask_fetch = [&](int it_, int t_) -> float {
+            const int key = t_ * AT_KT + r;
+            if (p.key_mask == nullptr || key >= p.nk) return 1.0f;
+            const int b_ = (blockIdx.x + it_ * gridDim.x) / pairs;
+            return __ldg(p.key_mask + static_cast<long long>(b_) * p.nk + key);
+        };
+        float mraw_next = (G > 0) ? mask_fetch(0, 0) : 1.0f;
+        int it = 0, t = 0, b = 0, hp = 0;
+        for (int g = 0; g < G; ++g, ++t) {
+            if (t == T) { t = 0; ++it; }
+            if (t == 0) {
+                const int w = blockIdx.x + it * gridDim.x;
+                b = w / pairs;
+                hp = w - b * pairs;
+            }
             const int slot = g & 1;
             const uint32_t ph = (g >> 1) & 1;
             if (t == 0) {
@@ -262,9 +275,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
             {
                 const int key = t * AT_KT + r;
                 float mv = -INFINITY;
-                if (key < p.nk)
-                    mv = (p.key_mask != nullptr && __ldg(p.key_mask + static_cast<long long>(b) * p.nk + key) == 0.f)
-                             ? AT_MASKED : 0.f;
+                if (key < p.nk) mv = (mraw_next == 0.f) ? AT_MASKED : 0.f;
+                if (g + 1 < G) mraw_next = (t + 1 == T) ? mask_fetch(it + 1, 0) : mask_fetch(it, t + 1);
                 sMask[slot * AT_KT + r] = mv;
                 const bool warp_plain = __all_sync(0xffffffffu, mv == 0.f);
                 if (lane == 0) sPlain[slot * 4 + warp_idx] = warp_plain ? 1 : 0;
