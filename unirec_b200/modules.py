@@ -384,7 +384,7 @@ class UserQFormer(nn.Module):
         self.prelayernorm_dtype = torch.float32
         # cross-attention K/V for all layers are materialised per chunk of users:
         # chunk * S * layers * 2 * H * 2 bytes (6.7 GB for 256 users x 1600 keys x 4 layers)
-        self.max_kv_bytes = 8 << 30
+        self.max_kv_bytes = 14 << 30               # K/V of all layers for one chunk of users (512 users at S = 1600)
         self._head_pack = None
         self._head_key = None
 
@@ -404,7 +404,10 @@ class UserQFormer(nn.Module):
     def _chunk_users(self, S: int) -> int:
         cfg = self.config
         per_user = S * cfg.num_hidden_layers * 2 * cfg.hidden_size * 2
-        return max(1, int(self.max_kv_bytes // max(per_user, 1)))
+        n = max(1, int(self.max_kv_bytes // max(per_user, 1)))
+        # multiples of 128 users keep every GEMM's row count a multiple of the 256-row CTA-pair tile and the tile
+        # counts of the small per-chunk GEMMs close to whole waves of 74 clusters
+        return (n // 128) * 128 if n >= 128 else n
 
     @torch.no_grad()
     def encode_queries(self, user_sequence_tokens: torch.Tensor, attention_mask: Optional[torch.Tensor],
