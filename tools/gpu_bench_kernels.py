@@ -100,6 +100,61 @@ def scoring_cases():
               f"table stream {c.numel() * 2 / ms / 1e6:8.1f} GB/s ({100 * c.numel() * 2 / ms / 1e6 / HBM:5.1f}% HBM)", flush=True)
 
 
+def train_cases():
+    """Kernels of the cfg-2 training step at its shapes (1024 items x 32 queries, hidden 1024, 16 heads)."""
+    H, heads, B, Q, F = 1024, 16, 1024, 32, 14
+    M = B * Q
+    drop = (ops.dropout_threshold(0.2), 12345, 7)
+    x = torch.randn(M, H, device=dev).to(bf)
+    res = torch.randn(M, H, device=dev).to(bf)
+    ms = timeit(lambda: ops.dropout_add(x, res, drop))
+    report("dropout_add (32768 x 1024)", ms, 3 * M * H * 2)
+    ms = timeit(lambda: ops.dropout_backward(x, drop))
+    report("dropout_backward (32768 x 1024)", ms, 2 * M * H * 2)
+    qkv = torch.randn(M, 3 * H, device=dev).to(bf)
+    do = torch.randn(M, H, device=dev).to(bf)
+    dqkv = torch.empty_like(qkv)
+    for name, d in (("", None), (" +dropout", drop)):
+        ms = timeit(lambda: ops.attention(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], batch=B, num_heads=heads, nq=Q, nk=Q,
+                                          dropout=d))
+        report(f"attention fwd self 32x32{name} (B=1024)", ms, 4 * M * H * 2)
+        ms = timeit(lambda: ops.attention_backward(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], do, dqkv[:, :H],
+                                                   dqkv[:, H:2 * H], dqkv[:, 2 * H:], batch=B, num_heads=heads, nq=Q, nk=Q,
+                                                   dropout=d))
+        report(f"attention bwd self 32x32{name} (B=1024)", ms, 8 * M * H * 2)
+    kv = torch.randn(B * F, 12 * H, device=dev).to(bf)
+    dkv = torch.zeros_like(kv)
+    qc = torch.randn(M, H, device=dev).to(bf)
+    dqc = torch.empty_like(qc)
+    mask = torch.ones(B, F, device=dev)
+    for name, d in (("", None), (" +dropout", drop)):
+        ms = timeit(lambda: ops.attention(qc, kv[:, :H], kv[:, H:2 * H], batch=B, num_heads=heads, nq=Q, nk=F, key_mask=mask,
+                                          dropout=d))
+        report(f"attention fwd cross 32x14{name} (B=1024)", ms, (2 * Q + 2 * F) * B * H * 2)
+        ms = timeit(lambda: ops.attention_backward(qc, kv[:, :H], kv[:, H:2 * H], do, dqc, dkv[:, :H], dkv[:, H:2 * H],
+                                                   batch=B, num_heads=heads, nq=Q, nk=F, key_mask=mask, dropout=d))
+        report(f"attention bwd cross 32x14{name} (B=1024)", ms, (4 * Q + 4 * F) * B * H * 2)
+    g = torch.ones(H, device=dev)
+    dg, db = torch.zeros(H, device=dev), torch.zeros(H, device=dev)
+    ms = timeit(lambda: ops.layernorm_backward(x, do, g, 1e-12, dg, db, dy2=res))
+    report("layernorm_backward (32768 x 1024, dy + dy2)", ms, 4 * M * H * 2)
+    z = torch.randn(M, 4 * H, device=dev).to(bf)
+    ms = timeit(lambda: ops.gelu(z))
+    report("gelu fwd (32768 x 4096)", ms, 2 * M * 4 * H * 2)
+    ms = timeit(lambda: ops.gelu_backward(z, z))
+    report("gelu bwd (32768 x 4096)", ms, 3 * M * 4 * H * 2)
+    bsum = torch.zeros(4 * H, device=dev)
+    ms = timeit(lambda: ops.colsum(z, bsum))
+    report("colsum (32768 x 4096)", ms, M * 4 * H * 2)
+    w = torch.randn(4 * H, H, device=dev).to(bf)
+    dw = torch.zeros(4 * H, H, device=dev)
+    for name, fn, fl in (("dgrad 32768x1024x4096", lambda: ops.linear_dgrad(z, w), 2.0 * M * H * 4 * H),
+                         ("wgrad 4096x1024x32768", lambda: ops.linear_wgrad(z, x, dw), 2.0 * M * H * 4 * H),
+                         ("fwd   32768x4096x1024", lambda: ops.linear(x, w), 2.0 * M * H * 4 * H)):
+        ms = timeit(fn)
+        print(f"gemm {name:44s} {ms:8.3f} ms  {fl / ms / 1e9:8.1f} TFLOP/s", flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["attention", "rowwise", "scoring"]
     print(torch.cuda.get_device_name(0), "HBM peak", HBM, "GB/s")
@@ -109,3 +164,5 @@ if __name__ == "__main__":
         rowwise_cases()
     if "scoring" in what:
         scoring_cases()
+    if "train" in what:
+        train_cases()

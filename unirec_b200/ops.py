@@ -44,18 +44,22 @@ class _Timed:
         if _timing is not None:
             self.e0 = torch.cuda.Event(enable_timing=True)
             self.e1 = torch.cuda.Event(enable_timing=True)
-            self.e0.record()
+            self.stream = torch.cuda.current_stream(torch._C._cuda_getDevice())
+            self.e0.record(self.stream)
         return self
 
     def __exit__(self, *exc):
         if _timing is not None:
-            self.e1.record()
+            self.e1.record(self.stream)
             _timing.append((self.kind, float(self.work), self.e0, self.e1))
         return False
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    # raw cudaStream_t of torch's current stream.  torch.cuda.current_stream() with no device argument goes through
+    # torch.cuda.is_available() -> cudaGetDeviceCount on every call (cProfile: the largest host cost of a training
+    # step); the two C calls below do not.
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def _req(t: torch.Tensor, dtype, name: str):
