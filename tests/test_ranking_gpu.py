@@ -103,6 +103,49 @@ def test_score_topk_adversarial_sample():
     _assert_topk_matches(s, i, u, C, k)
 
 
+def test_score_topk_full_size_properties():
+    """BASELINE size (1 M candidates x 1024, top-100): properties that do not need the CPU oracle's full [B, N]
+    matrix.  (1) lists are descending with unique in-range indices; (2) every returned score is the exact cosine of its
+    (user, candidate) pair; (3) completeness - no candidate outside a list beats the list's k-th score by more than
+    the tolerance (checked by a chunked fp32 torch.matmul sweep, used as a checker only); (4) scoring the pool as 8 row
+    shards + unirec_topk_merge (the multi-GPU path, config 5) gives the same lists; (5) the same call twice is
+    bit-identical."""
+    from unirec_b200 import ops
+    N, D, B, k, G = 1_000_000, 1024, 192, 100, 8
+    gen = torch.Generator(device=DEV).manual_seed(77)
+    C = torch.randn(N, D, device=DEV, generator=gen).to(torch.bfloat16)
+    u = torch.randn(B, D, device=DEV, generator=gen).to(torch.bfloat16)
+    s, i = ops.score_topk(u, C, k)
+    s2, i2 = ops.score_topk(u, C, k)
+    assert torch.equal(s, s2) and torch.equal(i, i2)                                      # (5)
+    assert bool((s[:, :-1] >= s[:, 1:]).all()) and int(i.min()) >= 0 and int(i.max()) < N   # (1)
+    assert all(len(set(r.tolist())) == k for r in i.cpu())
+    un = torch.nn.functional.normalize(u.float(), dim=-1)
+    picked = torch.nn.functional.normalize(C[i.reshape(-1)].float(), dim=-1).view(B, k, D)
+    exact = torch.einsum("bd,bkd->bk", un, picked)
+    assert torch.allclose(exact, s, atol=TOL, rtol=0), float((exact - s).abs().max())      # (2)
+    kth = s[:, -1:]
+    beating = torch.zeros(B, device=DEV, dtype=torch.long)
+    for c0 in range(0, N, 65536):                                                           # (3)
+        cn = torch.nn.functional.normalize(C[c0:c0 + 65536].float(), dim=-1)
+        beating += ((un @ cn.t()) > kth + 4 * TOL).sum(dim=1)
+    assert int(beating.max()) <= k - 1, int(beating.max())
+    parts_s, parts_i = [], []
+    for r in range(G):                                                                      # (4)
+        lo, hi = r * N // G, (r + 1) * N // G
+        ps, pi = ops.score_topk(u, C[lo:hi], k, index_base=lo)
+        parts_s.append(ps)
+        parts_i.append(pi)
+    ms, mi = ops.topk_merge(torch.stack(parts_s), torch.stack(parts_i))
+    assert torch.allclose(ms, s, atol=TOL, rtol=0)
+    same = (mi == i)
+    gap = torch.ones_like(same)
+    d = (s[:, :-1] - s[:, 1:]) > 4 * TOL
+    gap[:, 1:] &= d
+    gap[:, :-1] &= d
+    assert bool(same[gap].all())
+
+
 def test_topk_merge_matches_global_topk():
     from unirec_b200 import ops
     g = torch.Generator().manual_seed(11)

@@ -30,7 +30,7 @@ ncu)
   # step) and of one item batch; the .ncu-rep stays on the box (too large), raw-page CSVs come back
   timeout 1500 ncu --set full --clock-control none --import-source on --profile-from-start off \
       -f -o /tmp/prof_users \
-      python bench.py --steps 1 --warmup 1 --pool-items 131072 --users-per-gpu 256 --no-cpu-baseline --train-batch 0 --profile-range users \
+      python bench.py --steps 1 --warmup 1 --pool-items 131072 --users-per-gpu 512 --no-cpu-baseline --train-batch 0 --profile-range users \
       > gpurun_out/prof_users.out 2>&1
   ncu -i /tmp/prof_users.ncu-rep --page raw --csv > gpurun_out/prof_users_raw.csv 2> gpurun_out/prof_users_raw.err
   timeout 1500 ncu --set full --clock-control none --import-source on --profile-from-start off \

@@ -26,19 +26,22 @@ def start_timing():
 
 
 def stop_timing():
-    """Returns {kind: (launches, total_work, total_ms)}; call after torch.cuda.synchronize()."""
+    """Returns {kind: (launches, total_work, total_ms)} plus, per tagged launch shape, {"kind:tag": (...)}; call after
+    torch.cuda.synchronize()."""
     global _timing
     rec, _timing = _timing or [], None
     out = {}
-    for kind, work, e0, e1 in rec:
-        n, w, ms = out.get(kind, (0, 0.0, 0.0))
-        out[kind] = (n + 1, w + work, ms + e0.elapsed_time(e1))
+    for kind, tag, work, e0, e1 in rec:
+        dt = e0.elapsed_time(e1)
+        for key in ((kind,) if tag is None else (kind, f"{kind}:{tag}")):
+            n, w, ms = out.get(key, (0, 0.0, 0.0))
+            out[key] = (n + 1, w + work, ms + dt)
     return out
 
 
 class _Timed:
-    def __init__(self, kind, work):
-        self.kind, self.work = kind, work
+    def __init__(self, kind, work, tag=None):
+        self.kind, self.work, self.tag = kind, work, tag
 
     def __enter__(self):
         if _timing is not None:
@@ -51,7 +54,7 @@ class _Timed:
     def __exit__(self, *exc):
         if _timing is not None:
             self.e1.record(self.stream)
-            _timing.append((self.kind, float(self.work), self.e0, self.e1))
+            _timing.append((self.kind, self.tag, float(self.work), self.e0, self.e1))
         return False
 
 
@@ -110,7 +113,7 @@ def linear(a: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         _, _, ldr = _rows2d(residual, "linear.residual")
     if out.dtype not in (torch.bfloat16, torch.float32):
         raise RuntimeError("linear: out must be bf16 or fp32")
-    with _Timed("gemm", 2.0 * M * N * K):
+    with _Timed("gemm", 2.0 * M * N * K, f"{M}x{N}x{K}"):
         rc = _lib.load().unirec_linear_bf16(a.data_ptr(), lda, weight.data_ptr(), weight.stride(0), _ptr(bias),
                                             _ptr(residual), ldr, res_row_mod, out.data_ptr(), ldo,
                                             1 if out.dtype == torch.float32 else 0, M, N, K, epilogue, block_n,
@@ -167,7 +170,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, batch: int, 
         if tuple(key_mask.shape) != (batch, nk) or not key_mask.is_contiguous():
             raise RuntimeError("attention: key_mask must be contiguous [batch, nk]")
     # algorithmic bytes: Q, K, V read once + context written once (bf16)
-    with _Timed("attention", 2.0 * hd * batch * ((1 if q_broadcast else 1) * nq + 2 * nk + nq)):
+    with _Timed("attention", 2.0 * hd * batch * ((1 if q_broadcast else 1) * nq + 2 * nk + nq), f"{batch}x{nq}x{nk}"):
         if dropout is not None and dropout[0] > 0:
             rc = _lib.load().unirec_attention_dropout(q.data_ptr(), q.stride(0), 0 if q_broadcast else nq, k.data_ptr(),
                                                       k.stride(0), v.data_ptr(), v.stride(0), nk, _ptr(key_mask),
