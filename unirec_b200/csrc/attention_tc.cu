@@ -16,17 +16,17 @@
 // key and matrix, fetched by TMA as two 64-column slabs, 128-byte swizzle).  Kt is the K-major B operand of the
 // first MMA; Vt is used in place as the MN-major B operand of the second (no transpose anywhere).
 //
-// Warp roles (576 threads, one persistent CTA per SM):
-//     warps 0-15 softmax: four warps per TMEM lane quadrant, each thread owns one row x a quarter of the tile's keys
-//                (row maxima / sums exchanged through shared memory between the four).
+// Warp roles (320 threads, one persistent CTA per SM):
+//     warps 0-7  softmax: two warps per TMEM lane quadrant, each thread owns one row x half of the tile's keys
+//                (row maxima / sums exchanged through shared memory between the two).
 //                tcgen05.ld S -> scale + additive mask -> row max -> ex2 -> row sum,
 //                P (bf16) -> shared memory (K-major, swizzled) for the second MMA.  The running max is only
 //                raised when a tile exceeds it by more than 2^8 (exact: O and the row sum are accumulated against the
 //                same reference value), so O in TMEM is almost never rescaled.  Also builds Q2 for the NEXT item.
-//     warp 16    TMA producer: K tiles through a 3-stage ring, V tiles through a 2-stage ring.  P(g) is written IN PLACE
+//     warp 8     TMA producer: K tiles through a 3-stage ring, V tiles through a 2-stage ring.  P(g) is written IN PLACE
 //                over K(g) (same 32 KB footprint; K(g) is dead once S(g) has been accumulated), so the K slot is only
 //                released by PV(g) - P is effectively triple-buffered and the softmax of tile g+1 never waits for PV(g)
-//     warp 17    TMEM allocator + UMMA issuer; issue order S(g+1), PV(g) so that the softmax of tile g overlaps
+//     warp 9     TMEM allocator + UMMA issuer; issue order S(g+1), PV(g) so that the softmax of tile g overlaps
 //                the first MMA of tile g+1 (two S accumulators in TMEM) - across work items too
 // Mask semantics are those of attention.cu: key_mask == 0 adds -1e30 (log2 domain), keys beyond nk are excluded
 // (-inf), a row whose keys are all masked comes out uniform over the nk keys.
@@ -38,11 +38,10 @@ namespace unirec {
 constexpr int AT_KT = 128;                       // keys per tile
 constexpr int AT_SLAB = 128 * 64 * 2;            // [128 rows][64 bf16] = 16 KB
 constexpr int AT_TILE = 2 * AT_SLAB;             // 32 KB: Q2, a K tile, a V tile, P
-constexpr int AT_THREADS = 576;                  // 16 softmax warps + TMA producer + UMMA issuer
-constexpr int AT_ALIGN_SLACK = 768;              // dynamic smem base must be 256-byte aligned (checked in the kernel)
+constexpr int AT_THREADS = 320;                  // 8 softmax warps + TMA producer + UMMA issuer
 constexpr int AT_KSTAGES = 3;                    // K ring depth (a K slot is reused as that tile's P)
 constexpr int AT_SMEM_BYTES = 2 * AT_TILE /*Q2 x2*/ + AT_KSTAGES * AT_TILE /*K|P x3*/ + 2 * AT_TILE /*V x2*/ +
-                              4 * 512 /*row max / sum exchange*/ + 192 /*barriers*/ + AT_ALIGN_SLACK;
+                              2 * 2 * AT_KT * 2 /*row-max exchange*/ + 1024 /*align*/ + 256 /*barriers*/;
 static_assert(AT_SMEM_BYTES <= 232448, "shared memory budget exceeded");
 constexpr float AT_MASKED = -1.2676506002282294e30f;   // -2^100: stands in for finfo.min, exact in bf16 (row-max exchange)
 constexpr float AT_LAZY = 8.0f;                  // raise the running max only when exceeded by 2^8
@@ -82,12 +81,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    if (static_cast<int>(smem - smem_raw) > AT_ALIGN_SLACK) __trap();   // the 7 tiles leave 768 B of alignment slack
     uint8_t* sQ2 = smem;                          // [2][2 slabs]
     uint8_t* sK = smem + 2 * AT_TILE;             // [3][2 slabs]  K(g), later P(g)
     uint8_t* sV = smem + 5 * AT_TILE;             // [2][2 slabs]
-    // smem + 7 tiles: 4 x 512 B row max / sum exchange areas (one per TMEM lane quadrant)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * AT_TILE + 4 * 512);
+    // smem + 7 tiles: [2][2][128] bf16 row-max exchange between the two softmax warps of a row quadrant (1 KB)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * AT_TILE + 2 * 2 * AT_KT * 2);
     uint64_t* k_full = bars;            // [3]
     uint64_t* k_empty = bars + 3;       // [3]  issuer (commit after PV: the slot held K, then P)
     uint64_t* v_full = bars + 6;        // [2]
@@ -107,21 +105,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
     const int G = my_items * T;
     const int pairs = p.num_heads >> 1;
 
-    if (warp_idx == 16 && lane == 0) {
+    if (warp_idx == 8 && lane == 0) {
         tma_prefetch_desc(&tmap_k);
         tma_prefetch_desc(&tmap_v);
         for (int i = 0; i < AT_KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
-            mbar_init(&q_ready[i], 16); mbar_init(&q_free[i], 1);
-            mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 16);
+            mbar_init(&q_ready[i], 8); mbar_init(&q_free[i], 1);
+            mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 8);
         }
-        mbar_init(p_ready, 16);
+        mbar_init(p_ready, 8);
         mbar_init(pv_done, 1);
-        mbar_init(o_free, 16);
+        mbar_init(o_free, 8);
         fence_mbar_init();
     }
-    if (warp_idx == 17) {
+    if (warp_idx == 9) {
         tmem_alloc(tmem_ptr_smem, 512);
         tmem_relinquish();
     }
@@ -131,7 +129,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
     const uint32_t tmem_base = *tmem_ptr_smem;
     const uint32_t tmem_o = tmem_base + 256;
 
-    if (warp_idx == 16) {
+    if (warp_idx == 8) {
         // ===================== TMA producer =====================
         for (int g = 0; g < G; ++g) {
             const int it = g / T, t = g - it * T;
@@ -158,7 +156,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
             }
             __syncwarp();
         }
-    } else if (warp_idx == 17) {
+    } else if (warp_idx == 9) {
         // ===================== UMMA issuer =====================
         constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
         constexpr uint32_t idesc_pv = umma_idesc_bf16_bmn(128, 128);
@@ -215,56 +213,60 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
             issue_pv(g);
         }
     } else {
-        // ===================== softmax warps 0-15: thread = (accumulator row r, key quarter kq) =====================
-        // Four warps share each TMEM lane quadrant (a warp may only touch lanes 32*(warp%4)..+31): warps q, q+4, q+8, q+12
-        // own the same 32 rows and split the tile's 128 keys in quarters.  ncu on the 4- and 8-warp versions showed the
-        // softmax chain issue-latency bound (IPC 0.4 with two warps per scheduler, MUFU and HBM both idle half the time);
-        // four warps per scheduler hide the ALU / MUFU latencies and the tile period drops below the HBM time of a tile.
-        const int quad = warp_idx & 3, kq = warp_idx >> 2;
+        // ===================== softmax warps 0-7: thread = (accumulator row r, column half hf) =====================
+        // Two warps share each TMEM lane quadrant (a warp may only touch lanes 32*(warp%4)..+31): warp w and w+4 own
+        // the same 32 rows and split the tile's 128 keys in halves, so a tile's 16384 exponentials are spread over
+        // eight warps (two per scheduler) instead of four - the softmax, not HBM, was the tile period before.
+        const int quad = warp_idx & 3, hf = warp_idx >> 2;
         const int r = quad * 32 + lane;            // 0..127
         const int hsel = r >> 6;                   // 0: head 2*hp, 1: head 2*hp + 1
         const int qrow = r & 63;
         const uint32_t lane_field = static_cast<uint32_t>(quad * 32) << 16;
-        const int quad_bar = 1 + quad;             // named barrier of the four warps that share these rows (128 threads)
-        // exchange area of this row quadrant (512 B, touched by its four warps only): row maxima [2 slots][4 quarters][32]
-        // bf16 during the tiles, row sums [4 quarters][32] fp32 at the end of a work item
-        const uint32_t sx_addr = smem_u32(smem + 7 * AT_TILE + quad * 512);
+        const int pair_bar = 1 + quad;             // named barrier of the two warps that share these rows (64 threads)
+        // exchange area of this row quadrant (256 B, touched by its two warps only): row maxima [2 slots][2 halves][32]
+        // bf16 during the tiles, row sums [2 halves][32] fp32 at the end of a work item
+        __nv_bfloat16* sX = reinterpret_cast<__nv_bfloat16*>(smem + 7 * AT_TILE + quad * 256);
+        float* sSum = reinterpret_cast<float*>(smem + 7 * AT_TILE + quad * 256);
 
-        // Q2 rows: slab `hsel` holds this row's 64 query values (chunks 0-3 from the kq = 0 thread, 4-7 from kq = 1), the
-        // other slab is zero (kq = 2, 3)
-        auto load_q = [&](int it_, uint4 (&qv)[4]) {
+        // Q2 rows: slab `hsel` holds this row's 64 query values (written by the hf = 0 thread of the row), the other
+        // slab is zero (written by the hf = 1 thread)
+        auto load_q = [&](int it_, uint4 (&qv)[8]) {
             const int w = blockIdx.x + it_ * gridDim.x;
             const int b_ = w / pairs, hp_ = w - b_ * pairs;
             const __nv_bfloat16* src = p.q + (static_cast<long long>(b_) * p.q_batch_rows + qrow) * p.ldq +
-                                       (2 * hp_ + hsel) * 64 + (kq & 1) * 32;
+                                       (2 * hp_ + hsel) * 64;
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-                qv[c] = (kq < 2 && qrow < p.nq) ? __ldg(reinterpret_cast<const uint4*>(src) + c) : make_uint4(0, 0, 0, 0);
+            for (int c = 0; c < 8; ++c)
+                qv[c] = (hf == 0 && qrow < p.nq) ? __ldg(reinterpret_cast<const uint4*>(src) + c) : make_uint4(0, 0, 0, 0);
         };
-        auto store_q = [&](int it_, const uint4 (&qv)[4]) {
-            const uint32_t base = smem_u32(sQ2 + (it_ & 1) * AT_TILE + (kq < 2 ? hsel : (hsel ^ 1)) * AT_SLAB);
+        auto store_q = [&](int it_, const uint4 (&qv)[8]) {
+            uint8_t* base = sQ2 + (it_ & 1) * AT_TILE + (hf == 0 ? hsel : (hsel ^ 1)) * AT_SLAB;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) st_shared_v4(base + swz128(r, (kq & 1) * 4 + c), qv[c]);
+            for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(base + swz128(r, c)) = qv[c];
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&q_ready[it_ & 1]);
         };
 
-        uint4 qv[4];
+        uint4 qv[8];
         if (my_items > 0) {
             load_q(0, qv);
             store_q(0, qv);
         }
         float m_used = -INFINITY, l_part = 0.f;
-        // key_mask value of key (32*kq + lane) of tile (it_, t_), fetched one tile AHEAD (ncu: issued at the tile's start,
-        // the load's latency sat on the critical path of every tile); 1.0 = attend
-        auto mask_fetch = [&](int it_, int t_) -> float {
-            if (p.key_mask == nullptr) return 1.0f;
+        // key_mask values of keys (64*hf + lane) and (+32) of tile (it_, t_), fetched one tile AHEAD (ncu: issued at the
+        // tile's start, the load's latency sat on the critical path of every tile); 1.0 = attend
+        auto mask_fetch = [&](int it_, int t_, float& a, float& bq) {
+            a = 1.0f; bq = 1.0f;
+            if (p.key_mask == nullptr) return;
             const int b_ = (blockIdx.x + it_ * gridDim.x) / pairs;
-            const int key = t_ * AT_KT + 32 * kq + lane;
-            return key < p.nk ? __ldg(p.key_mask + static_cast<long long>(b_) * p.nk + key) : 1.0f;
+            const int key = t_ * AT_KT + 64 * hf + lane;
+            const float* mrow = p.key_mask + static_cast<long long>(b_) * p.nk;
+            if (key < p.nk) a = __ldg(mrow + key);
+            if (key + 32 < p.nk) bq = __ldg(mrow + key + 32);
         };
-        float mraw = (G > 0) ? mask_fetch(0, 0) : 1.0f;
+        float mrawA = 1.0f, mrawB = 1.0f;
+        if (G > 0) mask_fetch(0, 0, mrawA, mrawB);
         int it = 0, t = 0, b = 0, hp = 0;
         for (int g = 0; g < G; ++g, ++t) {
             if (t == T) { t = 0; ++it; }
@@ -278,54 +280,59 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
             }
             const int slot = g & 1;
             const uint32_t ph = (g >> 1) & 1;
-            // ---- this quarter-tile's key mask as one 32-bit word (bit j = key 32*kq + j attends); no shared memory
-            const int n_exist = min(max(p.nk - t * AT_KT - 32 * kq, 0), 32);      // keys of this quarter inside [0, nk)
-            const uint32_t att = __ballot_sync(0xffffffffu, lane < n_exist && mraw != 0.f);
-            const bool plain = att == 0xffffffffu;
-            if (g + 1 < G) mraw = (t + 1 == T) ? mask_fetch(it + 1, 0) : mask_fetch(it, t + 1);
+            // ---- this half-tile's key mask as two 32-bit words (bit j = key 64*hf + j attends); no shared memory
+            const int n_exist = min(max(p.nk - t * AT_KT - 64 * hf, 0), 64);      // keys of this half inside [0, nk)
+            const uint32_t att_lo = __ballot_sync(0xffffffffu, lane < n_exist && mrawA != 0.f);
+            const uint32_t att_hi = __ballot_sync(0xffffffffu, lane + 32 < n_exist && mrawB != 0.f);
+            const bool plain = (att_lo & att_hi) == 0xffffffffu;
+            if (g + 1 < G) {
+                if (t + 1 == T) mask_fetch(it + 1, 0, mrawA, mrawB);
+                else mask_fetch(it, t + 1, mrawA, mrawB);
+            }
 
             mbar_wait(&s_full[slot], ph);
             tc_fence_after();
+            const uint32_t tmem_s = tmem_base + slot * 128 + 64 * hf + lane_field;
 
-            // ---- this thread's 32 scores into registers, then hand the accumulator back to the issuer
-            uint32_t sv[32];
-            tmem_ld_32x32(tmem_base + slot * 128 + 32 * kq + lane_field, sv);
+            // ---- this thread's 64 scores into registers, then hand the accumulator back to the issuer
+            uint32_t sv[2][32];
+            tmem_ld_32x32(tmem_s, sv[0]);
+            tmem_ld_32x32(tmem_s + 32, sv[1]);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_free[slot]);
 
-            // ---- x = scale * s (+ mask); row maximum (four independent chains).  Plain tiles keep raw s and fold the
-            //      scale into the ex2 FFMA.
-            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            // ---- x = scale * s (+ mask); row maximum.  Plain tiles keep raw s and fold the scale into the ex2 FFMA.
+            float mx = -INFINITY;
             float xs = p.scale_log2;           // multiplier applied inside the exponent
             if (plain) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(sv[j]));
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(sv[c][j]));
+                mx *= p.scale_log2;            // scale > 0: max commutes with the scaling
             } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float x = ((att >> j) & 1u) ? __uint_as_float(sv[j]) * p.scale_log2
-                                                      : ((j < n_exist) ? AT_MASKED : -INFINITY);
-                    sv[j] = __float_as_uint(x);
-                    mx4[j & 3] = fmaxf(mx4[j & 3], x);
+                for (int c = 0; c < 2; ++c) {
+                    const uint32_t att = c == 0 ? att_lo : att_hi;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float x = ((att >> j) & 1u) ? __uint_as_float(sv[c][j]) * p.scale_log2
+                                                          : ((c * 32 + j < n_exist) ? AT_MASKED : -INFINITY);
+                        sv[c][j] = __float_as_uint(x);
+                        mx = fmaxf(mx, x);
+                    }
                 }
                 xs = 1.0f;
             }
-            float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-            if (plain) mx *= p.scale_log2;     // scale > 0: max commutes with the scaling
-            // ---- row maximum over the four quarters: exchange bf16-rounded maxima (every warp uses the rounded values, so
-            //      all four agree exactly; any common reference is valid for the lazy scheme)
+            // ---- row maximum over both halves: exchange bf16-rounded maxima with the partner warp (both sides use
+            //      the rounded values, so they agree exactly; any common reference is valid for the lazy scheme)
             {
                 const __nv_bfloat16 mine = __float2bfloat16_rn(mx);
-                const uint32_t slot_addr = sx_addr + slot * 256 + lane * 2;
-                st_shared_u16(slot_addr + kq * 64, __bfloat16_as_ushort(mine));
-                named_bar_sync(quad_bar, 128);
-                const float m0 = __bfloat162float(__ushort_as_bfloat16(ld_shared_u16(slot_addr)));
-                const float m1 = __bfloat162float(__ushort_as_bfloat16(ld_shared_u16(slot_addr + 64)));
-                const float m2 = __bfloat162float(__ushort_as_bfloat16(ld_shared_u16(slot_addr + 128)));
-                const float m3 = __bfloat162float(__ushort_as_bfloat16(ld_shared_u16(slot_addr + 192)));
-                mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                sX[(slot * 2 + hf) * 32 + lane] = mine;
+                named_bar_sync(pair_bar, 64);
+                mx = fmaxf(__bfloat162float(mine), __bfloat162float(sX[(slot * 2 + (hf ^ 1)) * 32 + lane]));
             }
             // ---- lazy running max: rescale only when this tile exceeds the reference by more than 2^8
             const bool raise = mx > m_used + AT_LAZY;      // first tile: m_used = -inf -> true (mx is finite or AT_MASKED)
@@ -342,33 +349,35 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
                 mbar_wait(pv_done, (g - 1) & 1);
                 tc_fence_after();
                 pv_seen = true;
-                const uint32_t tmem_orow = tmem_o + lane_field + hsel * 64 + kq * 16;   // this thread's 16 O columns
-                uint32_t v[16];
-                tmem_ld_32x16(tmem_orow, v);
+                const uint32_t tmem_orow = tmem_o + lane_field + hsel * 64 + hf * 32;   // this thread's 32 O columns
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_orow, v);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
-                tmem_st_32x16(tmem_orow, v);
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
+                tmem_st_32x32(tmem_orow, v);
                 tmem_st_wait();
             }
-            // ---- p = 2^(x - m_used) -> bf16 -> P tile in shared memory (this thread's 32 keys = 4 chunks of slab kq / 2);
-            //      row sum in four independent chains
+            // ---- p = 2^(x - m_used) -> bf16 -> P tile in shared memory (slab hf = this thread's 64 keys); row sum
             const float neg_m = -m_used;
-            const uint32_t prow = smem_u32(sK + (g % AT_KSTAGES) * AT_TILE + (kq >> 1) * AT_SLAB);
-            float ps4[4] = {0.f, 0.f, 0.f, 0.f};
-            uint32_t pk[16];
+            uint8_t* prow = sK + (g % AT_KSTAGES) * AT_TILE + hf * AT_SLAB;
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-                const float p0 = ex2_approx(fmaf(__uint_as_float(sv[j]), xs, neg_m));
-                const float p1 = ex2_approx(fmaf(__uint_as_float(sv[j + 1]), xs, neg_m));
-                ps4[(j >> 1) & 3] += p0 + p1;
-                pk[j >> 1] = pack_bf16(p0, p1);
+            for (int c = 0; c < 2; ++c) {
+                float psum = 0.f;
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(sv[c][j]), xs, neg_m));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(sv[c][j + 1]), xs, neg_m));
+                    psum += p0 + p1;
+                    pk[j >> 1] = pack_bf16(p0, p1);
+                }
+                l_part += psum;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4*>(prow + swz128(r, c * 4 + j)) =
+                        make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
             }
-            l_part += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                st_shared_v4(prow + swz128(r, (kq & 1) * 4 + j),
-                             make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
             // every phase of pv_done is consumed in order, and phase g-1 before p_ready(g) is signalled: PV(g) cannot be
             // issued earlier, so the barrier is never more than one phase ahead of this thread's parity bookkeeping
             if (!pv_seen) mbar_wait(pv_done, (g - 1) & 1);
@@ -383,28 +392,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
                 store_q(it + 1, qv);
             }
             if (t == T - 1) {
-                // ---- finalize: row sum over the four quarters, then O / l -> bf16 -> global (16 of the row's 64 columns)
-                named_bar_sync(quad_bar, 128);             // everyone has read this tile's maxima: the area is idle
-                st_shared_f32(sx_addr + kq * 128 + lane * 4, l_part);
-                named_bar_sync(quad_bar, 128);
-                const float l_row = (ld_shared_f32(sx_addr + lane * 4) + ld_shared_f32(sx_addr + 128 + lane * 4)) +
-                                    (ld_shared_f32(sx_addr + 256 + lane * 4) + ld_shared_f32(sx_addr + 384 + lane * 4));
-                const float inv = 1.0f / l_row;
-                named_bar_sync(quad_bar, 128);             // sums have been read before the area holds maxima again
+                // ---- finalize: row sum over both halves, then O / l -> bf16 -> global (32 of the row's 64 columns)
+                named_bar_sync(pair_bar, 64);              // partner has read this tile's maxima: the area is idle
+                sSum[hf * 32 + lane] = l_part;
+                named_bar_sync(pair_bar, 64);
+                const float inv = 1.0f / (l_part + sSum[(hf ^ 1) * 32 + lane]);
+                named_bar_sync(pair_bar, 64);              // partner has read my sum before the area holds maxima again
                 mbar_wait(pv_done, g & 1);
                 tc_fence_after();
-                const uint32_t tmem_orow = tmem_o + lane_field + hsel * 64 + kq * 16;
+                const uint32_t tmem_orow = tmem_o + lane_field + hsel * 64 + hf * 32;
                 __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.nq + qrow) * p.ldo + (2 * hp + hsel) * 64 +
-                                     kq * 16;
-                uint32_t v[16];
-                tmem_ld_32x16(tmem_orow, v);
+                                     hf * 32;
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_orow, v);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(o_free);
                 if (qrow < p.nq) {
 #pragma unroll
-                    for (int j = 0; j < 2; ++j)
+                    for (int j = 0; j < 4; ++j)
                         *reinterpret_cast<uint4*>(dst + j * 8) = make_uint4(
                             pack_bf16(__uint_as_float(v[8 * j]) * inv, __uint_as_float(v[8 * j + 1]) * inv),
                             pack_bf16(__uint_as_float(v[8 * j + 2]) * inv, __uint_as_float(v[8 * j + 3]) * inv),
@@ -417,7 +424,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
 
     tc_fence_before();
     __syncthreads();
-    if (warp_idx == 17) {
+    if (warp_idx == 9) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
