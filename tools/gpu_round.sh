@@ -8,8 +8,8 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 for w in $what; do
 case $w in
 tests)
-  timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-  timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
+  timeout 300 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+  timeout 150 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
   ;;
 bench)
   timeout 900 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; echo "bench rc=$?" >> gpurun_out/bench_full.err
@@ -44,7 +44,7 @@ ncu)
   ls -la /tmp/*.ncu-rep >> gpurun_out/prof_users_raw.err
   ;;
 kernels)
-  timeout 600 python tools/gpu_bench_kernels.py > gpurun_out/kernels.log 2>&1; echo "kernels rc=$?" >> gpurun_out/kernels.log
+  timeout 240 python tools/gpu_bench_kernels.py > gpurun_out/kernels.log 2>&1; echo "kernels rc=$?" >> gpurun_out/kernels.log
   ;;
 esac
 done

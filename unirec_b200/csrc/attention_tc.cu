@@ -87,17 +87,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
     uint8_t* sV = smem + 5 * AT_TILE;             // [2][2 slabs]
     // smem + 7 tiles: [2][2][128] bf16 row-max exchange between the two softmax warps of a row quadrant (1 KB)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * AT_TILE + 2 * 2 * AT_KT * 2);
-    uint64_t* k_full = bars;            // [3]
-    uint64_t* k_empty = bars + 3;       // [3]  issuer (commit after PV: the slot held K, then P)
-    uint64_t* v_full = bars + 6;        // [2]
-    uint64_t* v_empty = bars + 8;       // [2]
-    uint64_t* q_ready = bars + 10;      // softmax warps -> issuer (one phase per work item); bars[11..13] unused
-    uint64_t* s_full = bars + 14;       // [2]  issuer (commit) -> softmax warps
-    uint64_t* s_free = bars + 16;       // [2]  softmax warps -> issuer
-    uint64_t* p_ready = bars + 18;      // softmax warps -> issuer
-    uint64_t* pv_done = bars + 19;      // issuer (commit) -> softmax warps
-    uint64_t* o_free = bars + 20;       // softmax warps -> issuer (O of the finished item has been read)
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 21);
+    uint64_t* k_full = bars;                        // [AT_KSTAGES]
+    uint64_t* k_empty = bars + AT_KSTAGES;          // [AT_KSTAGES]  issuer (commit after PV: the slot held K, then P)
+    uint64_t* v_full = bars + 2 * AT_KSTAGES;       // [2]
+    uint64_t* v_empty = bars + 2 * AT_KSTAGES + 2;  // [2]
+    uint64_t* s_full = bars + 2 * AT_KSTAGES + 4;   // [2]  issuer (commit) -> softmax warps
+    uint64_t* s_free = bars + 2 * AT_KSTAGES + 6;   // [2]  softmax warps -> issuer
+    uint64_t* q_ready = bars + 2 * AT_KSTAGES + 8;  // softmax warps -> issuer (one phase per work item)
+    uint64_t* p_ready = bars + 2 * AT_KSTAGES + 9;  // softmax warps -> issuer
+    uint64_t* pv_done = bars + 2 * AT_KSTAGES + 10; // issuer (commit) -> softmax warps
+    uint64_t* o_free = bars + 2 * AT_KSTAGES + 11;  // softmax warps -> issuer (O of the finished item has been read)
+    static_assert((2 * AT_KSTAGES + 12) * 8 + 4 <= 256, "barrier area too small");
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * AT_KSTAGES + 12);
 
     const int T = (p.nk + AT_KT - 1) / AT_KT;
     const int my_items = (p.num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
