@@ -23,10 +23,9 @@
 //                P (bf16) -> shared memory (K-major, swizzled) for the second MMA.  The running max is only
 //                raised when a tile exceeds it by more than 2^8 (exact: O and the row sum are accumulated against the
 //                same reference value), so O in TMEM is almost never rescaled.  Also builds Q2 for the NEXT item.
-//     warp 8     TMA producer: K tiles through a 4-stage ring, V tiles through a 2-stage ring.  P(g) is written IN PLACE
+//     warp 8     TMA producer: K tiles through a 3-stage ring, V tiles through a 2-stage ring.  P(g) is written IN PLACE
 //                over K(g) (same 32 KB footprint; K(g) is dead once S(g) has been accumulated), so the K slot is only
-//                released by PV(g) - the softmax of tile g+1 never waits for PV(g).  Four K stages (the Q2 tile is single-buffered to
-//                make room) keep the K loads two tile periods ahead: with three, the load latency WAS the tile period
+//                released by PV(g) - P is effectively triple-buffered and the softmax of tile g+1 never waits for PV(g)
 //     warp 9     TMEM allocator + UMMA issuer; issue order S(g+1), PV(g) so that the softmax of tile g overlaps
 //                the first MMA of tile g+1 (two S accumulators in TMEM) - across work items too
 // Mask semantics are those of attention.cu: key_mask == 0 adds -1e30 (log2 domain), keys beyond nk are excluded
@@ -40,8 +39,8 @@ constexpr int AT_KT = 128;                       // keys per tile
 constexpr int AT_SLAB = 128 * 64 * 2;            // [128 rows][64 bf16] = 16 KB
 constexpr int AT_TILE = 2 * AT_SLAB;             // 32 KB: Q2, a K tile, a V tile, P
 constexpr int AT_THREADS = 320;                  // 8 softmax warps + TMA producer + UMMA issuer
-constexpr int AT_KSTAGES = 4;                    // K ring depth (a K slot is reused as that tile's P)
-constexpr int AT_SMEM_BYTES = AT_TILE /*Q2*/ + AT_KSTAGES * AT_TILE /*K|P x4*/ + 2 * AT_TILE /*V x2*/ +
+constexpr int AT_KSTAGES = 3;                    // K ring depth (a K slot is reused as that tile's P)
+constexpr int AT_SMEM_BYTES = 2 * AT_TILE /*Q2 x2*/ + AT_KSTAGES * AT_TILE /*K|P x3*/ + 2 * AT_TILE /*V x2*/ +
                               2 * 2 * AT_KT * 2 /*row-max exchange*/ + 1024 /*align*/ + 256 /*barriers*/;
 static_assert(AT_SMEM_BYTES <= 232448, "shared memory budget exceeded");
 constexpr float AT_MASKED = -1.2676506002282294e30f;   // -2^100: stands in for finfo.min, exact in bf16 (row-max exchange)
@@ -82,23 +81,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ2 = smem;                          // [2 slabs]     rewritten for the next item once its last S is done
-    uint8_t* sK = smem + 1 * AT_TILE;             // [4][2 slabs]  K(g), later P(g)
+    uint8_t* sQ2 = smem;                          // [2][2 slabs]
+    uint8_t* sK = smem + 2 * AT_TILE;             // [3][2 slabs]  K(g), later P(g)
     uint8_t* sV = smem + 5 * AT_TILE;             // [2][2 slabs]
     // smem + 7 tiles: [2][2][128] bf16 row-max exchange between the two softmax warps of a row quadrant (1 KB)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * AT_TILE + 2 * 2 * AT_KT * 2);
-    uint64_t* k_full = bars;                        // [AT_KSTAGES]
-    uint64_t* k_empty = bars + AT_KSTAGES;          // [AT_KSTAGES]  issuer (commit after PV: the slot held K, then P)
-    uint64_t* v_full = bars + 2 * AT_KSTAGES;       // [2]
-    uint64_t* v_empty = bars + 2 * AT_KSTAGES + 2;  // [2]
-    uint64_t* s_full = bars + 2 * AT_KSTAGES + 4;   // [2]  issuer (commit) -> softmax warps
-    uint64_t* s_free = bars + 2 * AT_KSTAGES + 6;   // [2]  softmax warps -> issuer
-    uint64_t* q_ready = bars + 2 * AT_KSTAGES + 8;  // softmax warps -> issuer (one phase per work item)
-    uint64_t* p_ready = bars + 2 * AT_KSTAGES + 9;  // softmax warps -> issuer
-    uint64_t* pv_done = bars + 2 * AT_KSTAGES + 10; // issuer (commit) -> softmax warps
-    uint64_t* o_free = bars + 2 * AT_KSTAGES + 11;  // softmax warps -> issuer (O of the finished item has been read)
-    static_assert((2 * AT_KSTAGES + 12) * 8 + 4 <= 256, "barrier area too small");
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * AT_KSTAGES + 12);
+    uint64_t* k_full = bars;            // [3]
+    uint64_t* k_empty = bars + 3;       // [3]  issuer (commit after PV: the slot held K, then P)
+    uint64_t* v_full = bars + 6;        // [2]
+    uint64_t* v_empty = bars + 8;       // [2]
+    uint64_t* q_ready = bars + 10;      // [2]  softmax warps -> issuer
+    uint64_t* q_free = bars + 12;       // [2]  issuer (commit) -> softmax warps
+    uint64_t* s_full = bars + 14;       // [2]  issuer (commit) -> softmax warps
+    uint64_t* s_free = bars + 16;       // [2]  softmax warps -> issuer
+    uint64_t* p_ready = bars + 18;      // softmax warps -> issuer
+    uint64_t* pv_done = bars + 19;      // issuer (commit) -> softmax warps
+    uint64_t* o_free = bars + 20;       // softmax warps -> issuer (O of the finished item has been read)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 21);
 
     const int T = (p.nk + AT_KT - 1) / AT_KT;
     const int my_items = (p.num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
@@ -112,9 +111,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
         for (int i = 0; i < AT_KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+            mbar_init(&q_ready[i], 8); mbar_init(&q_free[i], 1);
             mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 8);
         }
-        mbar_init(q_ready, 8);
         mbar_init(p_ready, 8);
         mbar_init(pv_done, 1);
         mbar_init(o_free, 8);
@@ -166,12 +165,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
             const int slot = g & 1;
             const uint32_t ph = (g >> 1) & 1;
             const int kslot = g % AT_KSTAGES;
-            if (t == 0) mbar_wait(q_ready, it & 1);
+            if (t == 0) mbar_wait(&q_ready[it & 1], (it >> 1) & 1);
             mbar_wait(&k_full[kslot], (g / AT_KSTAGES) & 1);
             mbar_wait(&s_free[slot], ph ^ 1);
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t a_addr = smem_u32(sQ2);
+                const uint32_t a_addr = smem_u32(sQ2 + (it & 1) * AT_TILE);
                 const uint32_t b_addr = smem_u32(sK + kslot * AT_TILE);
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
@@ -180,6 +179,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
                                  umma_smem_desc_sw128(b_addr + off), idesc_s, ks != 0 ? 1u : 0u);
                 }
                 umma_commit(&s_full[slot]);
+                if (t == T - 1) umma_commit(&q_free[it & 1]);
             }
             __syncwarp();
         };
@@ -240,13 +240,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
                 qv[c] = (hf == 0 && qrow < p.nq) ? __ldg(reinterpret_cast<const uint4*>(src) + c) : make_uint4(0, 0, 0, 0);
         };
         auto store_q = [&](int it_, const uint4 (&qv)[8]) {
-            (void)it_;
-            uint8_t* base = sQ2 + (hf == 0 ? hsel : (hsel ^ 1)) * AT_SLAB;
+            uint8_t* base = sQ2 + (it_ & 1) * AT_TILE + (hf == 0 ? hsel : (hsel ^ 1)) * AT_SLAB;
 #pragma unroll
             for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(base + swz128(r, c)) = qv[c];
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(q_ready);
+            if (lane == 0) mbar_arrive(&q_ready[it_ & 1]);
         };
 
         uint4 qv[8];
@@ -303,9 +302,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_free[slot]);
-            // Q2 of the next item: s_full of this item's LAST tile means every S MMA that reads the (single) Q2 buffer has
-            // completed, so it can be rewritten right here - well before the issuer needs it for the next item's first S
-            if (t == T - 1 && it + 1 < my_items) store_q(it + 1, qv);
 
             // ---- x = scale * s (+ mask); row maximum.  Plain tiles keep raw s and fold the scale into the ex2 FFMA.
             float mx = -INFINITY;
@@ -390,6 +386,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(p_ready);
 
+            if (t == 0 && it + 1 < my_items) {
+                // Q2 of the next item (its buffer was last read by item it-1, long finished)
+                if (it >= 1) mbar_wait(&q_free[(it + 1) & 1], ((it - 1) >> 1) & 1);
+                store_q(it + 1, qv);
+            }
             if (t == T - 1) {
                 // ---- finalize: row sum over both halves, then O / l -> bf16 -> global (32 of the row's 64 columns)
                 named_bar_sync(pair_bar, 64);              // partner has read this tile's maxima: the area is idle
