@@ -10,7 +10,7 @@ COLS = {
     "dur_ms": r"^gpu__time_duration\.sum$",
     "rd": r"^dram__bytes_read\.sum$",
     "wr": r"^dram__bytes_write\.sum$",
-    "dram_pct": r"dram__throughput\.avg\.pct_of_peak_sustained_elapsed$",
+    "dram_pct": r"^gpu__dram_throughput\.avg\.pct_of_peak_sustained_elapsed$",
     "tensor_pct": r"sm__pipe_tensor_cycles_active_realtime\.avg\.pct_of_peak_sustained_elapsed$",
     "issue_pct": r"^sm__issue_active\.avg\.pct_of_peak_sustained_elapsed$",
     "warps_pct": r"^sm__warps_active\.avg\.pct_of_peak_sustained_active$",
