@@ -283,10 +283,23 @@ def run_train_block(args, rank, world, dev, barrier, max_over_ranks, pk):
         torch.cuda.profiler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    prof = None
+    if os.environ.get("BENCH_PROFILE_TRAIN"):          # diagnostics: host-side profile of the steady-state loop
+        import cProfile
+        prof = cProfile.Profile()
+        prof.enable()
     t_host0 = time.perf_counter()
     for i in range(args.train_steps):
         loss = step(i)
     host_ms = (time.perf_counter() - t_host0) * 1e3 / args.train_steps
+    if prof is not None:
+        import io
+        import pstats
+        prof.disable()
+        buf = io.StringIO()
+        pstats.Stats(prof, stream=buf).sort_stats("tottime").print_stats(40)
+        pstats.Stats(prof, stream=buf).sort_stats("cumulative").print_stats(40)
+        open(os.environ["BENCH_PROFILE_TRAIN"], "w").write(buf.getvalue())
     e1.record()
     barrier()
     if args.profile_range == "train":
