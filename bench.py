@@ -278,7 +278,8 @@ def run_train_block(args, rank, world, dev, barrier, max_over_ranks, pk):
         step(i)
     barrier()
     l0 = _lib.launch_count()
-    ops.start_timing()
+    if world == 1:
+        ops.start_timing()      # per-launch CUDA events cost the host ~5 ms per step: only for the 1-GPU roofline
     if args.profile_range == "train":
         torch.cuda.profiler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -305,7 +306,7 @@ def run_train_block(args, rank, world, dev, barrier, max_over_ranks, pk):
     if args.profile_range == "train":
         torch.cuda.profiler.stop()
     ms = max_over_ranks(e0.elapsed_time(e1)) / args.train_steps
-    stats = ops.stop_timing()
+    stats = ops.stop_timing() if world == 1 else {}
     launches = (_lib.launch_count() - l0) // args.train_steps
     step(0, faithful=True)
     barrier()

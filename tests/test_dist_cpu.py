@@ -85,8 +85,17 @@ def _allreduce_worker(rank, world, port, q):
         for li in (2, 1, 0):                            # backward order
             red.layer_ready(li, layers[li])
         red.layer_ready(-1, [big, None])
+        # in-place bucket: the tensors are views tiling one contiguous buffer (the backbone's flat gradient buffer)
+        flatbuf = torch.randn(50, generator=g)
+        flat_keep = flatbuf.clone()
+        fviews = [flatbuf[:35].view(7, 5), flatbuf[35:40], flatbuf[40:]]
+        red.layer_ready(5, fviews, flatbuf)
         red.finish()
         assert not red.pending
+        gathered = [torch.empty_like(flat_keep) for _ in range(world)]
+        dist.all_gather(gathered, flat_keep)
+        assert torch.allclose(flatbuf, sum(gathered) / world, atol=1e-6)
+        assert torch.equal(fviews[0].reshape(-1), flatbuf[:35])
         # expected: mean over ranks
         ok = True
         for ts, mine in zip(layers + [[big]], keep):

@@ -138,8 +138,28 @@ class BackboneTrainFn(torch.autograd.Function):
             # gradient of the dense output behind dropout(dense) + residual
             return dpre if st is None else ops.dropout_backward(dpre, st)
 
+        # every parameter gradient of the backbone lives in ONE zero-initialised fp32 buffer (one memset instead of ~190
+        # torch.zeros launches per step - the host enqueues this step almost as slowly as the GPU runs it), laid out layer
+        # by layer from the last layer to the first, so that a layer's gradients are one contiguous bucket that the
+        # data-parallel all-reduce can take in place
+        def layer_numel(L):
+            n = 3 * H * H + 3 * H + H * H + H + 2 * H + I * H + I + H * I + H + 2 * H
+            if L["cross"]:
+                n += 2 * (H * H + H) + 2 * H
+            return n
+        n_cross = sum(1 for L in pk["layers"] if L["cross"])
+        E = ctx.enc2.shape[1]
+        kv_numel = (2 * H * n_cross) * E + 2 * H * n_cross if n_cross else 0
+        flat = torch.zeros(sum(layer_numel(L) for L in pk["layers"]) + kv_numel, device=dev, dtype=torch.float32)
+        cursor = [0]
+
         def zeros(*shape):
-            return torch.zeros(*shape, device=dev, dtype=torch.float32)
+            n = 1
+            for d_ in shape:
+                n *= d_
+            v = flat[cursor[0]:cursor[0] + n].view(*shape)
+            cursor[0] += n
+            return v
 
         def lin_bwd(dy, x, w16, need_dx=True):
             dw = zeros(*w16.shape)
@@ -148,7 +168,6 @@ class BackboneTrainFn(torch.autograd.Function):
             ops.colsum(dy, db)
             return (ops.linear_dgrad(dy, w16) if need_dx else None), dw, db
 
-        n_cross = sum(1 for L in pk["layers"] if L["cross"])
         d_kv_all = torch.zeros(B * S, 2 * H * n_cross, device=dev, dtype=torch.bfloat16) if n_cross else None
         dy = d_out.reshape(M, H).to(torch.bfloat16).contiguous()
         dy2 = None
@@ -156,6 +175,7 @@ class BackboneTrainFn(torch.autograd.Function):
         for li in range(len(pk["layers"]) - 1, -1, -1):
             L, t = pk["layers"][li], ctx.tape[li]
             g = {}
+            bucket_lo = cursor[0]
             # ---- query FFN: h_out = LN3(a W2^T + b2 + h_mid), a = gelu(h_mid W1^T + b1)
             g["ln3_g"], g["ln3_b"] = zeros(H), zeros(H)
             dpre3 = ops.layernorm_backward(t["pre3"], dy, L["ln3_g"], eps, g["ln3_g"], g["ln3_b"], dy2=dy2)
@@ -188,10 +208,12 @@ class BackboneTrainFn(torch.autograd.Function):
             dy, dy2 = dpre1, dh_in
             layer_grads[li] = g
             ctx.tape[li] = None                           # free this layer's activations
+            assert cursor[0] - bucket_lo == layer_numel(L)
             if on_ready is not None:
-                on_ready(li, [v for v in g.values()])
+                on_ready(li, [v for v in g.values()], flat[bucket_lo:cursor[0]])
         # ---- cross-attention K/V projection of all layers (one GEMM in the forward pass)
         g_kv_w = g_kv_b = None
+        kv_lo = cursor[0]
         if n_cross:
             _, g_kv_w, g_kv_b = lin_bwd(d_kv_all, ctx.enc2, pk["w_kv_all"], need_dx=False)
         # ---- query-token LayerNorm (batch-invariant): sum over the batch, then a [Q, H] LayerNorm backward (torch)
@@ -218,7 +240,9 @@ class BackboneTrainFn(torch.autograd.Function):
             grads += [g["w_1"], g["b_1"], g["w_2"], g["b_2"], g["ln3_g"], g["ln3_b"]]
         d_query = q0.grad.view(1, Q, H)
         if on_ready is not None:
-            on_ready(-1, ([g_kv_w, g_kv_b] if n_cross else []) + [eg.grad, eb.grad, d_query])
+            if n_cross:
+                on_ready(-1, [g_kv_w, g_kv_b], flat[kv_lo:cursor[0]])
+            on_ready(-3, [eg.grad, eb.grad, d_query])
         if on_finish is not None:
             on_finish()        # every bucket reduced and written back before autograd sees the gradients
         return (None, None, None, None, d_query) + tuple(grads)
@@ -262,19 +286,25 @@ class GradientAllReducer:
         backbone.grad_finish_hook = self.finish
         return self
 
-    def layer_ready(self, layer_index: int, tensors: List[torch.Tensor]):
+    def layer_ready(self, layer_index: int, tensors: List[torch.Tensor], flat: Optional[torch.Tensor] = None):
+        """`flat`: the tensors are views that tile this contiguous buffer exactly (the backbone's gradient buffer) -
+        it is reduced in place, without the pack / unpack copies."""
         tensors = [t for t in tensors if t is not None]
         if self.world == 1 or not tensors:
             return
-        flat = torch.cat([t.reshape(-1).to(self.bucket_dtype) for t in tensors])
+        in_place = flat is not None and flat.dtype == self.bucket_dtype
+        if not in_place:
+            flat = torch.cat([t.reshape(-1).to(self.bucket_dtype) for t in tensors])
         work = self.dist.all_reduce(flat, group=self.group, async_op=True)
         self.bytes_reduced += flat.numel() * flat.element_size()
-        self.pending.append((work, flat, tensors))
+        self.pending.append((work, flat, None if in_place else tensors))
 
     def finish(self):
         for work, flat, tensors in self.pending:
             work.wait()
             flat.div_(self.world)
+            if tensors is None:
+                continue
             off = 0
             for t in tensors:
                 n = t.numel()
