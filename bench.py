@@ -319,6 +319,54 @@ def run_train_block(args, rank, world, dev, barrier, max_over_ranks, pk):
     ms_faithful = max_over_ranks(f0.elapsed_time(f1)) / args.train_steps
     gemm = stats.get("gemm")
     ach = gemm[1] / (gemm[2] * 1e-3) / 1e12 if gemm and gemm[2] > 0 else None
+    eager_ms, eager_faithful_ms, eager_host_ms = ms, ms_faithful, host_ms
+
+    # ---- the same step replayed from a CUDA graph (training.TrainStepGraph): one launch per step instead of ~435, the
+    # gradient all-reduce (one flat bucket) and the fused AdamW stay outside the graph
+    graph_info = {"used": False}
+    try:
+        from unirec_b200.training import TrainStepGraph
+        opt.zero_grad(set_to_none=True)
+
+        def timed_graph(faithful):
+            tg = TrainStepGraph(model, fields[0], mask, faithful=faithful)
+
+            def gstep(i):
+                if faithful:
+                    loss_ = tg.step(fields[i % nb], mask, fields[(i + 1) % nb], fields[(i + 2) % nb])
+                else:
+                    loss_ = tg.step(fields[i % nb], mask, pos, neg)
+                red.reduce_tensors(tg.grad_tensors())
+                opt.step()
+                return loss_
+
+            for i in range(2):
+                gstep(i)
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            t_h = time.perf_counter()
+            for i in range(args.train_steps):
+                loss_ = gstep(i)
+            h_ms = (time.perf_counter() - t_h) * 1e3 / args.train_steps
+            g1.record()
+            barrier()
+            ms_ = max_over_ranks(g0.elapsed_time(g1)) / args.train_steps
+            val = float(loss_)
+            opt.zero_grad(set_to_none=True)
+            del tg
+            torch.cuda.empty_cache()
+            return ms_, h_ms, val
+
+        g_ms, g_host_ms, g_loss = timed_graph(False)
+        gf_ms, _, _ = timed_graph(True)
+        graph_info = {"used": True, "ms_per_step": g_ms, "host_enqueue_ms_per_step": g_host_ms,
+                      "faithful_ms_per_step": gf_ms, "final_loss": g_loss,
+                      "what": "forward + loss + backward replayed from one CUDA graph (device-resident dropout seed "
+                              "offset); flat gradient all-reduce and fused AdamW outside the graph"}
+        ms, ms_faithful, host_ms = g_ms, gf_ms, g_host_ms
+    except Exception as e:   # keep the eager numbers if capture is not possible on this box
+        graph_info = {"used": False, "error": f"{type(e).__name__}: {e}"[:300]}
     items_per_sec = Bg / (ms * 1e-3)
     del model, opt
     torch.cuda.empty_cache()
@@ -330,10 +378,15 @@ def run_train_block(args, rank, world, dev, barrier, max_over_ranks, pk):
         "reference_faithful_step": {"what": "anchor fwd+bwd + two no-grad train-mode forwards (positive, negative)",
                                     "ms_per_step": ms_faithful, "items_per_s": Bg / (ms_faithful * 1e-3)},
         "final_loss": float(loss.detach()), "gpu_launches_per_step": launches,
+        "mode": "cuda_graph" if graph_info.get("used") else "eager",
+        "cuda_graph": graph_info,
+        "eager": {"ms_per_step": eager_ms, "items_per_s": Bg / (eager_ms * 1e-3), "host_enqueue_ms_per_step": eager_host_ms,
+                  "faithful_ms_per_step": eager_faithful_ms},
         "allreduce_bytes_per_step": red.bytes_reduced // max(args.train_steps + 2, 1),
         "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                      "frac": (ach / pk["bf16_sustained"]) if ach else None,
-                     "share_of_step": (gemm[2] / (ms * args.train_steps)) if gemm else None,
+                     "share_of_step": (gemm[2] / (eager_ms * args.train_steps)) if gemm else None,
+                     "timed_in": "eager steps (per-launch CUDA events cannot be recorded inside a graph replay)",
                      "end_to_end_frac_of_tensor_peak":
                          items_per_sec / world * 3 * FLOPS_PER_ITEM / (pk["bf16_sustained"] * 1e12)},
     }

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define UNIREC_B200_ABI_VERSION 1
+#define UNIREC_B200_ABI_VERSION 2
 
 #define UNIREC_OK 0
 #define UNIREC_ERR_BAD_ARG 1
@@ -165,6 +165,9 @@ int unirec_attention_backward(const void* q, int64_t ldq, int64_t q_batch_rows,
  * masks from torch's global RNG; here a mask bit is a pure function of (seed, site, element) through Philox4x32-10 so
  * that forward, backward and the CPU oracle agree bit for bit (definition: unirec_b200/csrc/dropout.cuh, restated in
  * oracle/dropout_masks.py).  thr16 = round(p * 65536) (0 = off); kept elements are scaled by 65536 / (65536 - thr16).
+ * seed_offset: NULL, or a DEVICE pointer to one uint64 that the kernels add to `seed` when they run - a training step
+ * captured once into a CUDA graph (unirec_b200/training.py::TrainStepGraph) increments that word inside the graph and
+ * so draws fresh masks on every replay although `seed` itself is frozen in the captured launch parameters.
  * ------------------------------------------------------------------------------------------- */
 
 /* unirec_attention with dropout on the probabilities (after the softmax, before the product with V). */
@@ -172,7 +175,8 @@ int unirec_attention_dropout(const void* q, int64_t ldq, int64_t q_batch_rows,
                              const void* k, int64_t ldk, const void* v, int64_t ldv, int64_t kv_batch_rows,
                              const float* key_mask, void* out, int64_t ldo,
                              int64_t batch, int64_t num_heads, int64_t nq, int64_t nk, int64_t head_dim,
-                             float scale, uint32_t thr16, uint64_t seed, uint32_t site, void* stream);
+                             float scale, uint32_t thr16, uint64_t seed, uint32_t site,
+                             const uint64_t* seed_offset, void* stream);
 
 /* unirec_attention_backward for a forward pass run with unirec_attention_dropout(thr16, seed, site). */
 int unirec_attention_dropout_backward(const void* q, int64_t ldq, int64_t q_batch_rows,
@@ -180,18 +184,19 @@ int unirec_attention_dropout_backward(const void* q, int64_t ldq, int64_t q_batc
                                       const float* key_mask, const void* dout, int64_t lddo,
                                       void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
                                       int64_t batch, int64_t num_heads, int64_t nq, int64_t nk, int64_t head_dim,
-                                      float scale, uint32_t thr16, uint64_t seed, uint32_t site, void* stream);
+                                      float scale, uint32_t thr16, uint64_t seed, uint32_t site,
+                             const uint64_t* seed_offset, void* stream);
 
 /* out[r,:] = dropout(x[r % x_row_mod or r,:]) + residual[r,:]  (bf16; residual NULL = no residual; H % 8 == 0):
  * the pre-LayerNorm sum "dropout(dense(x)) + input_tensor" of models/qformer.py:287-288 / :373-374, and the dropped
  * query embeddings of :107 (x_row_mod = number of query tokens, residual NULL). */
 int unirec_dropout_add(const void* x, int64_t ldx, int64_t x_row_mod, const void* residual, int64_t ldres,
                        void* out, int64_t ldo, int64_t rows, int64_t H,
-                       uint32_t thr16, uint64_t seed, uint32_t site, void* stream);
+                       uint32_t thr16, uint64_t seed, uint32_t site, const uint64_t* seed_offset, void* stream);
 
 /* dx = dy o mask * scale  (gradient of the dropped branch). */
 int unirec_dropout_backward(const void* dy, int64_t lddy, void* dx, int64_t lddx, int64_t rows, int64_t H,
-                            uint32_t thr16, uint64_t seed, uint32_t site, void* stream);
+                            uint32_t thr16, uint64_t seed, uint32_t site, const uint64_t* seed_offset, void* stream);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/unirec_b200.h but not exported"
     # the ctypes binding covers exactly the declared surface
     assert set(_lib.EXPORTED_SYMBOLS) == declared
-    assert _lib.load().unirec_abi_version() == 1
+    assert _lib.load().unirec_abi_version() == 2
 
 
 def test_workspace_query_is_host_only():

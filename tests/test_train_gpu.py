@@ -310,3 +310,114 @@ def test_train_mode_no_grad_forward_uses_dropout_and_eval_does_not():
     e1 = model(x.to(DEV), mask.to(DEV))["query_outputs"]
     e2 = model(x.to(DEV), mask.to(DEV))["query_outputs"]
     assert torch.equal(e1, e2)
+
+
+def test_dropout_seed_offset_equals_seed_addition():
+    """The device-resident seed offset (include/unirec_b200.h: seed_offset) is exactly `seed + *seed_offset`: row
+    dropout and attention dropout with (seed, offset = d) reproduce (seed + d, no offset) bit for bit."""
+    from unirec_b200 import ops
+    thr = ops.dropout_threshold(0.2)
+    seed, d, site = (1 << 33) + 77, 4096 + 5, 11
+    off = torch.tensor([d], device=DEV, dtype=torch.int64)
+    x = _randn(300, 256, seed=70, dtype=torch.bfloat16)
+    res = _randn(300, 256, seed=71, dtype=torch.bfloat16)
+    assert torch.equal(ops.dropout_add(x, res, (thr, seed, site, off)), ops.dropout_add(x, res, (thr, seed + d, site)))
+    assert torch.equal(ops.dropout_backward(x, (thr, seed, site, off)), ops.dropout_backward(x, (thr, seed + d, site)))
+    assert not torch.equal(ops.dropout_add(x, res, (thr, seed, site, off)), ops.dropout_add(x, res, (thr, seed, site)))
+    B, heads, nq, nk = 5, 4, 32, 14
+    q = _randn(B * nq, heads * 64, seed=72, dtype=torch.bfloat16)
+    k = _randn(B * nk, heads * 64, seed=73, dtype=torch.bfloat16)
+    v = _randn(B * nk, heads * 64, seed=74, dtype=torch.bfloat16)
+    a = ops.attention(q, k, v, batch=B, num_heads=heads, nq=nq, nk=nk, dropout=(thr, seed, site, off))
+    b = ops.attention(q, k, v, batch=B, num_heads=heads, nq=nq, nk=nk, dropout=(thr, seed + d, site))
+    assert torch.equal(a, b)
+    do = _randn(B * nq, heads * 64, seed=75, dtype=torch.bfloat16)
+    g1 = [torch.empty_like(t) for t in (q, k, v)]
+    g2 = [torch.empty_like(t) for t in (q, k, v)]
+    ops.attention_backward(q, k, v, do, *g1, batch=B, num_heads=heads, nq=nq, nk=nk, dropout=(thr, seed, site, off))
+    ops.attention_backward(q, k, v, do, *g2, batch=B, num_heads=heads, nq=nq, nk=nk, dropout=(thr, seed + d, site))
+    for t1, t2 in zip(g1, g2):
+        assert torch.equal(t1, t2)
+
+
+def _small_train_model(dropout, seed=61):
+    from tests.golden_cases import ITEM_CASES
+    from unirec_b200 import synth
+    from unirec_b200.modules import QFormerForItemRepresentation
+    c = ITEM_CASES["small"]
+    mk = c["model"]
+    sd = synth.item_qformer_state_dict(**mk, seed=seed, attn_std=0.1)
+    model = QFormerForItemRepresentation(hidden_size=mk["hidden"], num_hidden_layers=mk["layers"],
+                                         num_attention_heads=c["heads"], intermediate_size=mk["inter"],
+                                         num_query_tokens=mk["num_query"], field_embedding_dim=mk["field_dim"],
+                                         num_fields=mk["num_fields"], dropout=dropout)
+    model.load_state_dict(sd, strict=True)
+    return model.to(DEV).train()
+
+
+def test_train_step_graph_matches_eager_steps():
+    """Three optimizer steps of the reference's training step (forward, QFormerLoss, backward, AdamW) replayed from
+    one CUDA graph give the same loss sequence and the same weights as the same three steps enqueued eagerly."""
+    from unirec_b200 import _lib, synth
+    from unirec_b200.training import TrainStepGraph, qformer_loss
+    B = 64
+    batches = [synth.item_fields(batch=B, num_fields=6, dim=256, seed=80 + i, clip_field=2, presence=0.8) for i in range(3)]
+    batches = [(x.to(DEV), m.to(DEV)) for x, m in batches]
+    pos, neg = _randn(B, 256, seed=90), _randn(B, 256, seed=91)
+
+    eager = _small_train_model(0.0)
+    opt_e = torch.optim.AdamW(eager.parameters(), lr=1e-3, fused=True)
+    losses_e = []
+    for x, m in batches:
+        loss = qformer_loss(eager(x, m), x, m, pos, neg)
+        loss.backward()
+        opt_e.step()
+        opt_e.zero_grad(set_to_none=True)
+        losses_e.append(float(loss))
+
+    model = _small_train_model(0.0)
+    opt_g = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=True)
+    tg = TrainStepGraph(model, batches[0][0], batches[0][1])
+    assert len(tg.grads) > 60
+    losses_g = []
+    for x, m in batches:
+        before = _lib.launch_count()
+        loss = tg.step(x, m, pos, neg)
+        assert _lib.launch_count() == before          # a replay enqueues nothing through the Python wrappers
+        opt_g.step()
+        losses_g.append(float(loss))
+    print("eager", losses_e, "graph", losses_g)
+    for a, b in zip(losses_e, losses_g):
+        assert abs(a - b) <= 2e-3 * abs(a) + 1e-4, (losses_e, losses_g)
+    assert losses_g[0] != losses_g[1]                  # the replays really consumed new inputs / new weights
+    # Adam's first updates are +-lr whatever the gradient's size, so an element whose gradient is rounding noise
+    # (split-K atomics reorder fp32 sums) may move the other way: bound the worst case by 3 steps x 2 lr and require
+    # that such elements are rare
+    worst, total, n_el = 0.0, 0.0, 0
+    for (n, pe), (_, pg) in zip(eager.named_parameters(), model.named_parameters()):
+        d = (pe - pg).abs()
+        worst, total, n_el = max(worst, float(d.max())), total + float(d.sum()), n_el + d.numel()
+    assert worst <= 6.5e-3 and total / n_el < 1e-4, (worst, total / n_el)
+
+
+def test_train_step_graph_draws_fresh_dropout_masks_per_replay():
+    """With dropout 0.2 the seed frozen into the captured launches is offset by a device counter that the graph
+    advances: replays on the same batch and weights give different losses, and resetting the counter reproduces one."""
+    from unirec_b200 import synth
+    from unirec_b200.training import TrainStepGraph
+    B = 64
+    x, m = synth.item_fields(batch=B, num_fields=6, dim=256, seed=85, clip_field=2, presence=0.8)
+    x, m = x.to(DEV), m.to(DEV)
+    model = _small_train_model(0.2)
+    model.dropout_seed = 999
+    tg = TrainStepGraph(model, x, m, faithful=True)
+    tg.seed_offset.zero_()
+    a = float(tg.step(x, m, x, x))
+    grad_a = tg.grad_tensors()[5].clone()
+    b = float(tg.step(x, m, x, x))
+    assert int(tg.seed_offset) == 2 * TrainStepGraph.SEED_STRIDE
+    assert abs(a - b) > 1e-4 * abs(a), (a, b)          # different masks
+    tg.seed_offset.zero_()
+    c = float(tg.step(x, m, x, x))
+    assert abs(a - c) <= 1e-5 * abs(a) + 1e-6, (a, c)  # same masks (split-K atomics reorder fp32 sums only)
+    torch.testing.assert_close(tg.grad_tensors()[5], grad_a, rtol=1e-3, atol=1e-5)

@@ -53,15 +53,15 @@ _SIGNATURES = {
                                           c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p]),
     "unirec_attention_dropout": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64,
                                          c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_float,
-                                         c_uint32, c_uint64, c_uint32, c_void_p]),
+                                         c_uint32, c_uint64, c_uint32, c_void_p, c_void_p]),
     "unirec_attention_dropout_backward": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                                                   c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                                   c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
-                                                  c_int64, c_float, c_uint32, c_uint64, c_uint32, c_void_p]),
+                                                  c_int64, c_float, c_uint32, c_uint64, c_uint32, c_void_p, c_void_p]),
     "unirec_dropout_add": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64,
-                                   c_uint32, c_uint64, c_uint32, c_void_p]),
+                                   c_uint32, c_uint64, c_uint32, c_void_p, c_void_p]),
     "unirec_dropout_backward": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_uint32, c_uint64,
-                                        c_uint32, c_void_p]),
+                                        c_uint32, c_void_p, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

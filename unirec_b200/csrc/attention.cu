@@ -208,21 +208,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
         if (DROP) {
             // the row sum above is that of the un-dropped probabilities (softmax first, dropout second, :250-258)
+            const DropoutParams drop = dropout_resolve(p.drop);
             const unsigned long long row0 =
                 static_cast<unsigned long long>(blockIdx.x + it * gridDim.x) * p.nq + warp * 16 + g4;
 #pragma unroll
             for (int kb = 0; kb < (KT + 31) / 32; ++kb) {
                 const uint32_t group = static_cast<uint32_t>(((tile * KT) >> 5) + kb) * 4 + t;
-                const uint32_t k0 = dropout_keep8(p.drop, row0, group);
-                const uint32_t k1 = dropout_keep8(p.drop, row0 + 8, group);
+                const uint32_t k0 = dropout_keep8(drop, row0, group);
+                const uint32_t k1 = dropout_keep8(drop, row0 + 8, group);
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) {
                     const int j = kb * 4 + nt;
                     if (j < KT / 8) {
-                        s[j][0] = ((k0 >> (2 * nt)) & 1u) ? s[j][0] * p.drop.scale : 0.f;
-                        s[j][1] = ((k0 >> (2 * nt + 1)) & 1u) ? s[j][1] * p.drop.scale : 0.f;
-                        s[j][2] = ((k1 >> (2 * nt)) & 1u) ? s[j][2] * p.drop.scale : 0.f;
-                        s[j][3] = ((k1 >> (2 * nt + 1)) & 1u) ? s[j][3] * p.drop.scale : 0.f;
+                        s[j][0] = ((k0 >> (2 * nt)) & 1u) ? s[j][0] * drop.scale : 0.f;
+                        s[j][1] = ((k0 >> (2 * nt + 1)) & 1u) ? s[j][1] * drop.scale : 0.f;
+                        s[j][2] = ((k1 >> (2 * nt)) & 1u) ? s[j][2] * drop.scale : 0.f;
+                        s[j][3] = ((k1 >> (2 * nt + 1)) & 1u) ? s[j][3] * drop.scale : 0.f;
                     }
                 }
             }
@@ -314,7 +315,8 @@ static bool attention_tc_enabled() {
 int attention(const void* q, long long ldq, long long q_batch_rows, const void* k, long long ldk, const void* v,
               long long ldv, long long kv_batch_rows, const float* key_mask, void* out, long long ldo, long long batch,
               long long num_heads, long long nq, long long nk, long long head_dim, float scale, unsigned drop_thr16,
-              unsigned long long drop_seed, unsigned drop_site, cudaStream_t stream) {
+              unsigned long long drop_seed, unsigned drop_site, const unsigned long long* drop_seed_offset,
+              cudaStream_t stream) {
     if (q == nullptr || k == nullptr || v == nullptr || out == nullptr || batch <= 0 || num_heads <= 0 || nq <= 0 ||
         nk <= 0) {
         set_last_error("attention: null pointer or empty shape");
@@ -343,7 +345,7 @@ int attention(const void* q, long long ldq, long long q_batch_rows, const void* 
     p.num_heads = static_cast<int>(num_heads); p.nq = static_cast<int>(nq); p.nk = static_cast<int>(nk);
     p.q_broadcast = q_batch_rows == 0 ? 1 : 0;
     p.scale_log2 = scale * 1.4426950408889634f;
-    p.drop.thr16 = drop_thr16; p.drop.seed = drop_seed; p.drop.site = drop_site;
+    p.drop.thr16 = drop_thr16; p.drop.seed = drop_seed; p.drop.site = drop_site; p.drop.seed_offset = drop_seed_offset;
     p.drop.scale = 65536.0f / (65536.0f - static_cast<float>(drop_thr16));
     const int nwarps = static_cast<int>((nq + 15) / 16);
     const int threads = nwarps * 32;

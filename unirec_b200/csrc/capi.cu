@@ -27,12 +27,14 @@ int inv_l2_norm(const void* x, int x_fp32, long long ldx, float* inv, long long 
 int attention(const void* q, long long ldq, long long q_batch_rows, const void* k, long long ldk, const void* v,
               long long ldv, long long kv_batch_rows, const float* key_mask, void* out, long long ldo, long long batch,
               long long num_heads, long long nq, long long nk, long long head_dim, float scale, unsigned drop_thr16,
-              unsigned long long drop_seed, unsigned drop_site, cudaStream_t stream);
+              unsigned long long drop_seed, unsigned drop_site, const unsigned long long* drop_seed_offset,
+              cudaStream_t stream);
 int dropout_add(const void* x, long long ldx, long long x_row_mod, const void* res, long long ldres, void* out,
                 long long ldo, long long rows, long long H, unsigned thr16, unsigned long long seed, unsigned site,
-                cudaStream_t stream);
+                const unsigned long long* seed_offset, cudaStream_t stream);
 int dropout_backward(const void* dy, long long lddy, void* dx, long long lddx, long long rows, long long H,
-                     unsigned thr16, unsigned long long seed, unsigned site, cudaStream_t stream);
+                     unsigned thr16, unsigned long long seed, unsigned site, const unsigned long long* seed_offset,
+                     cudaStream_t stream);
 
 int gemm_bf16_general(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, void* out,
                       long long ldo, int out_fp32, int accumulate, long long M, long long N, long long K, int ksplit,
@@ -47,7 +49,8 @@ int attention_backward(const void* q, long long ldq, long long q_batch_rows, con
                        long long ldv, long long kv_batch_rows, const float* key_mask, const void* dout, long long lddo,
                        void* dq, long long lddq, void* dk, long long lddk, void* dv, long long lddv, long long batch,
                        long long num_heads, long long nq, long long nk, long long head_dim, float scale,
-                       unsigned drop_thr16, unsigned long long drop_seed, unsigned drop_site, cudaStream_t stream);
+                       unsigned drop_thr16, unsigned long long drop_seed, unsigned drop_site,
+                       const unsigned long long* drop_seed_offset, cudaStream_t stream);
 
 std::atomic<long long> g_launch_count{0};
 }  // namespace unirec
@@ -85,26 +88,29 @@ int unirec_attention(const void* q, int64_t ldq, int64_t q_batch_rows, const voi
                      int64_t ldv, int64_t kv_batch_rows, const float* key_mask, void* out, int64_t ldo, int64_t batch,
                      int64_t num_heads, int64_t nq, int64_t nk, int64_t head_dim, float scale, void* stream) {
     COUNTED(attention(q, ldq, q_batch_rows, k, ldk, v, ldv, kv_batch_rows, key_mask, out, ldo, batch, num_heads, nq, nk,
-                      head_dim, scale, 0u, 0ull, 0u, static_cast<cudaStream_t>(stream)));
+                      head_dim, scale, 0u, 0ull, 0u, nullptr, static_cast<cudaStream_t>(stream)));
 }
 
 int unirec_attention_dropout(const void* q, int64_t ldq, int64_t q_batch_rows, const void* k, int64_t ldk, const void* v,
                              int64_t ldv, int64_t kv_batch_rows, const float* key_mask, void* out, int64_t ldo,
                              int64_t batch, int64_t num_heads, int64_t nq, int64_t nk, int64_t head_dim, float scale,
-                             uint32_t thr16, uint64_t seed, uint32_t site, void* stream) {
+                             uint32_t thr16, uint64_t seed, uint32_t site, const uint64_t* seed_offset, void* stream) {
     COUNTED(attention(q, ldq, q_batch_rows, k, ldk, v, ldv, kv_batch_rows, key_mask, out, ldo, batch, num_heads, nq, nk,
-                      head_dim, scale, thr16, seed, site, static_cast<cudaStream_t>(stream)));
+                      head_dim, scale, thr16, seed, site, reinterpret_cast<const unsigned long long*>(seed_offset),
+                      static_cast<cudaStream_t>(stream)));
 }
 
 int unirec_dropout_add(const void* x, int64_t ldx, int64_t x_row_mod, const void* residual, int64_t ldres, void* out,
-                       int64_t ldo, int64_t rows, int64_t H, uint32_t thr16, uint64_t seed, uint32_t site, void* stream) {
+                       int64_t ldo, int64_t rows, int64_t H, uint32_t thr16, uint64_t seed, uint32_t site,
+                       const uint64_t* seed_offset, void* stream) {
     COUNTED(dropout_add(x, ldx, x_row_mod, residual, ldres, out, ldo, rows, H, thr16, seed, site,
-                        static_cast<cudaStream_t>(stream)));
+                        reinterpret_cast<const unsigned long long*>(seed_offset), static_cast<cudaStream_t>(stream)));
 }
 
 int unirec_dropout_backward(const void* dy, int64_t lddy, void* dx, int64_t lddx, int64_t rows, int64_t H, uint32_t thr16,
-                            uint64_t seed, uint32_t site, void* stream) {
-    COUNTED(dropout_backward(dy, lddy, dx, lddx, rows, H, thr16, seed, site, static_cast<cudaStream_t>(stream)));
+                            uint64_t seed, uint32_t site, const uint64_t* seed_offset, void* stream) {
+    COUNTED(dropout_backward(dy, lddy, dx, lddx, rows, H, thr16, seed, site,
+                             reinterpret_cast<const unsigned long long*>(seed_offset), static_cast<cudaStream_t>(stream)));
 }
 
 int unirec_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream) {
@@ -168,7 +174,7 @@ int unirec_attention_backward(const void* q, int64_t ldq, int64_t q_batch_rows, 
                               void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t batch,
                               int64_t num_heads, int64_t nq, int64_t nk, int64_t head_dim, float scale, void* stream) {
     COUNTED(attention_backward(q, ldq, q_batch_rows, k, ldk, v, ldv, kv_batch_rows, key_mask, dout, lddo, dq, lddq, dk, lddk,
-                               dv, lddv, batch, num_heads, nq, nk, head_dim, scale, 0u, 0ull, 0u,
+                               dv, lddv, batch, num_heads, nq, nk, head_dim, scale, 0u, 0ull, 0u, nullptr,
                                static_cast<cudaStream_t>(stream)));
 }
 
@@ -177,10 +183,10 @@ int unirec_attention_dropout_backward(const void* q, int64_t ldq, int64_t q_batc
                                       const void* dout, int64_t lddo, void* dq, int64_t lddq, void* dk, int64_t lddk,
                                       void* dv, int64_t lddv, int64_t batch, int64_t num_heads, int64_t nq, int64_t nk,
                                       int64_t head_dim, float scale, uint32_t thr16, uint64_t seed, uint32_t site,
-                                      void* stream) {
+                                      const uint64_t* seed_offset, void* stream) {
     COUNTED(attention_backward(q, ldq, q_batch_rows, k, ldk, v, ldv, kv_batch_rows, key_mask, dout, lddo, dq, lddq, dk, lddk,
                                dv, lddv, batch, num_heads, nq, nk, head_dim, scale, thr16, seed, site,
-                               static_cast<cudaStream_t>(stream)));
+                               reinterpret_cast<const unsigned long long*>(seed_offset), static_cast<cudaStream_t>(stream)));
 }
 
 }  // extern "C"

@@ -11,8 +11,9 @@ template <bool BWD>
 __global__ void __launch_bounds__(256)
 dropout_rows_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int x_row_mod,
                     const __nv_bfloat16* __restrict__ res, long long ldres, __nv_bfloat16* __restrict__ out,
-                    long long ldo, long long rows, int H, uint32_t thr16, unsigned long long seed, uint32_t site) {
-    const DropoutParams d = make_dropout(thr16, seed, site);
+                    long long ldo, long long rows, int H, uint32_t thr16, unsigned long long seed, uint32_t site,
+                    const unsigned long long* __restrict__ seed_offset) {
+    const DropoutParams d = make_dropout(thr16, seed, site, seed_offset);
     const int groups = H >> 3;
     const long long total = rows * groups;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -41,7 +42,7 @@ dropout_rows_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int x_ro
 
 static int launch_rows(bool bwd, const void* x, long long ldx, long long x_row_mod, const void* res, long long ldres,
                        void* out, long long ldo, long long rows, long long H, unsigned thr16, unsigned long long seed,
-                       unsigned site, cudaStream_t stream, const char* what) {
+                       unsigned site, const unsigned long long* seed_offset, cudaStream_t stream, const char* what) {
     if (x == nullptr || out == nullptr || rows <= 0 || H <= 0 || H % 8 != 0 || ldx % 8 != 0 || ldo % 8 != 0 ||
         (res != nullptr && ldres % 8 != 0) || thr16 >= 65536u) {
         set_last_error("%s: null pointer, H %% 8 != 0, unaligned rows or p >= 1 (H=%lld)", what, H);
@@ -52,12 +53,12 @@ static int launch_rows(bool bwd, const void* x, long long ldx, long long x_row_m
     if (bwd)
         dropout_rows_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
             reinterpret_cast<const __nv_bfloat16*>(x), ldx, 0, nullptr, 0, reinterpret_cast<__nv_bfloat16*>(out), ldo, rows,
-            static_cast<int>(H), thr16, seed, site);
+            static_cast<int>(H), thr16, seed, site, seed_offset);
     else
         dropout_rows_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
             reinterpret_cast<const __nv_bfloat16*>(x), ldx, static_cast<int>(x_row_mod),
             reinterpret_cast<const __nv_bfloat16*>(res), ldres, reinterpret_cast<__nv_bfloat16*>(out), ldo, rows,
-            static_cast<int>(H), thr16, seed, site);
+            static_cast<int>(H), thr16, seed, site, seed_offset);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_last_error("%s launch: %s", what, cudaGetErrorString(e)); return UNIREC_ERR_CUDA; }
     return UNIREC_OK;
@@ -65,13 +66,16 @@ static int launch_rows(bool bwd, const void* x, long long ldx, long long x_row_m
 
 int dropout_add(const void* x, long long ldx, long long x_row_mod, const void* res, long long ldres, void* out,
                 long long ldo, long long rows, long long H, unsigned thr16, unsigned long long seed, unsigned site,
-                cudaStream_t stream) {
-    return launch_rows(false, x, ldx, x_row_mod, res, ldres, out, ldo, rows, H, thr16, seed, site, stream, "dropout_add");
+                const unsigned long long* seed_offset, cudaStream_t stream) {
+    return launch_rows(false, x, ldx, x_row_mod, res, ldres, out, ldo, rows, H, thr16, seed, site, seed_offset, stream,
+                       "dropout_add");
 }
 
 int dropout_backward(const void* dy, long long lddy, void* dx, long long lddx, long long rows, long long H,
-                     unsigned thr16, unsigned long long seed, unsigned site, cudaStream_t stream) {
-    return launch_rows(true, dy, lddy, 0, nullptr, 0, dx, lddx, rows, H, thr16, seed, site, stream, "dropout_backward");
+                     unsigned thr16, unsigned long long seed, unsigned site, const unsigned long long* seed_offset,
+                     cudaStream_t stream) {
+    return launch_rows(true, dy, lddy, 0, nullptr, 0, dx, lddx, rows, H, thr16, seed, site, seed_offset, stream,
+                       "dropout_backward");
 }
 
 }  // namespace unirec

@@ -20,13 +20,24 @@ struct DropoutParams {
     uint32_t site;
     unsigned long long seed;
     float scale;             // 65536 / (65536 - thr16)
+    // optional device-resident addend of the seed (NULL = none): lets a CUDA graph that was captured once with a fixed
+    // `seed` draw fresh masks on every replay - the graph itself increments *seed_offset (unirec_b200/training.py)
+    const unsigned long long* seed_offset;
 };
 
-UNIREC_DEVICE DropoutParams make_dropout(uint32_t thr16, unsigned long long seed, uint32_t site) {
-    DropoutParams d;
-    d.thr16 = thr16; d.site = site; d.seed = seed;
-    d.scale = 65536.0f / (65536.0f - static_cast<float>(thr16));
+// Effective parameters of a kernel: the seed with the device-resident offset folded in (one uniform load per thread).
+UNIREC_DEVICE DropoutParams dropout_resolve(DropoutParams d) {
+    if (d.seed_offset != nullptr) d.seed += __ldg(d.seed_offset);
+    d.seed_offset = nullptr;
     return d;
+}
+
+UNIREC_DEVICE DropoutParams make_dropout(uint32_t thr16, unsigned long long seed, uint32_t site,
+                                         const unsigned long long* seed_offset = nullptr) {
+    DropoutParams d;
+    d.thr16 = thr16; d.site = site; d.seed = seed; d.seed_offset = seed_offset;
+    d.scale = 65536.0f / (65536.0f - static_cast<float>(thr16));
+    return dropout_resolve(d);
 }
 
 UNIREC_DEVICE uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {

@@ -403,19 +403,20 @@ attention_bwd_kernel(const AttnBwdParams p) {
 #pragma unroll
     for (int j = 0; j < KT / 8; ++j) { mk[j][0] = mk[j][1] = mk[j][2] = mk[j][3] = 1.f; }
     if (p.drop.thr16 != 0) {
+        const DropoutParams drop = dropout_resolve(p.drop);
         const unsigned long long row0 = static_cast<unsigned long long>(blockIdx.x) * p.nq + warp * 16 + g4;
 #pragma unroll
         for (int kb = 0; kb < (KT + 31) / 32; ++kb) {
-            const uint32_t k0 = dropout_keep8(p.drop, row0, static_cast<uint32_t>(kb * 4 + t));
-            const uint32_t k1 = dropout_keep8(p.drop, row0 + 8, static_cast<uint32_t>(kb * 4 + t));
+            const uint32_t k0 = dropout_keep8(drop, row0, static_cast<uint32_t>(kb * 4 + t));
+            const uint32_t k1 = dropout_keep8(drop, row0 + 8, static_cast<uint32_t>(kb * 4 + t));
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
                 const int j = kb * 4 + nt;
                 if (j < KT / 8) {
-                    mk[j][0] = ((k0 >> (2 * nt)) & 1u) ? p.drop.scale : 0.f;
-                    mk[j][1] = ((k0 >> (2 * nt + 1)) & 1u) ? p.drop.scale : 0.f;
-                    mk[j][2] = ((k1 >> (2 * nt)) & 1u) ? p.drop.scale : 0.f;
-                    mk[j][3] = ((k1 >> (2 * nt + 1)) & 1u) ? p.drop.scale : 0.f;
+                    mk[j][0] = ((k0 >> (2 * nt)) & 1u) ? drop.scale : 0.f;
+                    mk[j][1] = ((k0 >> (2 * nt + 1)) & 1u) ? drop.scale : 0.f;
+                    mk[j][2] = ((k1 >> (2 * nt)) & 1u) ? drop.scale : 0.f;
+                    mk[j][3] = ((k1 >> (2 * nt + 1)) & 1u) ? drop.scale : 0.f;
                 }
             }
         }
@@ -525,7 +526,8 @@ int attention_backward(const void* q, long long ldq, long long q_batch_rows, con
                        long long ldv, long long kv_batch_rows, const float* key_mask, const void* dout, long long lddo,
                        void* dq, long long lddq, void* dk, long long lddk, void* dv, long long lddv, long long batch,
                        long long num_heads, long long nq, long long nk, long long head_dim, float scale,
-                       unsigned drop_thr16, unsigned long long drop_seed, unsigned drop_site, cudaStream_t stream) {
+                       unsigned drop_thr16, unsigned long long drop_seed, unsigned drop_site,
+                       const unsigned long long* drop_seed_offset, cudaStream_t stream) {
     if (q == nullptr || k == nullptr || v == nullptr || dout == nullptr || dq == nullptr || dk == nullptr || dv == nullptr ||
         batch <= 0 || num_heads <= 0 || nq <= 0 || nk <= 0) {
         set_last_error("attention_backward: null pointer or empty shape");
@@ -550,7 +552,7 @@ int attention_backward(const void* q, long long ldq, long long q_batch_rows, con
     p.num_heads = (int)num_heads; p.nq = (int)nq; p.nk = (int)nk;
     p.scale = scale;
     if (drop_thr16 >= 65536u) { set_last_error("attention_backward: dropout probability must be < 1"); return UNIREC_ERR_BAD_ARG; }
-    p.drop.thr16 = drop_thr16; p.drop.seed = drop_seed; p.drop.site = drop_site;
+    p.drop.thr16 = drop_thr16; p.drop.seed = drop_seed; p.drop.site = drop_site; p.drop.seed_offset = drop_seed_offset;
     p.drop.scale = 65536.0f / (65536.0f - static_cast<float>(drop_thr16));
     const int nwarps = (int)((nq + 15) / 16);
     const int threads = nwarps * 32;

@@ -279,6 +279,9 @@ class QFormerForItemRepresentation(nn.Module):
         # (reproducible under torch.manual_seed); an int = use it for the next call, then count up
         self.dropout_seed: Optional[int] = None
         self.last_dropout = None                   # (thr16, seed) of the most recent train-mode forward
+        # optional int64 CUDA tensor with one element, added to the seed by the kernels at run time: a training step
+        # captured in a CUDA graph increments it inside the graph (training.TrainStepGraph)
+        self.dropout_seed_offset: Optional[torch.Tensor] = None
 
     def _next_dropout(self):
         p = float(self.config.hidden_dropout_prob)
@@ -293,6 +296,8 @@ class QFormerForItemRepresentation(nn.Module):
             seed = int(self.dropout_seed)
             self.dropout_seed = seed + 1
         self.last_dropout = (ops.dropout_threshold(p), seed)
+        if self.dropout_seed_offset is not None:
+            return self.last_dropout + (self.dropout_seed_offset,)
         return self.last_dropout
 
     def _heads(self):
@@ -321,7 +326,7 @@ class QFormerForItemRepresentation(nn.Module):
     def _forward_train(self, field_embeddings, attention_mask, drop=None):
         """Differentiable forward (models/qformer_utils.py:37-60 under autograd): backbone = BackboneTrainFn,
         heads = LinearFn (tcgen05 fwd / dgrad / wgrad), the 32 -> num_fields projection in torch (0.9 GFLOP/1024 items).
-        drop = (thr16, seed) or None."""
+        drop = (thr16, seed[, seed_offset]) or None."""
         from .training import BackboneTrainFn, LinearFn
         bb = self.qformer
         qo = BackboneTrainFn.apply(bb, drop, field_embeddings, attention_mask, self.query_embeddings, *bb._live_params())

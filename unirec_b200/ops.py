@@ -155,7 +155,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, batch: int, 
               out: Optional[torch.Tensor] = None, dropout: Optional[Tuple[int, int, int]] = None) -> torch.Tensor:
     """Multi-head attention with head_dim 64.  q/k/v are 2-D row views (possibly column slices of a fused
     projection buffer): q [batch*nq (or nq if q_broadcast), heads*64], k/v [batch*nk, heads*64].
-    dropout = (thr16, seed, site): train-mode dropout of the probabilities (see dropout_threshold)."""
+    dropout = (thr16, seed, site[, seed_offset]): train-mode dropout of the probabilities (see dropout_threshold,
+    _drop_args)."""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _req(t, torch.bfloat16, f"attention.{n}")
         if t.dim() != 2:
@@ -172,16 +173,30 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, batch: int, 
     # algorithmic bytes: Q, K, V read once + context written once (bf16)
     with _Timed("attention", 2.0 * hd * batch * ((1 if q_broadcast else 1) * nq + 2 * nk + nq), f"{batch}x{nq}x{nk}"):
         if dropout is not None and dropout[0] > 0:
+            thr16, seed, site, off = _drop_args(dropout)
             rc = _lib.load().unirec_attention_dropout(q.data_ptr(), q.stride(0), 0 if q_broadcast else nq, k.data_ptr(),
                                                       k.stride(0), v.data_ptr(), v.stride(0), nk, _ptr(key_mask),
                                                       out.data_ptr(), out.stride(0), batch, num_heads, nq, nk, 64, 0.125,
-                                                      dropout[0], dropout[1], dropout[2], _stream())
+                                                      thr16, seed, site, off, _stream())
         else:
             rc = _lib.load().unirec_attention(q.data_ptr(), q.stride(0), 0 if q_broadcast else nq, k.data_ptr(),
                                               k.stride(0), v.data_ptr(), v.stride(0), nk, _ptr(key_mask), out.data_ptr(),
                                               out.stride(0), batch, num_heads, nq, nk, 64, 0.125, _stream())
     _lib.check(rc, "unirec_attention")
     return out
+
+
+def _drop_args(dropout):
+    """(thr16, seed, site[, seed_offset]) -> (thr16, seed, site, device pointer of the uint64 seed offset or None).
+    seed_offset: int64 CUDA tensor with one element, added to `seed` by the kernels when they run (CUDA-graph replays)."""
+    if dropout is None:
+        return 0, 0, 0, None
+    off = dropout[3] if len(dropout) > 3 else None
+    if off is not None:
+        _req(off, torch.int64, "dropout.seed_offset")
+        if off.numel() != 1:
+            raise RuntimeError("dropout.seed_offset must hold one int64")
+    return dropout[0], dropout[1], dropout[2], _ptr(off)
 
 
 def dropout_threshold(p: float) -> int:
@@ -202,8 +217,9 @@ def dropout_add(x: torch.Tensor, residual: Optional[torch.Tensor], dropout: Tupl
         _req(residual, torch.bfloat16, "dropout_add.residual")
         _, _, ldres = _rows2d(residual, "dropout_add.residual")
     out = torch.empty(rows, H, device=x.device, dtype=torch.bfloat16)
+    thr16, seed, site, off = _drop_args(dropout)
     rc = _lib.load().unirec_dropout_add(x.data_ptr(), ldx, x_row_mod, _ptr(residual), ldres, out.data_ptr(), H, rows, H,
-                                        dropout[0], dropout[1], dropout[2], _stream())
+                                        thr16, seed, site, off, _stream())
     _lib.check(rc, "unirec_dropout_add")
     return out
 
@@ -213,8 +229,9 @@ def dropout_backward(dy: torch.Tensor, dropout: Tuple[int, int, int]) -> torch.T
     _req(dy, torch.bfloat16, "dropout_backward.dy")
     rows, H, lddy = _rows2d(dy, "dropout_backward.dy")
     dx = torch.empty(rows, H, device=dy.device, dtype=torch.bfloat16)
-    rc = _lib.load().unirec_dropout_backward(dy.data_ptr(), lddy, dx.data_ptr(), H, rows, H, dropout[0], dropout[1],
-                                             dropout[2], _stream())
+    thr16, seed, site, off = _drop_args(dropout)
+    rc = _lib.load().unirec_dropout_backward(dy.data_ptr(), lddy, dx.data_ptr(), H, rows, H, thr16, seed, site, off,
+                                             _stream())
     _lib.check(rc, "unirec_dropout_backward")
     return dx
 
@@ -459,9 +476,9 @@ def attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, dout: 
             raise RuntimeError("attention_backward: tensors must be 2-D row views")
     if key_mask is not None:
         _req(key_mask, torch.float32, "attention_backward.key_mask")
-    thr16, seed, site = dropout if dropout is not None else (0, 0, 0)
+    thr16, seed, site, off = _drop_args(dropout)
     rc = _lib.load().unirec_attention_dropout_backward(
         q.data_ptr(), q.stride(0), nq, k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), nk, _ptr(key_mask),
         dout.data_ptr(), dout.stride(0), dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(),
-        dv.stride(0), batch, num_heads, nq, nk, 64, 0.125, thr16, seed, site, _stream())
+        dv.stride(0), batch, num_heads, nq, nk, 64, 0.125, thr16, seed, site, off, _stream())
     _lib.check(rc, "unirec_attention_dropout_backward")

@@ -61,11 +61,12 @@ class BackboneTrainFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, backbone, drop, enc, mask, query_embeddings, *params):
-        """drop = None (dropout off) or (thr16, seed)."""
+        """drop = None (dropout off) or (thr16, seed[, seed_offset]); seed_offset = int64 CUDA tensor with one element
+        that the kernels add to the seed when they run (CUDA-graph replays, see TrainStepGraph)."""
         cfg = backbone.config
 
         def site(layer, kind):
-            return None if drop is None else (drop[0], drop[1], 1 + 8 * layer + kind)
+            return None if drop is None else (drop[0], drop[1], 1 + 8 * layer + kind) + tuple(drop[2:])
 
         def dense_residual(x, w, b, res, st):
             # dropout(dense(x)) + res: fused into the GEMM epilogue when there is no dropout
@@ -85,7 +86,7 @@ class BackboneTrainFn(torch.autograd.Function):
             h = ops.layernorm(q0, pk["emb_g"], pk["emb_b"], cfg.layer_norm_eps, rows=B * Q, in_row_mod=Q)
         else:
             h = ops.dropout_add(ops.layernorm(q0, pk["emb_g"], pk["emb_b"], cfg.layer_norm_eps), None,
-                                (drop[0], drop[1], BackboneTrainFn.SITE_EMBEDDINGS), rows=B * Q, x_row_mod=Q)
+                                (drop[0], drop[1], BackboneTrainFn.SITE_EMBEDDINGS) + tuple(drop[2:]), rows=B * Q, x_row_mod=Q)
         K = BackboneTrainFn
         tape = []
         for li, L in enumerate(pk["layers"]):
@@ -132,7 +133,7 @@ class BackboneTrainFn(torch.autograd.Function):
         K = BackboneTrainFn
 
         def site(layer, kind):
-            return None if drop is None else (drop[0], drop[1], 1 + 8 * layer + kind)
+            return None if drop is None else (drop[0], drop[1], 1 + 8 * layer + kind) + tuple(drop[2:])
 
         def dense_grad(dpre, st):
             # gradient of the dense output behind dropout(dense) + residual
@@ -219,7 +220,7 @@ class BackboneTrainFn(torch.autograd.Function):
         # ---- query-token LayerNorm (batch-invariant): sum over the batch, then a [Q, H] LayerNorm backward (torch)
         dh0 = dy.float() + dy2.float()
         if drop is not None:
-            dh0 = ops.dropout_backward(dh0.to(torch.bfloat16), (drop[0], drop[1], K.SITE_EMBEDDINGS)).float()
+            dh0 = ops.dropout_backward(dh0.to(torch.bfloat16), (drop[0], drop[1], K.SITE_EMBEDDINGS) + tuple(drop[2:])).float()
         dh0 = dh0.view(B, Q, H).sum(dim=0)
         with torch.enable_grad():
             q0 = ctx.q0.clone().requires_grad_(True)
@@ -317,3 +318,124 @@ class GradientAllReducer:
         grads = [p.grad for p in params if p.grad is not None]
         self.layer_ready(-2, grads)
         self.finish()
+
+    def reduce_tensors(self, tensors: List[torch.Tensor]):
+        """Average `tensors` over the ranks in place with ONE all-reduce of one flat bucket (pack, reduce, unpack with a
+        single multi-tensor copy).  Used behind a CUDA-graph step, whose gradients all exist when the graph has run."""
+        tensors = [t for t in tensors if t is not None]
+        if self.world == 1 or not tensors:
+            return
+        flat = torch.cat([t.reshape(-1).to(self.bucket_dtype) for t in tensors])
+        self.dist.all_reduce(flat, group=self.group)
+        self.bytes_reduced += flat.numel() * flat.element_size()
+        flat.div_(self.world)
+        views, off = [], 0
+        for t in tensors:
+            n = t.numel()
+            views.append(flat[off:off + n].view_as(t))
+            off += n
+        torch._foreach_copy_(tensors, views)
+
+
+class TrainStepGraph:
+    """The reference's training step (training/item_qformer_training.py:117-131: forward, QFormerLoss, backward)
+    captured ONCE into a CUDA graph and replayed per step.
+
+    Why: one step is ~435 kernel launches and the Python host needs 35-38 ms to enqueue them - as long as the GPU needs
+    for a 1024-item batch, and several times longer than the GPU needs for the 128-item per-GPU batch of an 8-GPU
+    data-parallel run.  A replay is one launch.  What makes the step capturable:
+      * every kernel of the C ABI is enqueued on torch's current stream and allocates nothing; the tensor maps are
+        encoded on the host at capture time from addresses that stay valid (torch's graph-private memory pool);
+      * dropout masks are a pure function of (seed, site, element); the seed frozen into the captured launch parameters
+        is offset by a DEVICE-resident counter that the graph itself advances (`seed_offset`, include/unirec_b200.h),
+        so every replay draws fresh masks and the backward pass of the same replay sees the same ones;
+      * the bf16 weight packing of the backbone and the heads is part of the graph, so a replay always starts from
+        the current fp32 master weights (the optimizer updates them in place between replays).
+    Gradients land in static tensors (`.grads`); after `step()` they are attached to the parameters' `.grad`, so the
+    caller averages them over the ranks (`GradientAllReducer.reduce_tensors(graph.grad_tensors())`) and runs the
+    optimizer as usual.  Do not call `zero_grad(set_to_none=False)` between steps - a replay overwrites the gradients.
+    """
+
+    SEED_STRIDE = 1024     # > the number of forward passes in one step: replays never reuse an effective seed
+
+    def __init__(self, model, field_embeddings: torch.Tensor, attention_mask: torch.Tensor, *,
+                 faithful: bool = False, loss_kwargs: Optional[dict] = None, warmup: int = 3):
+        """field_embeddings [B, F, E] / attention_mask [B, F]: example inputs (shape, dtype and device of every later
+        step).  faithful: also run the two no-grad train-mode forwards that produce the positive / negative
+        representations (item_qformer_training.py:122-125) inside the graph; otherwise they are inputs of `step`."""
+        if not field_embeddings.is_cuda:
+            raise RuntimeError("TrainStepGraph: inputs must be CUDA tensors (unirec_b200 has no CPU path)")
+        dev = field_embeddings.device
+        self.model, self.faithful = model, faithful
+        self.loss_kwargs = dict(loss_kwargs or {})
+        B, E = field_embeddings.shape[0], model.item_representation_head.out_features
+        self.fields = field_embeddings.detach().clone()
+        self.mask = attention_mask.detach().clone()
+        if faithful:
+            self.fields_pos = torch.zeros_like(self.fields)
+            self.fields_neg = torch.zeros_like(self.fields)
+        else:
+            self.pos = torch.zeros(B, E, device=dev)
+            self.neg = torch.zeros(B, E, device=dev)
+        self.seed_offset = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        saved_offset = model.dropout_seed_offset
+        saved_hooks = (getattr(model.qformer, "grad_ready_hook", None), getattr(model.qformer, "grad_finish_hook", None))
+        model.dropout_seed_offset = self.seed_offset
+        model.qformer.grad_ready_hook = model.qformer.grad_finish_hook = None     # no collectives inside the graph
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(max(warmup, 1)):       # lazy one-time work (function attributes, caches) happens here
+                    self._clear_grads()
+                    self._body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            self._clear_grads()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.seed_offset.add_(self.SEED_STRIDE)
+                self.loss = self._body()
+        finally:
+            model.dropout_seed_offset = saved_offset
+            model.qformer.grad_ready_hook, model.qformer.grad_finish_hook = saved_hooks
+        self.grads = [(p, p.grad) for p in self.params if p.grad is not None]
+        self.replays = 0
+
+    def _clear_grads(self):
+        for p in self.params:
+            p.grad = None
+
+    def _body(self):
+        model = self.model
+        out = model(self.fields, self.mask)
+        if self.faithful:
+            with torch.no_grad():
+                p_rep = model(self.fields_pos, self.mask)["item_representation"]
+                n_rep = model(self.fields_neg, self.mask)["item_representation"]
+        else:
+            p_rep, n_rep = self.pos, self.neg
+        loss = qformer_loss(out, self.fields, self.mask, p_rep, n_rep, **self.loss_kwargs)
+        loss.backward()
+        return loss.detach()
+
+    def grad_tensors(self) -> List[torch.Tensor]:
+        return [g for _, g in self.grads]
+
+    def step(self, field_embeddings: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+             pos: Optional[torch.Tensor] = None, neg: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Copies the batch into the graph's static inputs (device-to-device, on the current stream), replays the graph
+        and returns the loss (a static tensor: read it before the next step).  `pos` / `neg` are the positive / negative
+        REPRESENTATIONS [B, E] (faithful=False) or their FIELD EMBEDDINGS [B, F, E] (faithful=True)."""
+        self.fields.copy_(field_embeddings, non_blocking=True)
+        if attention_mask is not None:
+            self.mask.copy_(attention_mask, non_blocking=True)
+        if pos is not None:
+            (self.fields_pos if self.faithful else self.pos).copy_(pos, non_blocking=True)
+        if neg is not None:
+            (self.fields_neg if self.faithful else self.neg).copy_(neg, non_blocking=True)
+        self.graph.replay()
+        self.replays += 1
+        for p, g in self.grads:
+            p.grad = g
+        return self.loss
