@@ -198,6 +198,43 @@ int unirec_dropout_add(const void* x, int64_t ldx, int64_t x_row_mod, const void
 int unirec_dropout_backward(const void* dy, int64_t lddy, void* dx, int64_t lddx, int64_t rows, int64_t H,
                             uint32_t thr16, uint64_t seed, uint32_t site, const uint64_t* seed_offset, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Per-user candidate-LIST scoring - the ranking of the reference's joint trainer:
+ * InfoNCELoss.forward (training/train_item_individual_token_joint.py:331-352) and
+ * MRREvaluator._compute_batch_mrr (:405-418).  Every user has its own list: one positive row and up to C negatives,
+ * either PADDED (cands = [B, C, D] rows b * C + c, mask [B, C] bytes, 0 = padding; the training collate :300-323) or
+ * RAGGED (cands = all lists concatenated, offsets [B + 1] row offsets, C = longest list; the validation collate
+ * :381-390).  users / pos / cands share one dtype (fp32 = 1: float, else bf16), rows 16-byte aligned, D % 8 == 0.
+ * List entry 0 is the positive, entry 1 + c the c-th negative.  F.normalize semantics: x / max(||x||, eps).
+ * ------------------------------------------------------------------------------------------- */
+
+/* sims[b, e] = cosine(user b, entry e), -inf for padding; inv_norm[b, e] = 1 / max(||entry||, eps) (may be NULL);
+ * both fp32 [B, 1 + C]. */
+int unirec_list_scores(const void* users, int64_t ldu, const void* pos, int64_t ldp, const void* cands, int64_t ldc,
+                       int fp32, const uint8_t* mask, const int64_t* offsets, int64_t B, int64_t C, int64_t D, float eps,
+                       float* sims, float* inv_norm, void* stream);
+
+/* loss[b] = -sims[b,0] / T + logsumexp_e(sims[b,e] / T) over the valid entries (:347-350);
+ * rank[b] = 1 + number of valid negatives scoring above the positive (the positive's 1-based position in the
+ * descending order of :413-415; MRR = mean(1 / rank)).  Either output may be NULL. */
+int unirec_infonce_rank(const float* sims, int64_t B, int64_t C, float temperature, float* loss, int32_t* rank,
+                        void* stream);
+
+/* Gradient of sum_b dloss[b] * loss[b]: d_user fp32 [B, D] is ACCUMULATED (zero it first); d_list (may be NULL) fp32
+ * [B, 1 + C, D] receives the gradient of every list entry (zero rows for padding). */
+int unirec_list_scores_backward(const void* users, int64_t ldu, const void* pos, int64_t ldp, const void* cands,
+                                int64_t ldc, int fp32, const uint8_t* mask, const int64_t* offsets, int64_t B, int64_t C,
+                                int64_t D, float eps, const float* sims, const float* inv_norm, const float* dloss,
+                                float temperature, float* d_user, float* d_list, void* stream);
+
+/* Token injection of the joint model (:160-171): text_embeds[b, s, :] = tokens[b, slot, :] wherever
+ * input_ids[b, s] == token_ids[slot]; tokens [B, num_slots, Hd] (num_slots = history items x query tokens per item),
+ * text_embeds rows [B * S] with row stride ld_text; fp32 or bf16 on either side (converted like the reference's
+ * indexed assignment). */
+int unirec_inject_tokens(const int64_t* input_ids, int64_t B, int64_t S, const int64_t* token_ids, int64_t num_slots,
+                         const void* tokens, int tokens_fp32, void* text_embeds, int text_fp32, int64_t ld_text,
+                         int64_t Hd, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -155,8 +155,41 @@ def train_cases():
         print(f"gemm {name:44s} {ms:8.3f} ms  {fl / ms / 1e9:8.1f} TFLOP/s", flush=True)
 
 
+def joint_cases():
+    """Per-user candidate-list scoring (csrc/list_scoring.cu): one streaming pass over [B, 1 + C, D] rows."""
+    from unirec_b200.joint import InfoNCELoss
+    for dt, name in ((torch.float32, "fp32"), (bf, "bf16")):
+        B, C, D = 8192, 100, 1024          # 3.4 GB fp32 / 1.7 GB bf16 of candidate rows: larger than L2
+        u = torch.randn(B, D, device=dev).to(dt)
+        p = torch.randn(B, D, device=dev).to(dt)
+        n = torch.randn(B, C, D, device=dev).to(dt)
+        m = torch.rand(B, C, device=dev) < 0.9
+        es = u.element_size()
+        ms = timeit(lambda: ops.list_scores(u, p, n, mask=m))
+        report(f"list_scores {name} (B=8192, 1+100 x 1024, 90% valid)", ms, (B * 2 + int(m.sum())) * D * es)
+        ms = timeit(lambda: ops.list_scores(u, p, n))
+        report(f"list_scores {name} (B=8192, 1+100 x 1024, no mask)", ms, B * (C + 2) * D * es)
+        sims, inv = ops.list_scores(u, p, n)
+        ms = timeit(lambda: ops.infonce_rank(sims, 0.07))
+        report(f"infonce_rank (B=8192, 101 sims)", ms, B * (C + 1) * 4)
+        dl = torch.full((B,), 1.0 / B, device=dev)
+        ms = timeit(lambda: ops.list_scores_backward(u, p, n, sims, inv, dl, 0.07))
+        report(f"list_scores_backward {name} (d_user only)", ms, B * (C + 2) * D * es + B * D * 4)
+        crit = InfoNCELoss(0.07)
+        ms = timeit(lambda: crit(u, p, n, m))
+        report(f"InfoNCELoss.forward {name} (module call, masked)", ms, (B * 2 + int(m.sum())) * D * es)
+    B, S, nh, Q, Hd = 64, 2048, 10, 32, 1024
+    ids = torch.randint(0, 150_000, (B, S), device=dev)
+    tok_ids = 151_700 + torch.arange(nh * Q, device=dev)
+    ids[:, 100:100 + nh * Q] = tok_ids
+    text = torch.randn(B, S, Hd, device=dev).to(bf)
+    toks = torch.randn(B, nh * Q, Hd, device=dev)
+    ms = timeit(lambda: ops.inject_tokens(text, ids, tok_ids, toks))
+    report("inject_tokens (B=64, S=2048, 320 placeholders, fp32->bf16)", ms, B * S * 8 + B * nh * Q * Hd * 6)
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["attention", "rowwise", "scoring"]
+    what = sys.argv[1:] or ["attention", "rowwise", "scoring", "joint"]
     print(torch.cuda.get_device_name(0), "HBM peak", HBM, "GB/s")
     if "attention" in what:
         attention_cases()
@@ -164,5 +197,7 @@ if __name__ == "__main__":
         rowwise_cases()
     if "scoring" in what:
         scoring_cases()
+    if "joint" in what:
+        joint_cases()
     if "train" in what:
         train_cases()

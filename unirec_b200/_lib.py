@@ -62,6 +62,14 @@ _SIGNATURES = {
                                    c_uint32, c_uint64, c_uint32, c_void_p, c_void_p]),
     "unirec_dropout_backward": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_uint32, c_uint64,
                                         c_uint32, c_void_p, c_void_p]),
+    "unirec_list_scores": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p,
+                                   c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p]),
+    "unirec_infonce_rank": (c_int, [c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p]),
+    "unirec_list_scores_backward": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p,
+                                            c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p,
+                                            c_float, c_void_p, c_void_p, c_void_p]),
+    "unirec_inject_tokens": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int,
+                                     c_int64, c_int64, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

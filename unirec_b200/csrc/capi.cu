@@ -52,6 +52,19 @@ int attention_backward(const void* q, long long ldq, long long q_batch_rows, con
                        unsigned drop_thr16, unsigned long long drop_seed, unsigned drop_site,
                        const unsigned long long* drop_seed_offset, cudaStream_t stream);
 
+int list_scores(const void* users, long long ldu, const void* pos, long long ldp, const void* cands, long long ldc,
+                int fp32, const unsigned char* mask, const long long* offsets, long long B, long long C, long long D,
+                float eps, float* sims, float* inv_norm, cudaStream_t stream);
+int infonce_rank(const float* sims, long long B, long long C, float temperature, float* loss, int* rank,
+                 cudaStream_t stream);
+int list_scores_backward(const void* users, long long ldu, const void* pos, long long ldp, const void* cands,
+                         long long ldc, int fp32, const unsigned char* mask, const long long* offsets, long long B,
+                         long long C, long long D, float eps, const float* sims, const float* inv_norm,
+                         const float* dloss, float temperature, float* d_user, float* d_list, cudaStream_t stream);
+int inject_tokens(const long long* input_ids, long long B, long long S, const long long* token_ids, long long num_slots,
+                  const void* tokens, int tokens_fp32, void* text_embeds, int text_fp32, long long ld_text, long long Hd,
+                  cudaStream_t stream);
+
 std::atomic<long long> g_launch_count{0};
 }  // namespace unirec
 
@@ -187,6 +200,35 @@ int unirec_attention_dropout_backward(const void* q, int64_t ldq, int64_t q_batc
     COUNTED(attention_backward(q, ldq, q_batch_rows, k, ldk, v, ldv, kv_batch_rows, key_mask, dout, lddo, dq, lddq, dk, lddk,
                                dv, lddv, batch, num_heads, nq, nk, head_dim, scale, thr16, seed, site,
                                reinterpret_cast<const unsigned long long*>(seed_offset), static_cast<cudaStream_t>(stream)));
+}
+
+int unirec_list_scores(const void* users, int64_t ldu, const void* pos, int64_t ldp, const void* cands, int64_t ldc,
+                       int fp32, const uint8_t* mask, const int64_t* offsets, int64_t B, int64_t C, int64_t D, float eps,
+                       float* sims, float* inv_norm, void* stream) {
+    COUNTED(list_scores(users, ldu, pos, ldp, cands, ldc, fp32, mask, reinterpret_cast<const long long*>(offsets), B, C, D,
+                        eps, sims, inv_norm, static_cast<cudaStream_t>(stream)));
+}
+
+int unirec_infonce_rank(const float* sims, int64_t B, int64_t C, float temperature, float* loss, int32_t* rank,
+                        void* stream) {
+    COUNTED(infonce_rank(sims, B, C, temperature, loss, rank, static_cast<cudaStream_t>(stream)));
+}
+
+int unirec_list_scores_backward(const void* users, int64_t ldu, const void* pos, int64_t ldp, const void* cands,
+                                int64_t ldc, int fp32, const uint8_t* mask, const int64_t* offsets, int64_t B, int64_t C,
+                                int64_t D, float eps, const float* sims, const float* inv_norm, const float* dloss,
+                                float temperature, float* d_user, float* d_list, void* stream) {
+    COUNTED(list_scores_backward(users, ldu, pos, ldp, cands, ldc, fp32, mask, reinterpret_cast<const long long*>(offsets),
+                                 B, C, D, eps, sims, inv_norm, dloss, temperature, d_user, d_list,
+                                 static_cast<cudaStream_t>(stream)));
+}
+
+int unirec_inject_tokens(const int64_t* input_ids, int64_t B, int64_t S, const int64_t* token_ids, int64_t num_slots,
+                         const void* tokens, int tokens_fp32, void* text_embeds, int text_fp32, int64_t ld_text,
+                         int64_t Hd, void* stream) {
+    COUNTED(inject_tokens(reinterpret_cast<const long long*>(input_ids), B, S, reinterpret_cast<const long long*>(token_ids),
+                          num_slots, tokens, tokens_fp32, text_embeds, text_fp32, ld_text, Hd,
+                          static_cast<cudaStream_t>(stream)));
 }
 
 }  // extern "C"

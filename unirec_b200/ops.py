@@ -482,3 +482,105 @@ def attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, dout: 
         dout.data_ptr(), dout.stride(0), dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(),
         dv.stride(0), batch, num_heads, nq, nk, 64, 0.125, thr16, seed, site, off, _stream())
     _lib.check(rc, "unirec_attention_dropout_backward")
+
+
+# ------------------------------------------------------------------------------------------------
+# Per-user candidate-list scoring and token injection of the joint trainer (C ABI: "candidate-LIST scoring" block)
+# ------------------------------------------------------------------------------------------------
+def _list_operands(users, pos, cands, mask, offsets, max_list):
+    if users.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError("list_scores: embeddings must be fp32 or bf16")
+    for t, n in ((users, "users"), (pos, "pos"), (cands, "cands")):
+        _req(t, users.dtype, f"list_scores.{n}")
+    if users.dim() != 2 or pos.shape != users.shape:
+        raise RuntimeError("list_scores: users and pos must both be [B, D]")
+    B, D = users.shape
+    if offsets is not None:
+        if mask is not None:
+            raise RuntimeError("list_scores: pass mask (padded lists) or offsets (ragged lists), not both")
+        _req(offsets, torch.int64, "list_scores.offsets")
+        if cands.dim() != 2 or cands.shape[1] != D or offsets.numel() != B + 1 or max_list is None:
+            raise RuntimeError("list_scores: ragged lists need cands [total, D], offsets [B + 1] and max_list")
+        C, ldc = int(max_list), cands.stride(0)
+        offsets = offsets.contiguous()
+    else:
+        if cands.dim() != 3 or cands.shape[0] != B or cands.shape[2] != D or not cands.is_contiguous():
+            raise RuntimeError("list_scores: padded lists need contiguous cands [B, C, D]")
+        C, ldc = cands.shape[1], D
+        if mask is not None:
+            _req(mask, torch.bool, "list_scores.mask")
+            if tuple(mask.shape) != (B, C):
+                raise RuntimeError("list_scores: mask must be [B, C]")
+            mask = mask.contiguous()
+    return B, C, D, ldc, mask, offsets
+
+
+def list_scores(users: torch.Tensor, pos: torch.Tensor, cands: torch.Tensor, *, mask: Optional[torch.Tensor] = None,
+                offsets: Optional[torch.Tensor] = None, max_list: Optional[int] = None, eps: float = 1e-12
+                ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Cosine similarity of every user with its own list: entry 0 = pos[b], entry 1 + c = its c-th negative.
+    Padded lists: cands [B, C, D] (+ bool mask [B, C], False = padding); ragged lists: cands [total, D], offsets int64
+    [B + 1], max_list = longest list.  Returns (sims, inv_norm), both fp32 [B, 1 + C]; padding scores -inf."""
+    B, C, D, ldc, mask, offsets = _list_operands(users, pos, cands, mask, offsets, max_list)
+    sims = torch.empty(B, C + 1, device=users.device, dtype=torch.float32)
+    inv = torch.empty(B, C + 1, device=users.device, dtype=torch.float32)
+    es = users.element_size()
+    with _Timed("list_scores", float(B) * (C + 2) * D * es):
+        rc = _lib.load().unirec_list_scores(users.data_ptr(), users.stride(0), pos.data_ptr(), pos.stride(0),
+                                            cands.data_ptr(), ldc, 1 if users.dtype == torch.float32 else 0, _ptr(mask),
+                                            _ptr(offsets), B, C, D, float(eps), sims.data_ptr(), inv.data_ptr(), _stream())
+    _lib.check(rc, "unirec_list_scores")
+    return sims, inv
+
+
+def infonce_rank(sims: torch.Tensor, temperature: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """sims fp32 [B, 1 + C] (column 0 = positive, -inf = padding) -> (InfoNCE loss per user fp32 [B], 1-based rank of
+    the positive int32 [B])."""
+    _req(sims, torch.float32, "infonce_rank.sims")
+    if sims.dim() != 2 or not sims.is_contiguous():
+        raise RuntimeError("infonce_rank: sims must be contiguous [B, 1 + C]")
+    B, C1 = sims.shape
+    loss = torch.empty(B, device=sims.device, dtype=torch.float32)
+    rank = torch.empty(B, device=sims.device, dtype=torch.int32)
+    rc = _lib.load().unirec_infonce_rank(sims.data_ptr(), B, C1 - 1, float(temperature), loss.data_ptr(), rank.data_ptr(),
+                                         _stream())
+    _lib.check(rc, "unirec_infonce_rank")
+    return loss, rank
+
+
+def list_scores_backward(users, pos, cands, sims, inv_norm, dloss, temperature: float, *, mask=None, offsets=None,
+                         max_list=None, eps: float = 1e-12, want_list_grad: bool = False):
+    """Gradient of sum_b dloss[b] * infonce_loss[b]: returns (d_user fp32 [B, D], d_list fp32 [B, 1 + C, D] or None)."""
+    B, C, D, ldc, mask, offsets = _list_operands(users, pos, cands, mask, offsets, max_list)
+    _req(dloss, torch.float32, "list_scores_backward.dloss")
+    d_user = torch.zeros(B, D, device=users.device, dtype=torch.float32)
+    d_list = torch.empty(B, C + 1, D, device=users.device, dtype=torch.float32) if want_list_grad else None
+    rc = _lib.load().unirec_list_scores_backward(
+        users.data_ptr(), users.stride(0), pos.data_ptr(), pos.stride(0), cands.data_ptr(), ldc,
+        1 if users.dtype == torch.float32 else 0, _ptr(mask), _ptr(offsets), B, C, D, float(eps), sims.data_ptr(),
+        inv_norm.data_ptr(), dloss.contiguous().data_ptr(), float(temperature), d_user.data_ptr(), _ptr(d_list), _stream())
+    _lib.check(rc, "unirec_list_scores_backward")
+    return d_user, d_list
+
+
+def inject_tokens(text_embeds: torch.Tensor, input_ids: torch.Tensor, token_ids: torch.Tensor,
+                  tokens: torch.Tensor) -> torch.Tensor:
+    """In place: text_embeds[b, s, :] = tokens[b, slot, :] wherever input_ids[b, s] == token_ids[slot].
+    text_embeds [B, S, Hd] (fp32 / bf16, contiguous), input_ids int64 [B, S], token_ids int64 [slots],
+    tokens [B, slots, Hd] (fp32 / bf16)."""
+    for t, n in ((text_embeds, "text_embeds"), (tokens, "tokens")):
+        if t.dtype not in (torch.float32, torch.bfloat16):
+            raise RuntimeError(f"inject_tokens: {n} must be fp32 or bf16")
+        _req(t, t.dtype, f"inject_tokens.{n}")
+    _req(input_ids, torch.int64, "inject_tokens.input_ids")
+    _req(token_ids, torch.int64, "inject_tokens.token_ids")
+    B, S, Hd = text_embeds.shape
+    slots = token_ids.numel()
+    if not text_embeds.is_contiguous() or tuple(input_ids.shape) != (B, S) or tuple(tokens.shape) != (B, slots, Hd):
+        raise RuntimeError("inject_tokens: expected contiguous text_embeds [B, S, Hd], input_ids [B, S], tokens [B, slots, Hd]")
+    rc = _lib.load().unirec_inject_tokens(input_ids.contiguous().data_ptr(), B, S, token_ids.contiguous().data_ptr(), slots,
+                                          tokens.contiguous().data_ptr(), 1 if tokens.dtype == torch.float32 else 0,
+                                          text_embeds.data_ptr(), 1 if text_embeds.dtype == torch.float32 else 0, Hd, Hd,
+                                          _stream())
+    _lib.check(rc, "unirec_inject_tokens")
+    return text_embeds
