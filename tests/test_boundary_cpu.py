@@ -116,3 +116,43 @@ def test_shard_range_partitions_exactly():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_range(10, 2, 2)
+
+
+def test_torch_custom_ops_are_registered_with_fake_impls_and_no_cpu_kernel():
+    """The torch custom-op layer (unirec_b200/torch_ops.py): every op of the namespace infers shapes / dtypes on meta
+    tensors (what FakeTensorMode and torch.export use) and refuses CPU tensors - there is no CPU kernel."""
+    import pytest
+    import torch
+    import unirec_b200.torch_ops as T
+    ns = torch.ops.unirec_b200
+    for name in T.OPS:
+        assert hasattr(ns, name), name
+
+    def m(*shape, dt=torch.bfloat16):
+        return torch.empty(*shape, device="meta", dtype=dt)
+
+    f32, i64 = torch.float32, torch.int64
+    y = ns.linear(m(64, 1024), m(4096, 1024), m(4096, dt=f32), None, 1, False)
+    assert tuple(y.shape) == (64, 4096) and y.dtype == torch.bfloat16
+    y = ns.linear(m(2, 32, 1024), m(1024, 1024), None, m(2, 32, 1024), 2, True)
+    assert tuple(y.shape) == (2, 32, 1024) and y.dtype == f32
+    assert tuple(ns.layernorm(m(32, 1024, dt=f32), m(1024, dt=f32), m(1024, dt=f32), 1e-12, None, 256, 32, False).shape) == (256, 1024)
+    assert tuple(ns.attention(m(64, 1024), m(28, 1024), m(28, 1024), m(2, 14, dt=f32), 2, 16, 32, 14, False).shape) == (64, 1024)
+    assert ns.cast_bf16(m(3, 5, dt=f32)).dtype == torch.bfloat16
+    assert tuple(ns.mean_tokens(m(7, 32, 1024), True).shape) == (7, 1024)
+    assert tuple(ns.field_projection(m(7, 32, 1024), m(14, 32, dt=f32), m(14, dt=f32), True).shape) == (7, 14, 1024)
+    seq, mask = ns.build_user_sequence(m(100, 32, 1024), m(4, 50, dt=i64), m(4, dt=torch.int32), None)
+    assert tuple(seq.shape) == (4, 1600, 1024) and tuple(mask.shape) == (4, 1600) and mask.dtype == f32
+    assert tuple(ns.inv_l2_norm(m(9, 1024), 1e-12).shape) == (9,)
+    s, i = ns.score_topk(m(8, 1024), m(1000, 1024), 100, None, None, 0)
+    assert tuple(s.shape) == (8, 100) and s.dtype == f32 and i.dtype == i64
+    s, i = ns.topk_merge(m(4, 8, 100, dt=f32), m(4, 8, 100, dt=i64))
+    assert tuple(s.shape) == (8, 100) and tuple(i.shape) == (8, 100)
+    sims, inv = ns.list_scores(m(8, 256, dt=f32), m(8, 256, dt=f32), m(8, 20, 256, dt=f32), None, None, 0, 1e-12)
+    assert tuple(sims.shape) == (8, 21) and tuple(inv.shape) == (8, 21)
+    sims, _ = ns.list_scores(m(8, 256, dt=f32), m(8, 256, dt=f32), m(90, 256, dt=f32), None, m(9, dt=i64), 33, 1e-12)
+    assert tuple(sims.shape) == (8, 34)
+    loss, rank = ns.infonce_rank(m(8, 21, dt=f32), 0.07)
+    assert tuple(loss.shape) == (8,) and rank.dtype == torch.int32
+    with pytest.raises(NotImplementedError):
+        ns.linear(torch.zeros(4, 64, dtype=torch.bfloat16), torch.zeros(256, 64, dtype=torch.bfloat16), None, None, 0, False)

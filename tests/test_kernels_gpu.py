@@ -291,3 +291,37 @@ def test_build_user_sequence_matches_oracle():
         assert torch.equal(seq, seq2) and torch.equal(mask, mask2)
     pe = ops.positional_encoding_table(Hmax * Q, D, _dev())
     torch.testing.assert_close(pe.cpu(), O.positional_encoding_table(Hmax * Q, D), rtol=0, atol=2e-4)
+
+
+def test_torch_ops_match_direct_wrappers():
+    """torch.ops.unirec_b200.* (unirec_b200/torch_ops.py) launch the same kernels as the ctypes wrappers the modules
+    call directly: identical bits, and FakeTensorMode infers the real outputs' shapes and dtypes."""
+    import unirec_b200.torch_ops  # noqa: F401
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from unirec_b200 import ops
+    ns = torch.ops.unirec_b200
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = torch.randn(300, 1024, generator=g).to(torch.bfloat16).to(_dev())
+    w = (torch.randn(512, 1024, generator=g) * 0.03).to(torch.bfloat16).to(_dev())
+    b = torch.randn(512, generator=g).to(_dev())
+    assert torch.equal(ns.linear(x, w, b, None, 1, False), ops.linear(x, w, b, epilogue=ops.EPI_BIAS_GELU))
+    gam, bet = torch.rand(1024, generator=g).to(_dev()), torch.randn(1024, generator=g).to(_dev())
+    assert torch.equal(ns.layernorm(x, gam, bet, 1e-12, None, 0, 0, False), ops.layernorm(x, gam, bet, 1e-12))
+    B, heads, nq, nk = 3, 16, 32, 14
+    q = torch.randn(B * nq, 1024, generator=g).to(torch.bfloat16).to(_dev())
+    k = torch.randn(B * nk, 1024, generator=g).to(torch.bfloat16).to(_dev())
+    v = torch.randn(B * nk, 1024, generator=g).to(torch.bfloat16).to(_dev())
+    mask = (torch.rand(B, nk, generator=g) < 0.8).float().to(_dev())
+    assert torch.equal(ns.attention(q, k, v, mask, B, heads, nq, nk, False),
+                       ops.attention(q, k, v, batch=B, num_heads=heads, nq=nq, nk=nk, key_mask=mask))
+    cands = torch.randn(5000, 1024, generator=g).to(torch.bfloat16).to(_dev())
+    users = torch.randn(6, 1024, generator=g).to(torch.bfloat16).to(_dev())
+    s1, i1 = ns.score_topk(users, cands, 10, None, None, 7)
+    s2, i2 = ops.score_topk(users, cands, 10, index_base=7)
+    assert torch.equal(s1, s2) and torch.equal(i1, i2)
+    with FakeTensorMode(allow_non_fake_inputs=False) as mode:
+        fx, fw, fb = mode.from_tensor(x), mode.from_tensor(w), mode.from_tensor(b)
+        fy = ns.linear(fx, fw, fb, None, 0, True)
+        assert tuple(fy.shape) == (300, 512) and fy.dtype == torch.float32 and fy.device.type == "cuda"
+    with pytest.raises(NotImplementedError):
+        ns.mean_tokens(torch.zeros(2, 4, 64, dtype=torch.bfloat16), False)

@@ -1,0 +1,177 @@
+"""torch custom-op layer over the C ABI: `torch.ops.unirec_b200.*`.
+
+The reference has no custom ops of its own; this layer is what BASELINE.json's north_star calls the
+"thin C-ABI torch custom-op layer": every forward kernel of the path is registered with `torch.library.custom_op`
+(CUDA only - there is no CPU kernel to dispatch to, a CPU tensor raises NotImplementedError) together with a fake /
+meta implementation for shape inference, so the ops can be used under FakeTensorMode / `torch.export` and from code
+that only knows the dispatcher.  Each op body is the ctypes wrapper of `unirec_b200.ops` (one kernel launch on the
+current stream).  The nn.Module mirrors in `modules.py` call those wrappers directly - the same launches without the
+dispatcher's per-call cost; `tests/test_kernels_gpu.py::test_torch_ops_match_direct_wrappers` pins the two together.
+
+    import unirec_b200.torch_ops                      # registers the namespace
+    y = torch.ops.unirec_b200.linear(x, w, b, None, 0, False)
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import ops
+
+_BF16, _F32 = torch.bfloat16, torch.float32
+NAMESPACE = "unirec_b200"
+
+
+def _dt(fp32: bool):
+    return _F32 if fp32 else _BF16
+
+
+# ------------------------------------------------------------------------------------------------ projections
+@torch.library.custom_op(f"{NAMESPACE}::linear", mutates_args=(), device_types="cuda")
+def linear(a: Tensor, weight: Tensor, bias: Optional[Tensor], residual: Optional[Tensor], epilogue: int,
+           out_fp32: bool) -> Tensor:
+    """epilogue(a @ weight.T + bias): 0 bias, 1 bias + erf-GELU, 2 bias + residual (include/unirec_b200.h)."""
+    return ops.linear(a, weight, bias, epilogue=epilogue, residual=residual, out_dtype=_dt(out_fp32))
+
+
+@linear.register_fake
+def _(a, weight, bias, residual, epilogue, out_fp32):
+    return a.new_empty(*a.shape[:-1], weight.shape[0], dtype=_dt(out_fp32))
+
+
+@torch.library.custom_op(f"{NAMESPACE}::layernorm", mutates_args=(), device_types="cuda")
+def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, residual: Optional[Tensor], rows: int,
+              in_row_mod: int, out_fp32: bool) -> Tensor:
+    """LayerNorm(x [+ residual]); rows = 0: as many rows as x; in_row_mod > 0: x rows broadcast over `rows` rows."""
+    return ops.layernorm(x, gamma, beta, eps, residual=residual, rows=rows if rows > 0 else None,
+                         in_row_mod=in_row_mod, out_dtype=_dt(out_fp32))
+
+
+@layernorm.register_fake
+def _(x, gamma, beta, eps, residual, rows, in_row_mod, out_fp32):
+    H = x.shape[-1]
+    if in_row_mod > 0 or x.dim() == 2:
+        return x.new_empty(rows if rows > 0 else x.numel() // H, H, dtype=_dt(out_fp32))
+    return x.new_empty(x.shape, dtype=_dt(out_fp32))
+
+
+@torch.library.custom_op(f"{NAMESPACE}::attention", mutates_args=(), device_types="cuda")
+def attention(q: Tensor, k: Tensor, v: Tensor, key_mask: Optional[Tensor], batch: int, num_heads: int, nq: int,
+              nk: int, q_broadcast: bool) -> Tensor:
+    """softmax(q k^T / 8 + mask) v per head (head_dim 64), heads merged: bf16 [batch * nq, num_heads * 64]."""
+    return ops.attention(q, k, v, batch=batch, num_heads=num_heads, nq=nq, nk=nk, key_mask=key_mask,
+                         q_broadcast=q_broadcast)
+
+
+@attention.register_fake
+def _(q, k, v, key_mask, batch, num_heads, nq, nk, q_broadcast):
+    return q.new_empty(batch * nq, num_heads * 64, dtype=_BF16)
+
+
+# ------------------------------------------------------------------------------------------------ row-wise
+@torch.library.custom_op(f"{NAMESPACE}::cast_bf16", mutates_args=(), device_types="cuda")
+def cast_bf16(x: Tensor) -> Tensor:
+    out = ops.cast_bf16(x)
+    return out.clone() if out is x else out          # custom ops may not return an alias of an input
+
+
+@cast_bf16.register_fake
+def _(x):
+    return x.new_empty(x.shape, dtype=_BF16)
+
+
+@torch.library.custom_op(f"{NAMESPACE}::mean_tokens", mutates_args=(), device_types="cuda")
+def mean_tokens(x: Tensor, out_fp32: bool) -> Tensor:
+    return ops.mean_tokens(x, out_dtype=_dt(out_fp32))
+
+
+@mean_tokens.register_fake
+def _(x, out_fp32):
+    return x.new_empty(x.shape[0], x.shape[2], dtype=_dt(out_fp32))
+
+
+@torch.library.custom_op(f"{NAMESPACE}::field_projection", mutates_args=(), device_types="cuda")
+def field_projection(rec: Tensor, weight: Tensor, bias: Tensor, out_fp32: bool) -> Tensor:
+    return ops.field_projection(rec, weight, bias, out_dtype=_dt(out_fp32))
+
+
+@field_projection.register_fake
+def _(rec, weight, bias, out_fp32):
+    return rec.new_empty(rec.shape[0], weight.shape[0], rec.shape[2], dtype=_dt(out_fp32))
+
+
+@torch.library.custom_op(f"{NAMESPACE}::build_user_sequence", mutates_args=(), device_types="cuda")
+def build_user_sequence(table: Tensor, history: Tensor, lengths: Tensor, context: Optional[Tensor]
+                        ) -> Tuple[Tensor, Tensor]:
+    return ops.build_user_sequence(table, history, lengths, context)
+
+
+@build_user_sequence.register_fake
+def _(table, history, lengths, context):
+    B, Hmax = history.shape
+    Q, D = table.shape[1], table.shape[2]
+    return table.new_empty(B, Hmax * Q, D, dtype=_BF16), table.new_empty(B, Hmax * Q, dtype=_F32)
+
+
+@torch.library.custom_op(f"{NAMESPACE}::inv_l2_norm", mutates_args=(), device_types="cuda")
+def inv_l2_norm(x: Tensor, eps: float) -> Tensor:
+    return ops.inv_l2_norm(x, eps)
+
+
+@inv_l2_norm.register_fake
+def _(x, eps):
+    return x.new_empty(x.numel() // x.shape[-1], dtype=_F32)
+
+
+# ------------------------------------------------------------------------------------------------ ranking
+@torch.library.custom_op(f"{NAMESPACE}::score_topk", mutates_args=(), device_types="cuda")
+def score_topk(users: Tensor, cands: Tensor, k: int, user_inv: Optional[Tensor], cand_inv: Optional[Tensor],
+               index_base: int) -> Tuple[Tensor, Tensor]:
+    """Cosine top-k of users [B, D] against cands [N, D]: (scores fp32 [B, k], global indices int64 [B, k])."""
+    return ops.score_topk(users, cands, k, user_inv=user_inv, cand_inv=cand_inv, index_base=index_base)
+
+
+@score_topk.register_fake
+def _(users, cands, k, user_inv, cand_inv, index_base):
+    B = users.shape[0]
+    return users.new_empty(B, k, dtype=_F32), users.new_empty(B, k, dtype=torch.int64)
+
+
+@torch.library.custom_op(f"{NAMESPACE}::topk_merge", mutates_args=(), device_types="cuda")
+def topk_merge(scores: Tensor, idx: Tensor) -> Tuple[Tensor, Tensor]:
+    return ops.topk_merge(scores, idx)
+
+
+@topk_merge.register_fake
+def _(scores, idx):
+    return scores.new_empty(scores.shape[1], scores.shape[2]), idx.new_empty(idx.shape[1], idx.shape[2])
+
+
+@torch.library.custom_op(f"{NAMESPACE}::list_scores", mutates_args=(), device_types="cuda")
+def list_scores(users: Tensor, pos: Tensor, cands: Tensor, mask: Optional[Tensor], offsets: Optional[Tensor],
+                max_list: int, eps: float) -> Tuple[Tensor, Tensor]:
+    """Per-user candidate lists (padded + mask, or ragged + offsets): (sims, inv_norm) fp32 [B, 1 + C]."""
+    return ops.list_scores(users, pos, cands, mask=mask, offsets=offsets,
+                           max_list=max_list if offsets is not None else None, eps=eps)
+
+
+@list_scores.register_fake
+def _(users, pos, cands, mask, offsets, max_list, eps):
+    C = max_list if offsets is not None else cands.shape[1]
+    return users.new_empty(users.shape[0], C + 1, dtype=_F32), users.new_empty(users.shape[0], C + 1, dtype=_F32)
+
+
+@torch.library.custom_op(f"{NAMESPACE}::infonce_rank", mutates_args=(), device_types="cuda")
+def infonce_rank(sims: Tensor, temperature: float) -> Tuple[Tensor, Tensor]:
+    return ops.infonce_rank(sims, temperature)
+
+
+@infonce_rank.register_fake
+def _(sims, temperature):
+    return sims.new_empty(sims.shape[0]), sims.new_empty(sims.shape[0], dtype=torch.int32)
+
+
+OPS = ("linear", "layernorm", "attention", "cast_bf16", "mean_tokens", "field_projection", "build_user_sequence",
+       "inv_l2_norm", "score_topk", "topk_merge", "list_scores", "infonce_rank")
