@@ -8,11 +8,11 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 for w in $what; do
 case $w in
 tests)
-  timeout 300 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+  timeout 600 python -m pytest tests -m gpu -q --timeout 200 --durations=12 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
   timeout 150 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
   ;;
 bench)
-  timeout 900 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; echo "bench rc=$?" >> gpurun_out/bench_full.err
+  timeout 700 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; echo "bench rc=$?" >> gpurun_out/bench_full.err
   ;;
 launches)
   # small pool so the run is short; every launch of one timed user step / two item chunks (cold-cache, serialised)
@@ -44,7 +44,7 @@ ncu)
   ls -la /tmp/*.ncu-rep >> gpurun_out/prof_users_raw.err
   ;;
 kernels)
-  timeout 240 python tools/gpu_bench_kernels.py > gpurun_out/kernels.log 2>&1; echo "kernels rc=$?" >> gpurun_out/kernels.log
+  timeout 300 python tools/gpu_bench_kernels.py > gpurun_out/kernels.log 2>&1; echo "kernels rc=$?" >> gpurun_out/kernels.log
   ;;
 esac
 done

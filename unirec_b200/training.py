@@ -392,6 +392,10 @@ class TrainStepGraph:
                     self._body()
             torch.cuda.current_stream(dev).wait_stream(side)
             self._clear_grads()
+            # the bf16 weight packs cached by the warm-up passes live outside the graph: drop them so that the packing
+            # kernels are captured and every replay re-packs the CURRENT fp32 master weights
+            model.qformer._pack = model.qformer._pack_key = None
+            model._head_pack = model._head_key = None
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self.seed_offset.add_(self.SEED_STRIDE)
