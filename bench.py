@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--users-per-gpu", type=int, default=4096)
     ap.add_argument("--item-batch", type=int, default=4096)
     ap.add_argument("--history", type=int, default=50)
+    ap.add_argument("--kv-gb", type=float, default=0.0, help="user Q-Former: bytes of cross-attention K/V materialised per "
+                    "chunk of users, in GiB (0 = the module's default)")
     ap.add_argument("--top-k", type=int, default=100)
     ap.add_argument("--cpu-users", type=int, default=8, help="users in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -63,6 +65,7 @@ def config_dict(args, n_gpus):
         "workload": "cfg5 nested item->user Q-Former encode + cosine top-100 over a 1M-item candidate pool "
                     "(item-token table + pool produced by cfg3 item-token generation)",
         "users_per_gpu_per_step": args.users_per_gpu, "global_users_per_step": args.users_per_gpu * n_gpus,
+        "user_chunk_kv_gib": args.kv_gb if args.kv_gb > 0 else "module default",
         "history_items": args.history, "tokens_per_item": 32, "keys_per_user": args.history * 32,
         "user_qformer": "4 layers x 64 queries, hidden 1024, 16 heads, FFN 4096, cross-attn every layer",
         "item_qformer": "12 layers x 32 queries, 14 fields x 1024, cross-attn every 2nd layer",
@@ -320,6 +323,12 @@ def run_train_block(args, rank, world, dev, barrier, max_over_ranks, pk):
     gemm = stats.get("gemm")
     ach = gemm[1] / (gemm[2] * 1e-3) / 1e12 if gemm and gemm[2] > 0 else None
     eager_ms, eager_faithful_ms, eager_host_ms = ms, ms_faithful, host_ms
+    final_loss = float(loss.detach())
+    # an autograd graph kept alive by `loss` keeps the parameters' AccumulateGrad nodes - bound to the stream of the
+    # eager steps - alive, and capture on another stream would be invalidated by them
+    del loss
+    import gc
+    gc.collect()
 
     # ---- the same step replayed from a CUDA graph (training.TrainStepGraph): one launch per step instead of ~435, the
     # gradient all-reduce (one flat bucket) and the fused AdamW stay outside the graph
@@ -377,7 +386,7 @@ def run_train_block(args, rank, world, dev, barrier, max_over_ranks, pk):
         "dropout": args.train_dropout, "host_enqueue_ms_per_step": host_ms,
         "reference_faithful_step": {"what": "anchor fwd+bwd + two no-grad train-mode forwards (positive, negative)",
                                     "ms_per_step": ms_faithful, "items_per_s": Bg / (ms_faithful * 1e-3)},
-        "final_loss": float(loss.detach()), "gpu_launches_per_step": launches,
+        "final_loss": final_loss, "gpu_launches_per_step": launches,
         "mode": "cuda_graph" if graph_info.get("used") else "eager",
         "cuda_graph": graph_info,
         "eager": {"ms_per_step": eager_ms, "items_per_s": Bg / (eager_ms * 1e-3), "host_enqueue_ms_per_step": eager_host_ms,
@@ -445,6 +454,8 @@ def run_ours(args, rank, world, local_rank):
         user = UserQFormer().eval()
     item.prelayernorm_dtype = torch.bfloat16
     user.prelayernorm_dtype = torch.bfloat16
+    if args.kv_gb > 0:
+        user.max_kv_bytes = int(args.kv_gb * (1 << 30))
 
     # ------------------------------------------------------------------ stage A: item-token generation (cfg 3)
     N, Bi = args.pool_items, args.item_batch

@@ -8,7 +8,7 @@
 // dot products in a bmm / a Python loop per user and builds the loss per user in another Python loop.
 //
 // Here: one streaming pass over the candidate rows (the only large operand; HBM-bound, B*(1+C)*D elements read
-// once, 16-byte loads, one warp per candidate row with four rows in flight) produces cosine similarities and the
+// once, 16-byte loads, one warp per candidate row with 4 fp32 / 8 bf16 rows in flight) produces cosine similarities and the
 // rows' inverse norms; a second tiny kernel (one warp per user) turns a user's similarities into the InfoNCE loss
 // (-s_pos/T + logsumexp over the positive and the valid negatives) and the 1-based rank of the positive; the
 // backward kernel re-streams the rows once and accumulates d loss / d user (the only operand that carries a
@@ -20,8 +20,11 @@ namespace unirec {
 
 constexpr int LS_THREADS = 256;
 constexpr int LS_WARPS = LS_THREADS / 32;
-constexpr int LS_ROWS_PER_WARP = 4;
-constexpr int LS_ROWS_PER_CTA = LS_WARPS * LS_ROWS_PER_WARP;     // 32 list entries (entry 0 = the positive)
+// list entries one warp keeps in flight in the forward pass: 4 fp32 rows or 8 bf16 rows (the same bytes per lane;
+// ncu-less first measurement: bf16 with 4 rows reached 58 % of HBM peak where fp32 reached 92 %)
+template <bool FP32> constexpr int ls_rows_per_warp() { return FP32 ? 4 : 8; }
+constexpr int LSB_THREADS = 128;         // backward: one 16-byte chunk of the row per thread, 16 list entries per CTA
+constexpr int LSB_ROWS = 16;
 
 struct ListParams {
     const void* users; long long ldu;
@@ -34,17 +37,38 @@ struct ListParams {
     float eps;
 };
 
+// 8 consecutive elements of a row: raw 16-byte loads first (so that several rows' loads are in flight without holding
+// their unpacked values in registers), conversion to fp32 at the point of use.
+template <bool FP32> struct Raw8 { uint4 a; uint4 b; };
+template <> struct Raw8<false> { uint4 a; };
+
+template <bool FP32>
+UNIREC_DEVICE Raw8<FP32> load_raw8(const void* row, int vi) {
+    Raw8<FP32> q;
+    if constexpr (FP32) {
+        q.a = __ldg(reinterpret_cast<const uint4*>(row) + 2 * vi);
+        q.b = __ldg(reinterpret_cast<const uint4*>(row) + 2 * vi + 1);
+    } else {
+        q.a = __ldg(reinterpret_cast<const uint4*>(row) + vi);
+    }
+    return q;
+}
+
+template <bool FP32>
+UNIREC_DEVICE void unpack8(const Raw8<FP32>& q, float (&f)[8]) {
+    if constexpr (FP32) {
+        f[0] = __uint_as_float(q.a.x); f[1] = __uint_as_float(q.a.y); f[2] = __uint_as_float(q.a.z);
+        f[3] = __uint_as_float(q.a.w); f[4] = __uint_as_float(q.b.x); f[5] = __uint_as_float(q.b.y);
+        f[6] = __uint_as_float(q.b.z); f[7] = __uint_as_float(q.b.w);
+    } else {
+        f[0] = bf16_lo(q.a.x); f[1] = bf16_hi(q.a.x); f[2] = bf16_lo(q.a.y); f[3] = bf16_hi(q.a.y);
+        f[4] = bf16_lo(q.a.z); f[5] = bf16_hi(q.a.z); f[6] = bf16_lo(q.a.w); f[7] = bf16_hi(q.a.w);
+    }
+}
+
 template <bool FP32>
 UNIREC_DEVICE void load8(const void* row, int vi, float (&f)[8]) {
-    if constexpr (FP32) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(row) + 2 * vi);
-        const float4 b = __ldg(reinterpret_cast<const float4*>(row) + 2 * vi + 1);
-        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-    } else {
-        const uint4 a = __ldg(reinterpret_cast<const uint4*>(row) + vi);
-        f[0] = bf16_lo(a.x); f[1] = bf16_hi(a.x); f[2] = bf16_lo(a.y); f[3] = bf16_hi(a.y);
-        f[4] = bf16_lo(a.z); f[5] = bf16_hi(a.z); f[6] = bf16_lo(a.w); f[7] = bf16_hi(a.w);
-    }
+    unpack8<FP32>(load_raw8<FP32>(row, vi), f);
 }
 
 // Row pointer of list entry e (0 = positive, e >= 1 = negative e - 1) of user b, or nullptr if the entry is padding.
@@ -89,37 +113,42 @@ UNIREC_DEVICE float stage_user(const ListParams& p, long long b, float* s_u, flo
 
 // sims[b, e] = cos(user_b, entry e) (-inf for padding), inv_norm[b, e] = 1 / max(||entry||, eps) (0 for padding).
 template <bool FP32>
-__global__ void __launch_bounds__(LS_THREADS)
+__global__ void __launch_bounds__(LS_THREADS, 2)
 list_scores_kernel(const ListParams p, float* __restrict__ sims, float* __restrict__ inv_norm) {
+    constexpr int ROWS = ls_rows_per_warp<FP32>();
     extern __shared__ float s_u[];
     __shared__ float s_red[LS_WARPS];
     const long long b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float inv_u = stage_user<FP32>(p, b, s_u, s_red);
-    const int e0 = blockIdx.x * LS_ROWS_PER_CTA + warp * LS_ROWS_PER_WARP;
-    const void* rows[LS_ROWS_PER_WARP];
+    const int e0 = (blockIdx.x * LS_WARPS + warp) * ROWS;
+    const void* rows[ROWS];
 #pragma unroll
-    for (int r = 0; r < LS_ROWS_PER_WARP; ++r) rows[r] = (e0 + r <= p.C) ? list_row<FP32>(p, b, e0 + r) : nullptr;
-    float dot[LS_ROWS_PER_WARP] = {0.f, 0.f, 0.f, 0.f}, ss[LS_ROWS_PER_WARP] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < ROWS; ++r) rows[r] = (e0 + r <= p.C) ? list_row<FP32>(p, b, e0 + r) : nullptr;
+    float dot[ROWS], ss[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) { dot[r] = 0.f; ss[r] = 0.f; }
     for (int vi = lane; vi < p.D / 8; vi += 32) {
-        float f[LS_ROWS_PER_WARP][8];
+        Raw8<FP32> q[ROWS];
 #pragma unroll
-        for (int r = 0; r < LS_ROWS_PER_WARP; ++r) {
-            if (rows[r] != nullptr) load8<FP32>(rows[r], vi, f[r]);
+        for (int r = 0; r < ROWS; ++r) {
+            if (rows[r] != nullptr) q[r] = load_raw8<FP32>(rows[r], vi);
         }
         const float4 u0 = *reinterpret_cast<const float4*>(s_u + vi * 8);
         const float4 u1 = *reinterpret_cast<const float4*>(s_u + vi * 8 + 4);
         const float u[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
 #pragma unroll
-        for (int r = 0; r < LS_ROWS_PER_WARP; ++r) {
+        for (int r = 0; r < ROWS; ++r) {
             if (rows[r] != nullptr) {
+                float f[8];
+                unpack8<FP32>(q[r], f);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { dot[r] += u[j] * f[r][j]; ss[r] += f[r][j] * f[r][j]; }
+                for (int j = 0; j < 8; ++j) { dot[r] += u[j] * f[j]; ss[r] += f[j] * f[j]; }
             }
         }
     }
 #pragma unroll
-    for (int r = 0; r < LS_ROWS_PER_WARP; ++r) {
+    for (int r = 0; r < ROWS; ++r) {
         const int e = e0 + r;
         if (e > p.C) continue;
         const float d = warp_sum(dot[r]), s2 = warp_sum(ss[r]);
@@ -164,77 +193,109 @@ infonce_rank_kernel(const float* __restrict__ sims, int B, int C, float inv_temp
 //   d s / d u = (c^ - s u^) / ||u||,   d s / d c = (u^ - s c^) / ||c||     (no projection term where the norm is clamped)
 // d_user[b, :] (fp32, zero-initialised by the caller) += sum_e g_e d s_e / d u; d_list (optional, fp32, [B, 1 + C, D],
 // zero rows for padding) = g_e d s_e / d c.
+// A CTA owns LSB_ROWS list entries of one user; every thread owns 16-byte chunks of the D axis and walks the CTA's rows
+// with its partial sum_e g_e c^_e in registers (the first version let one warp own a row and summed in shared memory
+// with atomics: 18 % of HBM peak), then adds its share to d_user with one global atomic per element.
 template <bool FP32>
-__global__ void __launch_bounds__(LS_THREADS)
+__global__ void __launch_bounds__(LSB_THREADS)
 list_scores_backward_kernel(const ListParams p, const float* __restrict__ sims, const float* __restrict__ inv_norm,
                             const float* __restrict__ dloss, float inv_temperature, float* __restrict__ d_user,
                             float* __restrict__ d_list) {
-    extern __shared__ float smem_f[];
-    float* s_u = smem_f;                 // user vector
-    float* s_acc = smem_f + p.D;         // this CTA's share of sum_e g_e * inv_c * c
-    __shared__ float s_red[LS_WARPS];
-    __shared__ float s_coef[LS_WARPS];   // per warp: sum_e g_e * s_e
+    __shared__ const void* s_row[LSB_ROWS];
+    __shared__ float s_g[LSB_ROWS], s_se[LSB_ROWS], s_invc[LSB_ROWS];
+    __shared__ float s_red[LSB_THREADS / 32];
+    __shared__ float s_ctot;
     const long long b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float inv_u = stage_user<FP32>(p, b, s_u, s_red);
-    for (int i = threadIdx.x; i < p.D; i += LS_THREADS) s_acc[i] = 0.f;
-    __syncthreads();
-    // softmax statistics of the user's list (every warp recomputes them: 1 + C <= a few hundred values)
-    const float* s = sims + b * (p.C + 1);
-    float m = -INFINITY;
-    for (int e = lane; e <= p.C; e += 32) m = fmaxf(m, s[e]);
-    m = warp_max(m) * inv_temperature;
-    float z = 0.f;
-    for (int e = lane; e <= p.C; e += 32) {
-        const float v = s[e];
-        if (v != -INFINITY) z += __expf(v * inv_temperature - m);
+    const size_t es = FP32 ? 4 : 2;
+    const void* urow = reinterpret_cast<const unsigned char*>(p.users) + static_cast<size_t>(b * p.ldu) * es;
+    // ||u||: every thread sums the squares of its chunks
+    float ss = 0.f;
+    for (int vi = threadIdx.x; vi < p.D / 8; vi += LSB_THREADS) {
+        float f[8];
+        load8<FP32>(urow, vi, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
     }
-    z = warp_sum(z);
-    const float gscale = dloss[b] * inv_temperature;
-    const bool u_clamped = inv_u >= 1.0f / p.eps;     // ||u|| <= eps: u^ = u / eps, no projection term
-
-    const int e0 = blockIdx.x * LS_ROWS_PER_CTA + warp * LS_ROWS_PER_WARP;
-    float coef = 0.f;
-#pragma unroll 1
-    for (int r = 0; r < LS_ROWS_PER_WARP; ++r) {
-        const int e = e0 + r;
-        if (e > p.C) break;
-        const void* row = list_row<FP32>(p, b, e);
-        float* drow = d_list != nullptr ? d_list + (b * (p.C + 1) + e) * static_cast<long long>(p.D) : nullptr;
-        if (row == nullptr) {
-            if (drow != nullptr)
-                for (int i = lane; i < p.D; i += 32) drow[i] = 0.f;
-            continue;
+    ss = warp_sum(ss);
+    if (lane == 0) s_red[warp] = ss;
+    // warp 0: softmax statistics of the user's list and the per-row coefficients of this CTA's entries
+    const int e0 = blockIdx.x * LSB_ROWS;
+    if (warp == 0) {
+        const float* s = sims + b * (p.C + 1);
+        float m = -INFINITY;
+        for (int e = lane; e <= p.C; e += 32) m = fmaxf(m, s[e]);
+        m = warp_max(m) * inv_temperature;
+        float z = 0.f;
+        for (int e = lane; e <= p.C; e += 32) {
+            const float v = s[e];
+            if (v != -INFINITY) z += __expf(v * inv_temperature - m);
         }
-        const float se = s[e];
-        const float inv_c = inv_norm[b * (p.C + 1) + e];
-        const float g = gscale * (__expf(se * inv_temperature - m) / z - (e == 0 ? 1.f : 0.f));
-        coef += g * se;
-        const bool c_clamped = inv_c >= 1.0f / p.eps;
-        const float wc = g * inv_c;                 // weight of c in d_user (through c^ = c * inv_c)
-        for (int vi = lane; vi < p.D / 8; vi += 32) {
+        z = warp_sum(z);
+        float gs = 0.f;
+        if (lane < LSB_ROWS) {
+            const int e = e0 + lane;
+            const void* row = e <= p.C ? list_row<FP32>(p, b, e) : nullptr;
+            float g = 0.f, se = 0.f, ic = 0.f;
+            if (row != nullptr) {
+                se = s[e];
+                ic = inv_norm[b * (p.C + 1) + e];
+                g = dloss[b] * inv_temperature * (__expf(se * inv_temperature - m) / z - (e == 0 ? 1.f : 0.f));
+            }
+            s_row[lane] = row; s_g[lane] = g; s_se[lane] = se; s_invc[lane] = ic;
+            gs = g * se;
+        }
+        gs = warp_sum(gs);
+        if (lane == 0) s_ctot = gs;
+    }
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < LSB_THREADS / 32; ++w) tot += s_red[w];
+    const float inv_u = 1.0f / fmaxf(sqrtf(tot), p.eps);
+    const bool u_clamped = inv_u >= 1.0f / p.eps;      // ||u|| <= eps: u^ = u / eps, no projection term
+    const float ctot = u_clamped ? 0.f : s_ctot;
+    const int n_rows = min(LSB_ROWS, p.C + 1 - e0);
+
+    for (int vi = threadIdx.x; vi < p.D / 8; vi += LSB_THREADS) {
+        float u[8], acc[8];
+        load8<FP32>(urow, vi, u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { u[j] *= inv_u; acc[j] = 0.f; }
+#pragma unroll 4
+        for (int r = 0; r < n_rows; ++r) {
+            const void* row = s_row[r];
+            float* drow = d_list != nullptr ? d_list + ((b * (p.C + 1) + e0 + r) * static_cast<long long>(p.D) + vi * 8)
+                                            : nullptr;
+            if (row == nullptr) {
+                if (drow != nullptr) {
+                    reinterpret_cast<float4*>(drow)[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    reinterpret_cast<float4*>(drow)[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                continue;
+            }
             float f[8];
             load8<FP32>(row, vi, f);
+            const float g = s_g[r], se = s_se[r], ic = s_invc[r];
+            const float wc = g * ic;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                atomicAdd(&s_acc[vi * 8 + j], wc * f[j]);
-                if (drow != nullptr) {
-                    const float uh = s_u[vi * 8 + j] * inv_u, ch = f[j] * inv_c;
-                    drow[vi * 8 + j] = g * (uh - (c_clamped ? 0.f : se * ch)) * inv_c;
-                }
+            for (int j = 0; j < 8; ++j) acc[j] += wc * f[j];
+            if (drow != nullptr) {
+                const float proj = (ic >= 1.0f / p.eps) ? 0.f : se * ic;     // clamped ||c||: no projection term
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = wc * (u[j] - proj * f[j]);
+                reinterpret_cast<float4*>(drow)[0] = make_float4(o[0], o[1], o[2], o[3]);
+                reinterpret_cast<float4*>(drow)[1] = make_float4(o[4], o[5], o[6], o[7]);
             }
         }
-    }
-    if (lane == 0) s_coef[warp] = coef;
-    __syncthreads();
-    float ctot = 0.f;
+        // d_user += (sum_e g_e c^_e - (sum_e g_e s_e) u^) / ||u||_clamped
+        float* du = d_user + b * static_cast<long long>(p.D) + vi * 8;
 #pragma unroll
-    for (int w = 0; w < LS_WARPS; ++w) ctot += s_coef[w];
-    if (u_clamped) ctot = 0.f;
-    // d_user += (sum_e g_e c^_e - (sum_e g_e s_e) u^) / ||u||_clamped
-    for (int i = threadIdx.x; i < p.D; i += LS_THREADS) {
-        const float v = (s_acc[i] - ctot * s_u[i] * inv_u) * inv_u;
-        if (v != 0.f) atomicAdd(d_user + b * static_cast<long long>(p.D) + i, v);
+        for (int j = 0; j < 8; ++j) {
+            const float v = (acc[j] - ctot * u[j]) * inv_u;
+            if (v != 0.f) atomicAdd(du + j, v);
+        }
     }
 }
 
@@ -311,7 +372,8 @@ int list_scores(const void* users, long long ldu, const void* pos, long long ldp
     if (rc != UNIREC_OK) return rc;
     if (sims == nullptr) { set_last_error("list_scores: sims is null"); return UNIREC_ERR_BAD_ARG; }
     const ListParams p = make_list_params(users, ldu, pos, ldp, cands, ldc, mask, offsets, C, D, eps);
-    const dim3 grid(static_cast<unsigned>((C + 1 + LS_ROWS_PER_CTA - 1) / LS_ROWS_PER_CTA), static_cast<unsigned>(B));
+    const int rows_per_cta = LS_WARPS * (fp32 ? ls_rows_per_warp<true>() : ls_rows_per_warp<false>());
+    const dim3 grid(static_cast<unsigned>((C + 1 + rows_per_cta - 1) / rows_per_cta), static_cast<unsigned>(B));
     const size_t smem = static_cast<size_t>(D) * sizeof(float);
     if (fp32) list_scores_kernel<true><<<grid, LS_THREADS, smem, stream>>>(p, sims, inv_norm);
     else list_scores_kernel<false><<<grid, LS_THREADS, smem, stream>>>(p, sims, inv_norm);
@@ -346,28 +408,13 @@ int list_scores_backward(const void* users, long long ldu, const void* pos, long
         return UNIREC_ERR_BAD_ARG;
     }
     const ListParams p = make_list_params(users, ldu, pos, ldp, cands, ldc, mask, offsets, C, D, eps);
-    const dim3 grid(static_cast<unsigned>((C + 1 + LS_ROWS_PER_CTA - 1) / LS_ROWS_PER_CTA), static_cast<unsigned>(B));
-    const size_t smem = 2 * static_cast<size_t>(D) * sizeof(float);
-    if (smem > 48 * 1024) {
-        static bool attr_set[2] = {false, false};
-        if (!attr_set[fp32 ? 1 : 0]) {
-            cudaError_t e = fp32 ? cudaFuncSetAttribute(list_scores_backward_kernel<true>,
-                                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)
-                                 : cudaFuncSetAttribute(list_scores_backward_kernel<false>,
-                                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-            if (e != cudaSuccess) {
-                set_last_error("list_scores_backward: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-                return UNIREC_ERR_CUDA;
-            }
-            attr_set[fp32 ? 1 : 0] = true;
-        }
-    }
+    const dim3 grid(static_cast<unsigned>((C + 1 + LSB_ROWS - 1) / LSB_ROWS), static_cast<unsigned>(B));
     if (fp32)
-        list_scores_backward_kernel<true><<<grid, LS_THREADS, smem, stream>>>(p, sims, inv_norm, dloss, 1.0f / temperature,
-                                                                             d_user, d_list);
+        list_scores_backward_kernel<true><<<grid, LSB_THREADS, 0, stream>>>(p, sims, inv_norm, dloss, 1.0f / temperature,
+                                                                           d_user, d_list);
     else
-        list_scores_backward_kernel<false><<<grid, LS_THREADS, smem, stream>>>(p, sims, inv_norm, dloss,
-                                                                              1.0f / temperature, d_user, d_list);
+        list_scores_backward_kernel<false><<<grid, LSB_THREADS, 0, stream>>>(p, sims, inv_norm, dloss, 1.0f / temperature,
+                                                                            d_user, d_list);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_last_error("list_scores_backward launch: %s", cudaGetErrorString(e));
