@@ -373,7 +373,11 @@ def run_train_block(args, rank, world, dev, barrier, max_over_ranks, pk):
                       "faithful_ms_per_step": gf_ms, "final_loss": g_loss,
                       "what": "forward + loss + backward replayed from one CUDA graph (device-resident dropout seed "
                               "offset); flat gradient all-reduce and fused AdamW outside the graph"}
-        ms, ms_faithful, host_ms = g_ms, gf_ms, g_host_ms
+        if g_ms < eager_ms:       # the headline of the block is the faster mode; both are reported
+            ms, ms_faithful, host_ms = g_ms, gf_ms, g_host_ms
+        else:
+            graph_info["note"] = ("eager is faster at this size: its per-layer all-reduce overlaps the backward pass and "
+                                  "the host still keeps ahead of the GPU")
     except Exception as e:   # keep the eager numbers if capture is not possible on this box
         graph_info = {"used": False, "error": f"{type(e).__name__}: {e}"[:300]}
     items_per_sec = Bg / (ms * 1e-3)
@@ -387,7 +391,7 @@ def run_train_block(args, rank, world, dev, barrier, max_over_ranks, pk):
         "reference_faithful_step": {"what": "anchor fwd+bwd + two no-grad train-mode forwards (positive, negative)",
                                     "ms_per_step": ms_faithful, "items_per_s": Bg / (ms_faithful * 1e-3)},
         "final_loss": final_loss, "gpu_launches_per_step": launches,
-        "mode": "cuda_graph" if graph_info.get("used") else "eager",
+        "mode": "cuda_graph" if (graph_info.get("used") and ms < eager_ms) else "eager",
         "cuda_graph": graph_info,
         "eager": {"ms_per_step": eager_ms, "items_per_s": Bg / (eager_ms * 1e-3), "host_enqueue_ms_per_step": eager_host_ms,
                   "faithful_ms_per_step": eager_faithful_ms},

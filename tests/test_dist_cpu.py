@@ -104,6 +104,24 @@ def _allreduce_worker(rank, world, port, q):
                 dist.all_gather(gathered, m)
                 ok = ok and torch.allclose(t, sum(gathered) / world, atol=1e-6)
         ok = ok and torch.equal(torch.cat(views), big)  # views see the in-place result
+        # reduce_tensors (behind a CUDA-graph step): views of one buffer are reduced as that buffer, in place; tensors
+        # that stand alone go through one packed bucket
+        buf = torch.randn(60, generator=g)
+        alone = [torch.randn(3, 4, generator=g), torch.randn(5, generator=g)]
+        mix = [buf[:24].view(4, 6), buf[24:30], buf[30:].view(3, 10)] + alone
+        mix_keep = [t.clone() for t in mix]
+        buckets, rest = GradientAllReducer.alias_buckets(mix)
+        assert len(buckets) == 1 and buckets[0].numel() == 60 and buckets[0].data_ptr() == buf.data_ptr()
+        assert len(rest) == 2
+        sparse_cover, lonely = GradientAllReducer.alias_buckets([buf[:5], buf[50:55]])
+        assert not sparse_cover and len(lonely) == 2        # two small views far apart: not worth reducing the span
+        before = red.bytes_reduced
+        red.reduce_tensors(mix + [None])
+        assert red.bytes_reduced - before == (60 + 12 + 5) * 4
+        for t, m in zip(mix, mix_keep):
+            gathered = [torch.empty_like(m) for _ in range(world)]
+            dist.all_gather(gathered, m)
+            ok = ok and torch.allclose(t, sum(gathered) / world, atol=1e-6)
         p = torch.nn.Parameter(torch.zeros(3))
         p.grad = torch.full((3,), float(rank + 1))
         red.reduce_params([p, torch.nn.Parameter(torch.zeros(2))])      # second one has no grad: skipped

@@ -319,22 +319,52 @@ class GradientAllReducer:
         self.layer_ready(-2, grads)
         self.finish()
 
+    @staticmethod
+    def alias_buckets(tensors: List[torch.Tensor], min_cover: float = 0.9):
+        """Split `tensors` into (buckets, rest): a bucket is ONE flat tensor that aliases the storage range spanned by
+        several of the tensors (contiguous views of one buffer that cover at least `min_cover` of that range, e.g. the
+        backbone's flat gradient buffer behind autograd's `.grad` views) - reducing it in place reduces all of them
+        without pack / unpack copies; `rest` are the tensors that stand alone."""
+        groups = {}
+        for t in tensors:
+            groups.setdefault((t.untyped_storage().data_ptr(), t.dtype), []).append(t)
+        buckets, rest = [], []
+        for ts in groups.values():
+            if len(ts) < 2 or any(not t.is_contiguous() for t in ts):
+                rest += ts
+                continue
+            lo = min(t.storage_offset() for t in ts)
+            hi = max(t.storage_offset() + t.numel() for t in ts)
+            if sum(t.numel() for t in ts) < min_cover * (hi - lo):
+                rest += ts
+                continue
+            buckets.append(ts[0].new_empty(0).set_(ts[0].untyped_storage(), lo, (hi - lo,)))
+        return buckets, rest
+
     def reduce_tensors(self, tensors: List[torch.Tensor]):
-        """Average `tensors` over the ranks in place with ONE all-reduce of one flat bucket (pack, reduce, unpack with a
-        single multi-tensor copy).  Used behind a CUDA-graph step, whose gradients all exist when the graph has run."""
+        """Average `tensors` over the ranks in place.  Tensors that are views of one buffer are reduced as that buffer
+        (one all-reduce, no copies); the others are packed into one flat bucket, reduced and unpacked with a single
+        multi-tensor copy.  Used behind a CUDA-graph step, whose gradients all exist when the graph has run."""
         tensors = [t for t in tensors if t is not None]
         if self.world == 1 or not tensors:
             return
-        flat = torch.cat([t.reshape(-1).to(self.bucket_dtype) for t in tensors])
+        buckets, rest = self.alias_buckets(tensors)
+        for bkt in buckets:
+            self.dist.all_reduce(bkt, group=self.group)
+            self.bytes_reduced += bkt.numel() * bkt.element_size()
+            bkt.div_(self.world)
+        if not rest:
+            return
+        flat = torch.cat([t.reshape(-1).to(self.bucket_dtype) for t in rest])
         self.dist.all_reduce(flat, group=self.group)
         self.bytes_reduced += flat.numel() * flat.element_size()
         flat.div_(self.world)
         views, off = [], 0
-        for t in tensors:
+        for t in rest:
             n = t.numel()
             views.append(flat[off:off + n].view_as(t))
             off += n
-        torch._foreach_copy_(tensors, views)
+        torch._foreach_copy_(rest, views)
 
 
 class TrainStepGraph:
