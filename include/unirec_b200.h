@@ -235,6 +235,13 @@ int unirec_inject_tokens(const int64_t* input_ids, int64_t B, int64_t S, const i
                          const void* tokens, int tokens_fp32, void* text_embeds, int text_fp32, int64_t ld_text,
                          int64_t Hd, void* stream);
 
+/* Reconstruction-quality metrics (evaluation/evaluate_item_qformer.py:66-95), one pass, no synchronisation:
+ * over the rows (item, field) with mask != 0:  acc[0] += ||rec - orig||^2,  acc[1] += cosine(rec, orig),  acc[2] += 1.
+ * rec [rows, E] fp32 (rec_fp32 = 1) or bf16, orig fp32 [rows, E], mask fp32 [rows], acc = 3 doubles on the device
+ * (accumulated: zero them before the first batch).  masked MSE of a batch (:74-75) = acc[0] / acc[2]. */
+int unirec_reconstruction_metrics(const void* rec, int rec_fp32, const float* orig, const float* mask, int64_t rows,
+                                  int64_t E, float eps, double* acc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

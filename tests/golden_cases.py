@@ -38,3 +38,8 @@ USER_CASES = {
 }
 
 SCORING_CASE = dict(users=8, cands=4096, dim=1024, k=100, seed=13)
+
+# evaluation/evaluate_item_qformer.py:40-103 run on the 'small' item model over 23 synthetic items in batches of 8
+# (the last batch is ragged); tests/golden/eval_metrics.npz holds the reference function's two result numbers
+EVAL_CASE = dict(item_case="small", batch_size=8,
+                 input=dict(batch=23, num_fields=6, dim=256, seed=77, clip_field=2, presence=0.7))

@@ -43,3 +43,22 @@ def test_inject_tokens_oracle_semantics():
     assert torch.equal(out[0, 4], toks[0, 1, 2]) and torch.equal(out[0, 5], toks[0, 1, 2])     # every occurrence
     assert torch.equal(out[1, 0], toks[1, 1, 1]) and torch.equal(out[1, 8], toks[1, 0, 2])
     assert float(out[0, 0].abs().sum()) == 0 and float(out[1, 1:8].abs().sum()) == 0
+
+
+def test_eval_oracle_matches_reference_golden():
+    """oracle/eval_oracle.py over the CPU item-Q-Former oracle reproduces the two numbers the UNMODIFIED reference
+    function evaluate_reconstruction_quality returned (oracle/pin_eval_against_reference.py)."""
+    from oracle import eval_oracle as EO
+    from oracle import qformer_oracle as O
+    from tests.golden_cases import EVAL_CASE, ITEM_CASES
+    from unirec_b200 import synth
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "eval_metrics.npz"))
+    c = ITEM_CASES[EVAL_CASE["item_case"]]
+    sd = synth.item_qformer_state_dict(**c["model"], seed=c["seed"], attn_std=c["attn_std"])
+    x, mask = synth.item_fields(**EVAL_CASE["input"])
+    with torch.no_grad():
+        got = EO.reconstruction_quality(
+            lambda f, m: O.item_qformer_forward(sd, f, m, num_heads=c["heads"])["reconstructed_fields"], x, mask,
+            EVAL_CASE["batch_size"])
+    assert abs(got["val_recon_loss"] - float(z["val_recon_loss"])) <= 2e-5 * abs(float(z["val_recon_loss"]))
+    assert abs(got["avg_cosine_similarity"] - float(z["avg_cosine_similarity"])) <= 2e-6

@@ -157,3 +157,50 @@ def test_list_scores_rejects_bad_arguments():
         ops.list_scores(u, u, torch.randn(4, 3, 64, device=DEV).to(torch.bfloat16))   # mixed dtypes
     with pytest.raises(RuntimeError):
         ops.list_scores(u[:, :60], u[:, :60], torch.randn(4, 3, 60, device=DEV))      # D % 8 != 0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_reconstruction_metrics_kernel_matches_oracle(dtype):
+    from oracle import eval_oracle as EO
+    from unirec_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    B, F_, E = 300, 14, 1024
+    orig = torch.randn(B, F_, E, generator=g)
+    orig[:, 7, 768:] = 0
+    rec = (orig * 0.8 + 0.5 * torch.randn(B, F_, E, generator=g)).to(dtype)
+    mask = (torch.rand(B, F_, generator=g) < 0.7).long()
+    mask[3] = 0
+    loss, cos_sum, n = EO.batch_metrics(rec, orig, mask)
+    acc = ops.reconstruction_metrics(rec.to(DEV), orig.to(DEV), mask.to(DEV)).cpu()
+    assert int(acc[2]) == n == int(mask.sum())
+    assert abs(float(acc[0]) / n - loss) <= 1e-5 * loss
+    assert abs(float(acc[1]) - cos_sum) <= 1e-5 * abs(cos_sum)
+    # accumulation over batches into the same three doubles
+    acc2 = torch.zeros(3, device=DEV, dtype=torch.float64)
+    for lo in range(0, B, 128):
+        ops.reconstruction_metrics(rec[lo:lo + 128].to(DEV), orig[lo:lo + 128].to(DEV), mask[lo:lo + 128].to(DEV), acc2)
+    torch.testing.assert_close(acc2.cpu(), acc, rtol=1e-6, atol=0)
+
+
+def test_evaluate_reconstruction_matches_reference_golden():
+    """The evaluation loop on the CUDA path against the two numbers of the unmodified reference function."""
+    from tests.golden_cases import EVAL_CASE, ITEM_CASES
+    from unirec_b200 import synth
+    from unirec_b200.evaluation import evaluate_reconstruction
+    from unirec_b200.modules import QFormerForItemRepresentation
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "eval_metrics.npz"))
+    c = ITEM_CASES[EVAL_CASE["item_case"]]
+    mk = c["model"]
+    sd = synth.item_qformer_state_dict(**mk, seed=c["seed"], attn_std=c["attn_std"])
+    model = QFormerForItemRepresentation(hidden_size=mk["hidden"], num_hidden_layers=mk["layers"],
+                                         num_attention_heads=c["heads"], intermediate_size=mk["inter"],
+                                         num_query_tokens=mk["num_query"], field_embedding_dim=mk["field_dim"],
+                                         num_fields=mk["num_fields"])
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).eval()
+    x, mask = synth.item_fields(**EVAL_CASE["input"])                       # host tensors, like the cached files
+    got = evaluate_reconstruction(model, x, mask, batch_size=EVAL_CASE["batch_size"])
+    # bf16 activations: the reconstruction differs from fp32 by ~1e-2 relative per element; the loss is a mean of
+    # squares dominated by the targets' own energy
+    assert abs(got["val_recon_loss"] - float(z["val_recon_loss"])) <= 5e-3 * float(z["val_recon_loss"]), got
+    assert abs(got["avg_cosine_similarity"] - float(z["avg_cosine_similarity"])) <= 2e-3, got

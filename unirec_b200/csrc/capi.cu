@@ -65,6 +65,9 @@ int inject_tokens(const long long* input_ids, long long B, long long S, const lo
                   const void* tokens, int tokens_fp32, void* text_embeds, int text_fp32, long long ld_text, long long Hd,
                   cudaStream_t stream);
 
+int reconstruction_metrics(const void* rec, int rec_fp32, const float* orig, const float* mask, long long rows, long long E,
+                           float eps, double* acc, cudaStream_t stream);
+
 std::atomic<long long> g_launch_count{0};
 }  // namespace unirec
 
@@ -229,6 +232,11 @@ int unirec_inject_tokens(const int64_t* input_ids, int64_t B, int64_t S, const i
     COUNTED(inject_tokens(reinterpret_cast<const long long*>(input_ids), B, S, reinterpret_cast<const long long*>(token_ids),
                           num_slots, tokens, tokens_fp32, text_embeds, text_fp32, ld_text, Hd,
                           static_cast<cudaStream_t>(stream)));
+}
+
+int unirec_reconstruction_metrics(const void* rec, int rec_fp32, const float* orig, const float* mask, int64_t rows,
+                                  int64_t E, float eps, double* acc, void* stream) {
+    COUNTED(reconstruction_metrics(rec, rec_fp32, orig, mask, rows, E, eps, acc, static_cast<cudaStream_t>(stream)));
 }
 
 }  // extern "C"

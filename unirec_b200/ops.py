@@ -584,3 +584,28 @@ def inject_tokens(text_embeds: torch.Tensor, input_ids: torch.Tensor, token_ids:
                                           _stream())
     _lib.check(rc, "unirec_inject_tokens")
     return text_embeds
+
+
+def reconstruction_metrics(reconstructed: torch.Tensor, original: torch.Tensor, attention_mask: torch.Tensor,
+                           acc: Optional[torch.Tensor] = None, eps: float = 1e-12) -> torch.Tensor:
+    """acc (float64 [3], created zeroed if None) += [sum of squared errors, sum of cosine similarities, count] over the
+    (item, field) rows with attention_mask != 0.  reconstructed [B, F, E] fp32 / bf16, original fp32 [B, F, E]."""
+    if reconstructed.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError("reconstruction_metrics: reconstructed must be fp32 or bf16")
+    _req(reconstructed, reconstructed.dtype, "reconstruction_metrics.reconstructed")
+    _req(original, torch.float32, "reconstruction_metrics.original")
+    if reconstructed.shape != original.shape or reconstructed.dim() != 3:
+        raise RuntimeError("reconstruction_metrics: expected two [B, F, E] tensors")
+    B, F_, E = reconstructed.shape
+    if not attention_mask.is_cuda or tuple(attention_mask.shape) != (B, F_):
+        raise RuntimeError("reconstruction_metrics: attention_mask must be a CUDA tensor [B, F]")
+    m = attention_mask.to(torch.float32).contiguous()
+    if acc is None:
+        acc = torch.zeros(3, device=reconstructed.device, dtype=torch.float64)
+    _req(acc, torch.float64, "reconstruction_metrics.acc")
+    rc = _lib.load().unirec_reconstruction_metrics(reconstructed.contiguous().data_ptr(),
+                                                   1 if reconstructed.dtype == torch.float32 else 0,
+                                                   original.contiguous().data_ptr(), m.data_ptr(), B * F_, E, float(eps),
+                                                   acc.data_ptr(), _stream())
+    _lib.check(rc, "unirec_reconstruction_metrics")
+    return acc
