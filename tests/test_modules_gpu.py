@@ -180,3 +180,20 @@ def test_train_mode_dropout_entry_points():
     u.train()
     with pytest.raises(NotImplementedError):
         u(torch.randn(2, 64, 256, device=DEV), torch.ones(2, 64, device=DEV))
+
+
+def test_generate_item_tokens_streamed_matches_in_memory_generation():
+    """Host-to-host streamed generation (copies on their own streams, ragged last chunk) returns exactly what the
+    in-memory loop returns."""
+    from unirec_b200 import synth
+    from unirec_b200.modules import QFormerForItemRepresentation
+    from unirec_b200.pipeline import generate_item_tokens, generate_item_tokens_streamed
+    dev = torch.device("cuda:0")
+    model = QFormerForItemRepresentation(hidden_size=256, num_hidden_layers=2, num_attention_heads=4,
+                                         intermediate_size=512, field_embedding_dim=256, num_fields=6).to(dev).eval()
+    x, m = synth.item_fields(batch=1000, num_fields=6, dim=256, seed=8, clip_field=2, presence=0.8)
+    tok_ref, pooled_ref, _ = generate_item_tokens(model, x.to(dev), mask=m.to(dev), batch_size=192)
+    out = torch.empty(1000, 32, 256, dtype=torch.bfloat16).pin_memory()
+    pooled = generate_item_tokens_streamed(model, x.pin_memory(), m.pin_memory(), out, batch_size=192, depth=2)
+    torch.cuda.synchronize()
+    assert torch.equal(out, tok_ref.cpu()) and torch.equal(pooled, pooled_ref)

@@ -3,6 +3,8 @@
   * generate_item_tokens  - batched item-query-token generation, item-range sharded (config 3;
                             intent of data_processing/generate_all_item_embeddings.py:238-267, working
                             equivalent data_processing/qformer_inference.py:143-168): no collective.
+  * generate_item_tokens_streamed - the same loop from pinned host memory to pinned host memory with the two
+                            transfers on their own streams (the reference's copy -> model -> .cpu() pattern).
   * NestedRanker          - user-sequence build (models/user_sequence_encoder.py:128-140) -> UserQFormer
                             -> pooled scoring vector -> cosine top-k over a row-sharded candidate pool with
                             an NCCL all-gather + merge of the per-GPU top-k lists (config 5).
@@ -68,6 +70,54 @@ def generate_item_tokens(model: QFormerForItemRepresentation, fields: FieldSourc
             tokens_out[c0 - lo:c1 - lo].copy_(tok)
         pooled_out[c0 - lo:c1 - lo].copy_(ops.mean_tokens(tok))
     return (tokens_out if keep_tokens else None), pooled_out, (lo, hi)
+
+
+@torch.no_grad()
+def generate_item_tokens_streamed(model: QFormerForItemRepresentation, fields_host: torch.Tensor,
+                                  mask_host: Optional[torch.Tensor], tokens_host_out: torch.Tensor, *,
+                                  batch_size: int = 4096, pooled_out: Optional[torch.Tensor] = None, depth: int = 2,
+                                  device: Optional[torch.device] = None) -> torch.Tensor:
+    """Host-to-host item-token generation - the I/O pattern of the reference loop (data_processing/
+    qformer_inference.py:143-168: a host batch goes to the device, `query_outputs` comes back with `.cpu()`), with the
+    transfers taken off the critical path: the host-to-device copy of chunk i+1 and the device-to-host copy of chunk i-1
+    run on their own streams while chunk i is encoded (the reference serialises copy -> model -> copy and synchronises
+    per batch).  fields_host [N, F, E] fp32 and tokens_host_out [N, Q, H] bf16 should be PINNED for the copies to be
+    asynchronous; at most `depth` chunks are in flight.  Returns pooled candidate vectors bf16 [N, H] on the device
+    (`pooled_out` if given).  The caller's stream is synchronised with the last copy on return."""
+    dev = device or next(model.parameters()).device
+    if dev.type != "cuda":
+        raise RuntimeError("generate_item_tokens_streamed: the model must live on a CUDA device (no CPU path)")
+    n = fields_host.shape[0]
+    H = model.config.hidden_size
+    if pooled_out is None:
+        pooled_out = torch.empty(n, H, device=dev, dtype=torch.bfloat16)
+    cur = torch.cuda.current_stream(dev)
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    s_in.wait_stream(cur)
+    s_out.wait_stream(cur)
+    done = []                                            # per chunk: event "encoded and copied out"
+    for i, c0 in enumerate(range(0, n, batch_size)):
+        c1 = min(c0 + batch_size, n)
+        if i >= depth:
+            done[i - depth].synchronize()                # bounds the device memory held by chunks in flight
+        with torch.cuda.stream(s_in):
+            x = fields_host[c0:c1].to(dev, non_blocking=True)
+            m = None if mask_host is None else mask_host[c0:c1].to(dev, non_blocking=True)
+            ev_in = s_in.record_event()
+        cur.wait_event(ev_in)
+        x.record_stream(cur)
+        if m is not None:
+            m.record_stream(cur)
+        tok = model.encode_query_tokens(x, m, out_dtype=torch.bfloat16)
+        pooled_out[c0:c1].copy_(ops.mean_tokens(tok))
+        ev_c = cur.record_event()
+        s_out.wait_event(ev_c)
+        with torch.cuda.stream(s_out):
+            tokens_host_out[c0:c1].copy_(tok, non_blocking=True)
+            done.append(s_out.record_event())
+        tok.record_stream(s_out)
+    cur.wait_stream(s_out)
+    return pooled_out
 
 
 def gather_lists(scores: torch.Tensor, idx: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
