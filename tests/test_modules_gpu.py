@@ -197,3 +197,42 @@ def test_generate_item_tokens_streamed_matches_in_memory_generation():
     pooled = generate_item_tokens_streamed(model, x.pin_memory(), m.pin_memory(), out, batch_size=192, depth=2)
     torch.cuda.synchronize()
     assert torch.equal(out, tok_ref.cpu()) and torch.equal(pooled, pooled_ref)
+
+
+@pytest.mark.parametrize("kind", ["item", "user"])
+def test_layer0_hoist_is_the_same_arithmetic(kind):
+    """The batch-invariant head of the encoder (layer 0's self-attention block + cross-attention query projection)
+    computed once on Q rows gives what the per-batch-element computation gives; the cache follows weight updates."""
+    from unirec_b200.modules import QFormerForItemRepresentation, UserQFormer
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    if kind == "item":
+        model = QFormerForItemRepresentation(hidden_size=256, num_hidden_layers=3, num_attention_heads=4,
+                                             intermediate_size=512, field_embedding_dim=256, num_fields=6).to(dev).eval()
+        x, m = synth.item_fields(batch=70, num_fields=6, dim=256, seed=9, clip_field=2, presence=0.7)
+        args = (x.to(dev), m.to(dev))
+        run = lambda: model(*args)["query_outputs"]
+    else:
+        model = UserQFormer(hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=512,
+                            input_embedding_dim=256, num_item_tokens_to_predict=8).to(dev).eval()
+        g = torch.Generator().manual_seed(4)
+        seq = torch.randn(9, 200, 256, generator=g).to(dev)
+        mask = (torch.arange(200).unsqueeze(0) < torch.randint(1, 201, (9, 1), generator=g)).float().to(dev)
+        run = lambda: model(seq, mask)
+    model.qformer.hoist_layer0 = False
+    ref = run().float()
+    model.qformer.hoist_layer0 = True
+    got = run().float()
+    assert "l0" in model.qformer.packed()
+    diff = (got - ref).abs()
+    print(kind, "max", float(diff.max()), "mean", float(diff.mean()))
+    assert float(diff.max()) <= 0.03 and float(diff.mean()) <= 1e-3
+    # the cached rows follow the parameters: change the learned queries and a layer-0 weight in place
+    with torch.no_grad():
+        model.query_embeddings.add_(0.25)
+        model.qformer.encoder.layer[0].attention.output.dense.weight.mul_(1.5)
+    got2 = run().float()
+    model.qformer.hoist_layer0 = False
+    ref2 = run().float()
+    assert float((got2 - got).abs().max()) > 1e-2
+    assert float((got2 - ref2).abs().max()) <= 0.03 and float((got2 - ref2).abs().mean()) <= 1e-3

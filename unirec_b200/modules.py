@@ -114,6 +114,7 @@ class QFormerBackbone(nn.Module):
         self._init_weights()
         self._pack: Optional[dict] = None
         self._pack_key = None
+        self.hoist_layer0 = True        # compute the batch-invariant head of the encoder once (see `encode`)
 
     def _init_weights(self):
         # reference rule, models/qformer.py:664-674: N(0, initializer_range) weights, zero bias, LN (1, 0)
@@ -189,6 +190,29 @@ class QFormerBackbone(nn.Module):
         self._pack, self._pack_key = pack, key
         return pack
 
+    def _layer0_invariants(self, pk: dict, query_embeddings: torch.Tensor, prelayernorm_dtype: torch.dtype) -> dict:
+        """The batch-invariant head of the encoder on Q rows: pre1 = dense(self-attention(LN(queries))) + LN(queries)
+        (the input of layer 0's first LayerNorm) and qc = layer 0's cross-attention query projection of LN1(pre1).
+        Cached in the weight pack (rebuilt with it) and keyed by the query tensor's version."""
+        key = (query_embeddings.data_ptr(), query_embeddings._version, prelayernorm_dtype)
+        inv = pk.get("l0")
+        if inv is not None and inv["key"] == key:
+            return inv
+        cfg = self.config
+        H, heads = cfg.hidden_size, cfg.num_attention_heads
+        Q = query_embeddings.shape[1]
+        L = pk["layers"][0]
+        q0 = query_embeddings.detach().reshape(Q, H).float().contiguous()
+        h0 = ops.layernorm(q0, pk["emb_g"], pk["emb_b"], cfg.layer_norm_eps)
+        qkv = ops.linear(h0, L["w_qkv"], L["b_qkv"])
+        ctx = ops.attention(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], batch=1, num_heads=heads, nq=Q, nk=Q)
+        pre1 = ops.linear(ctx, L["w_o"], L["b_o"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=h0,
+                          out_dtype=prelayernorm_dtype)
+        h1 = ops.layernorm(pre1, L["ln1_g"], L["ln1_b"], cfg.layer_norm_eps)
+        inv = {"key": key, "pre1": pre1, "qc": ops.linear(h1, L["w_qc"], L["b_qc"])}
+        pk["l0"] = inv
+        return inv
+
     # -------------------------------------------------------------------------------------- forward
     def encode(self, query_embeddings: torch.Tensor, encoder_hidden_states: torch.Tensor,
                encoder_attention_mask: Optional[torch.Tensor], out_dtype: torch.dtype = torch.float32,
@@ -216,23 +240,40 @@ class QFormerBackbone(nn.Module):
         # cross-attention K/V of every cross layer in one GEMM (the encoder input is layer-invariant)
         kv_all = ops.linear(enc, pk["w_kv_all"], pk["b_kv_all"]) if pk["w_kv_all"] is not None else None
 
-        # BertEmbeddings query-only branch: LayerNorm of the learned tokens, batch-invariant -> broadcast
-        q0 = query_embeddings.detach().reshape(Q, H).float().contiguous()
-        h = ops.layernorm(q0, pk["emb_g"], pk["emb_b"], cfg.layer_norm_eps, rows=B * Q, in_row_mod=Q)
-
+        # BertEmbeddings query-only branch: LayerNorm of the learned tokens - batch-invariant, and so is everything up
+        # to the first cross-attention: layer 0's whole self-attention block and its cross-attention QUERY projection
+        # see the same [Q, H] rows for every batch element.  They are computed once on Q rows per (weights, queries)
+        # version and cached (`_layer0_invariants`); per call only the LayerNorm that ends the block runs on B*Q rows
+        # (it broadcasts its Q input rows) and the cross-attention reads one shared set of queries (q_broadcast).
+        # Exactly the reference's arithmetic (models/qformer.py:103-108, 417-432) with the B-fold repetition removed:
+        # 3.1 % of the item model's FLOPs, 1.9 % of the user model's.
         nl = len(pk["layers"])
+        hoist = self.hoist_layer0 and nl > 0 and pk["layers"][0]["cross"]
+        if hoist:
+            inv = self._layer0_invariants(pk, query_embeddings, prelayernorm_dtype)
+        else:
+            q0 = query_embeddings.detach().reshape(Q, H).float().contiguous()
+            h = ops.layernorm(q0, pk["emb_g"], pk["emb_b"], cfg.layer_norm_eps, rows=B * Q, in_row_mod=Q)
+
         for li, L in enumerate(pk["layers"]):
             last = li == nl - 1
-            qkv = ops.linear(h, L["w_qkv"], L["b_qkv"])
-            ctx = ops.attention(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], batch=B, num_heads=heads, nq=Q, nk=Q)
-            pre = ops.linear(ctx, L["w_o"], L["b_o"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=h,
-                             out_dtype=prelayernorm_dtype)
-            h = ops.layernorm(pre, L["ln1_g"], L["ln1_b"], cfg.layer_norm_eps)
+            if li == 0 and hoist:
+                h = ops.layernorm(inv["pre1"], L["ln1_g"], L["ln1_b"], cfg.layer_norm_eps, rows=B * Q, in_row_mod=Q)
+            else:
+                qkv = ops.linear(h, L["w_qkv"], L["b_qkv"])
+                ctx = ops.attention(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], batch=B, num_heads=heads, nq=Q, nk=Q)
+                pre = ops.linear(ctx, L["w_o"], L["b_o"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=h,
+                                 out_dtype=prelayernorm_dtype)
+                h = ops.layernorm(pre, L["ln1_g"], L["ln1_b"], cfg.layer_norm_eps)
             if L["cross"]:
-                qc = ops.linear(h, L["w_qc"], L["b_qc"])
                 off = L["kv_slot"] * 2 * H
-                ctx = ops.attention(qc, kv_all[:, off:off + H], kv_all[:, off + H:off + 2 * H], batch=B,
-                                    num_heads=heads, nq=Q, nk=S, key_mask=mask)
+                if li == 0 and hoist:
+                    ctx = ops.attention(inv["qc"], kv_all[:, off:off + H], kv_all[:, off + H:off + 2 * H], batch=B,
+                                        num_heads=heads, nq=Q, nk=S, key_mask=mask, q_broadcast=True)
+                else:
+                    qc = ops.linear(h, L["w_qc"], L["b_qc"])
+                    ctx = ops.attention(qc, kv_all[:, off:off + H], kv_all[:, off + H:off + 2 * H], batch=B,
+                                        num_heads=heads, nq=Q, nk=S, key_mask=mask)
                 pre = ops.linear(ctx, L["w_oc"], L["b_oc"], epilogue=ops.EPI_BIAS_RESIDUAL, residual=h,
                                  out_dtype=prelayernorm_dtype)
                 h = ops.layernorm(pre, L["ln2_g"], L["ln2_b"], cfg.layer_norm_eps)
