@@ -98,3 +98,34 @@ def test_pickle_to_token_table(tmp_path):
     t = formats.pickle_to_token_table(p, str(tmp_path / "tbl"))
     assert t.item_ids == ["x", "y", "z", "u", "v", "w"]
     assert torch.equal(t.read(), tok.to(torch.bfloat16))
+
+
+def test_item_checkpoint_round_trip(tmp_path):
+    """The reference's checkpoint dictionary ({'model_state_dict', 'config', 'field_names'},
+    training/item_qformer_training.py:176-184) written and read back: same config attributes the reference's loaders
+    read (qformer_inference.py:36-45), same weights, strict key match; missing 'field_names' raises ValueError."""
+    import pytest
+    import torch
+    from unirec_b200 import formats
+    from unirec_b200.modules import QFormerForItemRepresentation
+    fields = ["brand", "categories", "main_image", "price", "title"]
+    model = QFormerForItemRepresentation(hidden_size=128, num_hidden_layers=2, num_attention_heads=2,
+                                         intermediate_size=256, num_query_tokens=8, field_embedding_dim=96,
+                                         num_fields=len(fields), dropout=0.15)
+    path = str(tmp_path / "ckpt" / "best_qformer_model.pth")
+    formats.save_item_checkpoint(path, model, fields)
+    raw = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(raw) == {"model_state_dict", "config", "field_names"}
+    cfg = raw["config"]
+    assert (cfg.hidden_size, cfg.num_hidden_layers, cfg.num_attention_heads, cfg.intermediate_size, cfg.query_length,
+            cfg.encoder_width, cfg.hidden_dropout_prob) == (128, 2, 2, 256, 8, 96, 0.15)
+    loaded, names = formats.load_item_checkpoint(path)
+    assert names == fields and not loaded.training and loaded.num_query_tokens == 8
+    sd0, sd1 = model.state_dict(), loaded.state_dict()
+    assert list(sd0) == list(sd1)
+    for k in sd0:
+        assert torch.equal(sd0[k], sd1[k]), k
+    del raw["field_names"]
+    torch.save(raw, path)
+    with pytest.raises(ValueError):
+        formats.load_item_checkpoint(path)

@@ -205,3 +205,37 @@ def pickle_to_token_table(pickle_path: str, directory: str) -> TokenTable:
     w.write_shard(0, tok)
     w.close(item_ids=ids)
     return TokenTable(directory)
+
+
+# --------------------------------------------------------------------------------------------- checkpoints
+def save_item_checkpoint(path: str, model, field_names: Sequence[str]) -> None:
+    """Write the reference's checkpoint dictionary (training/item_qformer_training.py:176-184):
+    {'model_state_dict', 'config' (the BertConfig object), 'field_names'} - loadable by the reference's
+    `load_qformer_model` (data_processing/qformer_inference.py:13-55) and `load_trained_model`
+    (evaluation/evaluate_item_qformer.py:14-38) as well as by `load_item_checkpoint` below."""
+    d = os.path.dirname(os.path.abspath(path))
+    os.makedirs(d, exist_ok=True)
+    torch.save({"model_state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()},
+                "config": model.config, "field_names": list(field_names)}, path)
+
+
+def load_item_checkpoint(path: str, device=None):
+    """The reference's loaders (qformer_inference.py:13-55 / evaluate_item_qformer.py:14-38) over the CUDA modules:
+    rebuild the model from the stored config and field list, load the weights (same keys, strict), eval().
+    Returns (model, field_names).  Raises ValueError when the checkpoint holds no 'field_names' (:21-22)."""
+    from .modules import QFormerForItemRepresentation
+    ckpt = torch.load(path, map_location="cpu", weights_only=False)
+    cfg = ckpt["config"]
+    field_names = ckpt.get("field_names")
+    if field_names is None:
+        raise ValueError("Checkpoint must contain 'field_names'")
+    model = QFormerForItemRepresentation(
+        hidden_size=cfg.hidden_size, num_hidden_layers=cfg.num_hidden_layers,
+        num_attention_heads=cfg.num_attention_heads, intermediate_size=cfg.intermediate_size,
+        num_query_tokens=cfg.query_length, field_embedding_dim=cfg.encoder_width, num_fields=len(field_names),
+        dropout=cfg.hidden_dropout_prob)
+    model.load_state_dict(ckpt["model_state_dict"])
+    if device is not None:
+        model = model.to(device)
+    model.eval()
+    return model, field_names
