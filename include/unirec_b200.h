@@ -150,6 +150,19 @@ int unirec_layernorm_backward(const void* x, int64_t ldx, const void* dy, int64_
                               const float* gamma, float eps, void* dx, int64_t lddx, float* dgamma, float* dbeta,
                               int64_t rows, int64_t H, void* stream);
 
+/* unirec_layernorm_backward with the two things that always follow it in the reference's blocks
+ * "LayerNorm(dropout(dense(x)) + input)" (models/qformer.py:285-289, :371-375) fused in:
+ *   dx_drop (may be NULL) = dx o mask(thr16, seed, site) * scale - the gradient of dense(x) behind its dropout
+ *                           (thr16 = 0: a plain copy of dx; the mask is applied to the bf16-rounded dx, like
+ *                           unirec_dropout_backward on the stored tensor);
+ *   dbias (may be NULL, fp32 [H], atomically accumulated) += column sums of dx_drop (of dx when dx_drop is NULL) - the
+ *                           gradient of that dense layer's bias. */
+int unirec_layernorm_backward_fused(const void* x, int64_t ldx, const void* dy, int64_t lddy, const void* dy2,
+                                    int64_t lddy2, const float* gamma, float eps, void* dx, int64_t lddx, float* dgamma,
+                                    float* dbeta, int64_t rows, int64_t H, uint32_t thr16, uint64_t seed, uint32_t site,
+                                    const uint64_t* seed_offset, void* dx_drop, int64_t lddrop, float* dbias,
+                                    void* stream);
+
 /* Backward of unirec_attention for nq <= 64 and nk <= 64 (item self- and cross-attention): dq/dk/dv bf16 with the
  * layouts of q/k/v (row strides lddq/lddk/lddv); probabilities are recomputed from q, k and key_mask. */
 int unirec_attention_backward(const void* q, int64_t ldq, int64_t q_batch_rows,

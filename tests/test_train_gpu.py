@@ -421,3 +421,34 @@ def test_train_step_graph_draws_fresh_dropout_masks_per_replay():
     c = float(tg.step(x, m, x, x))
     assert abs(a - c) <= 1e-5 * abs(a) + 1e-6, (a, c)  # same masks (split-K atomics reorder fp32 sums only)
     torch.testing.assert_close(tg.grad_tensors()[5], grad_a, rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize("H", [256, 1024])
+def test_layernorm_backward_fused_dropout_and_bias_sums(H):
+    """unirec_layernorm_backward_fused: dx is the plain kernel's dx, dx_drop is dropout_backward(dx) bit for bit, dbias
+    is the column sum of what the consumer GEMMs read (dx_drop, or dx without dropout)."""
+    from unirec_b200 import ops
+    rows = 2500
+    x = _randn(rows, H, seed=41, scale=2.0, dtype=torch.bfloat16)
+    dy = _randn(rows, H, seed=42, dtype=torch.bfloat16)
+    dy2 = _randn(rows, H, seed=43, dtype=torch.bfloat16)
+    g = _randn(H, seed=44, scale=0.1) + 1.0
+    st = (ops.dropout_threshold(0.2), 777, 21)
+
+    def zeros():
+        return torch.zeros(H, device=DEV), torch.zeros(H, device=DEV)
+    dg0, db0 = zeros()
+    dx0 = ops.layernorm_backward(x, dy, g, 1e-12, dg0, db0, dy2=dy2)
+    dg1, db1 = zeros()
+    dbias1 = torch.zeros(H, device=DEV)
+    dx1, dxd1 = ops.layernorm_backward(x, dy, g, 1e-12, dg1, db1, dy2=dy2, dropout=st, dbias=dbias1)
+    assert torch.equal(dx1, dx0)
+    assert torch.equal(dxd1, ops.dropout_backward(dx0, st))
+    torch.testing.assert_close(dg1, dg0, rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(db1, db0, rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(dbias1, dxd1.float().sum(0), rtol=1e-4, atol=2e-3)
+    dg2, db2 = zeros()
+    dbias2 = torch.full((H,), 0.5, device=DEV)
+    dx2 = ops.layernorm_backward(x, dy, g, 1e-12, dg2, db2, dy2=dy2, dbias=dbias2)       # no dropout: sums of dx, accumulated
+    assert torch.equal(dx2, dx0)
+    torch.testing.assert_close(dbias2, 0.5 + dx0.float().sum(0), rtol=1e-4, atol=2e-3)

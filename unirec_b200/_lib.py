@@ -48,6 +48,9 @@ _SIGNATURES = {
     "unirec_colsum": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "unirec_layernorm_backward": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_float,
                                           c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    "unirec_layernorm_backward_fused": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_float,
+                                                c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_uint32,
+                                                c_uint64, c_uint32, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "unirec_attention_backward": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64,
                                           c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                           c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p]),

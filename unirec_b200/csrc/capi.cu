@@ -44,7 +44,9 @@ int gelu_backward(const void* z, const void* da, void* dz, long long n, cudaStre
 int colsum(const void* x, long long ld, long long rows, long long N, float* out, cudaStream_t stream);
 int layernorm_backward(const void* x, long long ldx, const void* dy, long long lddy, const void* dy2, long long lddy2,
                        const float* gamma, float eps, void* dx, long long lddx, float* dgamma, float* dbeta,
-                       long long rows, long long H, cudaStream_t stream);
+                       long long rows, long long H, unsigned drop_thr16, unsigned long long drop_seed, unsigned drop_site,
+                       const unsigned long long* drop_seed_offset, void* dx_drop, long long lddrop, float* dbias,
+                       cudaStream_t stream);
 int attention_backward(const void* q, long long ldq, long long q_batch_rows, const void* k, long long ldk, const void* v,
                        long long ldv, long long kv_batch_rows, const float* key_mask, const void* dout, long long lddo,
                        void* dq, long long lddq, void* dk, long long lddk, void* dv, long long lddv, long long batch,
@@ -181,7 +183,17 @@ int unirec_colsum(const void* x, int64_t ld, int64_t rows, int64_t N, float* out
 int unirec_layernorm_backward(const void* x, int64_t ldx, const void* dy, int64_t lddy, const void* dy2, int64_t lddy2,
                               const float* gamma, float eps, void* dx, int64_t lddx, float* dgamma, float* dbeta,
                               int64_t rows, int64_t H, void* stream) {
-    COUNTED(layernorm_backward(x, ldx, dy, lddy, dy2, lddy2, gamma, eps, dx, lddx, dgamma, dbeta, rows, H,
+    COUNTED(layernorm_backward(x, ldx, dy, lddy, dy2, lddy2, gamma, eps, dx, lddx, dgamma, dbeta, rows, H, 0u, 0ull, 0u,
+                               nullptr, nullptr, 0, nullptr, static_cast<cudaStream_t>(stream)));
+}
+
+int unirec_layernorm_backward_fused(const void* x, int64_t ldx, const void* dy, int64_t lddy, const void* dy2,
+                                    int64_t lddy2, const float* gamma, float eps, void* dx, int64_t lddx, float* dgamma,
+                                    float* dbeta, int64_t rows, int64_t H, uint32_t thr16, uint64_t seed, uint32_t site,
+                                    const uint64_t* seed_offset, void* dx_drop, int64_t lddrop, float* dbias,
+                                    void* stream) {
+    COUNTED(layernorm_backward(x, ldx, dy, lddy, dy2, lddy2, gamma, eps, dx, lddx, dgamma, dbeta, rows, H, thr16, seed,
+                               site, reinterpret_cast<const unsigned long long*>(seed_offset), dx_drop, lddrop, dbias,
                                static_cast<cudaStream_t>(stream)));
 }
 

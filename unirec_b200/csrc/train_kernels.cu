@@ -181,9 +181,10 @@ __global__ void __launch_bounds__(512, 1)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ dy, long long lddy,
                      const __nv_bfloat16* __restrict__ dy2, long long lddy2, const float* __restrict__ gamma, float eps,
                      __nv_bfloat16* __restrict__ dx, long long lddx, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                     int rows, int H, int tpg) {
+                     int rows, int H, int tpg, const DropoutParams drop_in, __nv_bfloat16* __restrict__ dx_drop,
+                     long long lddrop, float* __restrict__ dbias) {
     __shared__ float s_x[4][LNB_MAX_WARPS][2 * LNB_ROWS];      // [exchange slot][warp][value]
-    __shared__ float s_acc[2][1024];                           // column sums of the CTA's groups
+    __shared__ float s_acc[3][1024];                           // column sums of the CTA's groups
     const int groups = blockDim.x / tpg;
     const int group = threadIdx.x / tpg;
     const int tg = threadIdx.x - group * tpg;                  // thread inside the group
@@ -192,10 +193,13 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const _
     const int col = tg * 8;
     const bool active = col < H;                               // tpg * 8 >= H; the last warp of a group may be partly idle
     const float inv_h = 1.0f / static_cast<float>(H);
-    for (int i = threadIdx.x; i < 2 * 1024; i += blockDim.x) (&s_acc[0][0])[i] = 0.f;
-    float gm[8], adg[8], adb[8];
+    for (int i = threadIdx.x; i < 3 * 1024; i += blockDim.x) (&s_acc[0][0])[i] = 0.f;
+    // optional second output: dx_drop = dx o mask * scale - the gradient of the dense layer whose dropped output entered this
+    // LayerNorm's input sum (models/qformer.py:287-288 / :373-374 backwards) - and its column sums (that layer's bias gradient)
+    const DropoutParams drop = dropout_resolve(drop_in);
+    float gm[8], adg[8], adb[8], ads[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { gm[j] = 0.f; adg[j] = 0.f; adb[j] = 0.f; }
+    for (int j = 0; j < 8; ++j) { gm[j] = 0.f; adg[j] = 0.f; adb[j] = 0.f; ads[j] = 0.f; }
     if (active) {
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col));
         const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + col) + 1);
@@ -272,8 +276,32 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const _
             float o[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = rstd[r] * (d[r][j] - m1 - f[r][j] * m2);
-            *reinterpret_cast<uint4*>(dx + row * lddx + col) =
+            const uint4 packed =
                 make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+            *reinterpret_cast<uint4*>(dx + row * lddx + col) = packed;
+            if (dx_drop != nullptr) {
+                // the mask applies to the bf16-rounded gradient, exactly like dropout_backward on the stored dx
+                float q[8];
+                unpack_bf16x8(packed, q);
+                const uint32_t keep = drop.thr16 != 0
+                    ? dropout_keep8(drop, static_cast<unsigned long long>(row), static_cast<uint32_t>(col >> 3)) : 0xffffu;
+                const float sc = drop.thr16 != 0 ? drop.scale : 1.0f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) q[j] = ((keep >> j) & 1u) ? q[j] * sc : 0.f;
+                const uint4 pd =
+                    make_uint4(pack_bf16(q[0], q[1]), pack_bf16(q[2], q[3]), pack_bf16(q[4], q[5]), pack_bf16(q[6], q[7]));
+                *reinterpret_cast<uint4*>(dx_drop + row * lddrop + col) = pd;
+                if (dbias != nullptr) {
+                    unpack_bf16x8(pd, q);            // column sums of the values the consumer GEMMs will read
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) ads[j] += q[j];
+                }
+            } else if (dbias != nullptr) {
+                float q[8];
+                unpack_bf16x8(packed, q);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ads[j] += q[j];
+            }
         }
     }
     __syncthreads();                                 // s_acc is zeroed (every thread passed its zeroing loop)
@@ -282,21 +310,26 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const _
         for (int j = 0; j < 8; ++j) {
             atomicAdd(&s_acc[0][col + j], adg[j]);
             atomicAdd(&s_acc[1][col + j], adb[j]);
+            if (dbias != nullptr) atomicAdd(&s_acc[2][col + j], ads[j]);
         }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < H; i += blockDim.x) {
         atomicAdd(dgamma + i, s_acc[0][i]);
         atomicAdd(dbeta + i, s_acc[1][i]);
+        if (dbias != nullptr) atomicAdd(dbias + i, s_acc[2][i]);
     }
 }
 
 int layernorm_backward(const void* x, long long ldx, const void* dy, long long lddy, const void* dy2, long long lddy2,
                        const float* gamma, float eps, void* dx, long long lddx, float* dgamma, float* dbeta,
-                       long long rows, long long H, cudaStream_t stream) {
+                       long long rows, long long H, unsigned drop_thr16, unsigned long long drop_seed, unsigned drop_site,
+                       const unsigned long long* drop_seed_offset, void* dx_drop, long long lddrop, float* dbias,
+                       cudaStream_t stream) {
     if (x == nullptr || dy == nullptr || gamma == nullptr || dx == nullptr || dgamma == nullptr || dbeta == nullptr ||
         rows <= 0 || H <= 0 || H > 1024 || H % 8 != 0 || ldx % 8 != 0 || lddy % 8 != 0 || lddx % 8 != 0 ||
-        (dy2 != nullptr && lddy2 % 8 != 0) || rows > 2147483647LL) {
+        (dy2 != nullptr && lddy2 % 8 != 0) || rows > 2147483647LL || (dx_drop != nullptr && lddrop % 8 != 0) ||
+        drop_thr16 >= 65536u || (drop_thr16 != 0 && dx_drop == nullptr)) {
         set_last_error("layernorm_backward: bad arguments (rows=%lld H=%lld)", rows, H);
         return UNIREC_ERR_BAD_ARG;
     }
@@ -305,10 +338,13 @@ int layernorm_backward(const void* x, long long ldx, const void* dy, long long l
     if (groups > LNB_MAX_GROUPS) groups = LNB_MAX_GROUPS;
     long long blocks = (rows + groups * LNB_ROWS - 1) / (groups * LNB_ROWS);
     if (blocks > 148) blocks = 148;                                     // one CTA per SM (128 registers x 512 threads)
+    DropoutParams dp;
+    dp.thr16 = drop_thr16; dp.seed = drop_seed; dp.site = drop_site; dp.seed_offset = drop_seed_offset;
+    dp.scale = 65536.0f / (65536.0f - static_cast<float>(drop_thr16));
     layernorm_bwd_kernel<<<static_cast<unsigned>(blocks), groups * tpg, 0, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<const __nv_bfloat16*>(dy), lddy,
         reinterpret_cast<const __nv_bfloat16*>(dy2), lddy2, gamma, eps, reinterpret_cast<__nv_bfloat16*>(dx), lddx, dgamma,
-        dbeta, (int)rows, (int)H, tpg);
+        dbeta, (int)rows, (int)H, tpg, dp, reinterpret_cast<__nv_bfloat16*>(dx_drop), lddrop, dbias);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_last_error("layernorm_backward launch: %s", cudaGetErrorString(e)); return UNIREC_ERR_CUDA; }
     return UNIREC_OK;

@@ -447,9 +447,12 @@ def colsum(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
 
 
 def layernorm_backward(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, eps: float, dgamma: torch.Tensor,
-                       dbeta: torch.Tensor, dy2: Optional[torch.Tensor] = None) -> torch.Tensor:
+                       dbeta: torch.Tensor, dy2: Optional[torch.Tensor] = None, *,
+                       dropout: Optional[Tuple] = None, dbias: Optional[torch.Tensor] = None):
     """x = LayerNorm input (bf16 [rows, H]), dy (+ dy2) = gradient of its output; returns dx bf16 and accumulates
-    dgamma / dbeta (fp32 [H])."""
+    dgamma / dbeta (fp32 [H]).  Fused extras for the block LayerNorm(dropout(dense(.)) + input): with
+    dropout = (thr16, seed, site[, seed_offset]) the call returns (dx, dx_drop) where dx_drop = dropout_backward(dx);
+    dbias (fp32 [H]) accumulates the column sums of dx_drop (of dx without dropout) - the dense layer's bias gradient."""
     for t_, n in ((x, "x"), (dy, "dy")):
         _req(t_, torch.bfloat16, f"layernorm_backward.{n}")
     rows, H, ldx = _rows2d(x, "layernorm_backward.x")
@@ -459,11 +462,21 @@ def layernorm_backward(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, e
         _req(dy2, torch.bfloat16, "layernorm_backward.dy2")
         _, _, lddy2 = _rows2d(dy2, "layernorm_backward.dy2")
     dx = torch.empty(rows, H, device=x.device, dtype=torch.bfloat16)
-    rc = _lib.load().unirec_layernorm_backward(x.data_ptr(), ldx, dy.data_ptr(), lddy, _ptr(dy2), lddy2, gamma.data_ptr(),
-                                               float(eps), dx.data_ptr(), H, dgamma.data_ptr(), dbeta.data_ptr(), rows, H,
-                                               _stream())
-    _lib.check(rc, "unirec_layernorm_backward")
-    return dx
+    if dropout is None and dbias is None:
+        rc = _lib.load().unirec_layernorm_backward(x.data_ptr(), ldx, dy.data_ptr(), lddy, _ptr(dy2), lddy2,
+                                                   gamma.data_ptr(), float(eps), dx.data_ptr(), H, dgamma.data_ptr(),
+                                                   dbeta.data_ptr(), rows, H, _stream())
+        _lib.check(rc, "unirec_layernorm_backward")
+        return dx
+    thr16, seed, site, off = _drop_args(dropout)
+    dx_drop = torch.empty(rows, H, device=x.device, dtype=torch.bfloat16) if dropout is not None else None
+    if dbias is not None:
+        _req(dbias, torch.float32, "layernorm_backward.dbias")
+    rc = _lib.load().unirec_layernorm_backward_fused(
+        x.data_ptr(), ldx, dy.data_ptr(), lddy, _ptr(dy2), lddy2, gamma.data_ptr(), float(eps), dx.data_ptr(), H,
+        dgamma.data_ptr(), dbeta.data_ptr(), rows, H, thr16, seed, site, off, _ptr(dx_drop), H, _ptr(dbias), _stream())
+    _lib.check(rc, "unirec_layernorm_backward_fused")
+    return dx if dropout is None else (dx, dx_drop)
 
 
 def attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, dout: torch.Tensor, dq: torch.Tensor,

@@ -135,10 +135,6 @@ class BackboneTrainFn(torch.autograd.Function):
         def site(layer, kind):
             return None if drop is None else (drop[0], drop[1], 1 + 8 * layer + kind) + tuple(drop[2:])
 
-        def dense_grad(dpre, st):
-            # gradient of the dense output behind dropout(dense) + residual
-            return dpre if st is None else ops.dropout_backward(dpre, st)
-
         # every parameter gradient of the backbone lives in ONE zero-initialised fp32 buffer (one memset instead of ~190
         # torch.zeros launches per step - the host enqueues this step almost as slowly as the GPU runs it), laid out layer
         # by layer from the last layer to the first, so that a layer's gradients are one contiguous bucket that the
@@ -169,6 +165,20 @@ class BackboneTrainFn(torch.autograd.Function):
             ops.colsum(dy, db)
             return (ops.linear_dgrad(dy, w16) if need_dx else None), dw, db
 
+        def ln_dense_bwd(pre, dy, dy2, gamma, dgamma, dbeta, st, x_act, w16):
+            """Backward of LayerNorm(dropout(dense(x_act)) + residual): ONE kernel gives the gradient of the LayerNorm
+            input (= the residual branch's gradient), its dropped copy (= the dense output's gradient) and the dense
+            bias gradient; then the dense layer's wgrad / dgrad.  Returns (dpre, dx_act, dw, db)."""
+            db = zeros(w16.shape[0])
+            if st is None:
+                dpre = ops.layernorm_backward(pre, dy, gamma, eps, dgamma, dbeta, dy2=dy2, dbias=db)
+                ddense = dpre
+            else:
+                dpre, ddense = ops.layernorm_backward(pre, dy, gamma, eps, dgamma, dbeta, dy2=dy2, dropout=st, dbias=db)
+            dw = zeros(*w16.shape)
+            ops.linear_wgrad(ddense, x_act, dw)
+            return dpre, ops.linear_dgrad(ddense, w16), dw, db
+
         d_kv_all = torch.zeros(B * S, 2 * H * n_cross, device=dev, dtype=torch.bfloat16) if n_cross else None
         dy = d_out.reshape(M, H).to(torch.bfloat16).contiguous()
         dy2 = None
@@ -179,16 +189,16 @@ class BackboneTrainFn(torch.autograd.Function):
             bucket_lo = cursor[0]
             # ---- query FFN: h_out = LN3(a W2^T + b2 + h_mid), a = gelu(h_mid W1^T + b1)
             g["ln3_g"], g["ln3_b"] = zeros(H), zeros(H)
-            dpre3 = ops.layernorm_backward(t["pre3"], dy, L["ln3_g"], eps, g["ln3_g"], g["ln3_b"], dy2=dy2)
-            da, g["w_2"], g["b_2"] = lin_bwd(dense_grad(dpre3, site(li, K.KIND_FFN_OUT)), t["a"], L["w_2"])
+            dpre3, da, g["w_2"], g["b_2"] = ln_dense_bwd(t["pre3"], dy, dy2, L["ln3_g"], g["ln3_g"], g["ln3_b"],
+                                                         site(li, K.KIND_FFN_OUT), t["a"], L["w_2"])
             dz = ops.gelu_backward(t["z"], da)
             h_mid = t["h2"] if L["cross"] else t["h1"]
             dh_mid, g["w_1"], g["b_1"] = lin_bwd(dz, h_mid, L["w_1"])
             dy, dy2 = dpre3, dh_mid                       # gradient of h_mid = residual branch + FFN branch
             if L["cross"]:
                 g["ln2_g"], g["ln2_b"] = zeros(H), zeros(H)
-                dpre2 = ops.layernorm_backward(t["pre2"], dy, L["ln2_g"], eps, g["ln2_g"], g["ln2_b"], dy2=dy2)
-                dctxc, g["w_oc"], g["b_oc"] = lin_bwd(dense_grad(dpre2, site(li, K.KIND_CROSS_OUT)), t["ctxc"], L["w_oc"])
+                dpre2, dctxc, g["w_oc"], g["b_oc"] = ln_dense_bwd(t["pre2"], dy, dy2, L["ln2_g"], g["ln2_g"], g["ln2_b"],
+                                                                   site(li, K.KIND_CROSS_OUT), t["ctxc"], L["w_oc"])
                 off = L["kv_slot"] * 2 * H
                 dqc = torch.empty(M, H, device=dev, dtype=torch.bfloat16)
                 ops.attention_backward(t["qc"], ctx.kv_all[:, off:off + H], ctx.kv_all[:, off + H:off + 2 * H], dctxc, dqc,
@@ -198,8 +208,8 @@ class BackboneTrainFn(torch.autograd.Function):
                 dy, dy2 = dpre2, dh1
             # ---- self-attention block: h1 = LN1(ctx Wo^T + bo + h_in)
             g["ln1_g"], g["ln1_b"] = zeros(H), zeros(H)
-            dpre1 = ops.layernorm_backward(t["pre1"], dy, L["ln1_g"], eps, g["ln1_g"], g["ln1_b"], dy2=dy2)
-            dctx, g["w_o"], g["b_o"] = lin_bwd(dense_grad(dpre1, site(li, K.KIND_SELF_OUT)), t["ctx"], L["w_o"])
+            dpre1, dctx, g["w_o"], g["b_o"] = ln_dense_bwd(t["pre1"], dy, dy2, L["ln1_g"], g["ln1_g"], g["ln1_b"],
+                                                            site(li, K.KIND_SELF_OUT), t["ctx"], L["w_o"])
             qkv = t["qkv"]
             dqkv = torch.empty(M, 3 * H, device=dev, dtype=torch.bfloat16)
             ops.attention_backward(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], dctx, dqkv[:, :H], dqkv[:, H:2 * H],
