@@ -44,7 +44,7 @@ ncu)
   ls -la /tmp/*.ncu-rep >> gpurun_out/prof_users_raw.err
   ;;
 kernels)
-  timeout 300 python tools/gpu_bench_kernels.py > gpurun_out/kernels.log 2>&1; echo "kernels rc=$?" >> gpurun_out/kernels.log
+  timeout 300 python tools/gpu_bench_kernels.py attention rowwise scoring joint train > gpurun_out/kernels.log 2>&1; echo "kernels rc=$?" >> gpurun_out/kernels.log
   ;;
 esac
 done
