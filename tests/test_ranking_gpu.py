@@ -194,3 +194,32 @@ def test_nested_ranker_end_to_end_small():
     overlap = np.mean([len(set(a.tolist()) & set(b.tolist())) / k for a, b in zip(i.cpu().numpy(), ref_i.numpy())])
     print("top-100 overlap with the fp32 oracle chain:", overlap)
     assert overlap > 0.85 and float((s.cpu() - ref_s).abs().max()) < 2e-2
+
+
+@pytest.mark.parametrize("B,N", [(32768, 125_000), (16384, 250_000)])
+def test_score_topk_multi_gpu_rank_shapes(B, N):
+    """The per-rank scoring call of the 8- and 4-GPU runs of config 5: ALL users of the group (4096 per GPU) against this
+    rank's 1/G of the 1 M-row pool (B x N > 2^32 score pairs).  Properties as in the full-size test, checked on a sample
+    of user rows spread over the whole batch: descending unique in-range lists, exact cosines, completeness."""
+    from unirec_b200 import ops
+    D, k = 1024, 100
+    gen = torch.Generator(device=DEV).manual_seed(B + N)
+    C = torch.randn(N, D, device=DEV, generator=gen).to(torch.bfloat16)
+    u = torch.randn(B, D, device=DEV, generator=gen).to(torch.bfloat16)
+    s, i = ops.score_topk(u, C, k, index_base=7 * N)
+    i = i - 7 * N
+    assert tuple(s.shape) == (B, k) and bool((s[:, :-1] >= s[:, 1:]).all())
+    assert int(i.min()) >= 0 and int(i.max()) < N
+    rows = torch.cat([torch.arange(0, 40), torch.arange(B // 2 - 20, B // 2 + 20), torch.arange(B - 40, B),
+                      torch.randint(0, B, (136,), generator=torch.Generator().manual_seed(1))]).to(DEV)
+    us, ss, ii = u[rows], s[rows], i[rows]
+    assert all(len(set(r.tolist())) == k for r in ii.cpu())
+    un = torch.nn.functional.normalize(us.float(), dim=-1)
+    picked = torch.nn.functional.normalize(C[ii.reshape(-1)].float(), dim=-1).view(len(rows), k, D)
+    exact = torch.einsum("bd,bkd->bk", un, picked)
+    assert torch.allclose(exact, ss, atol=TOL, rtol=0), float((exact - ss).abs().max())
+    beating = torch.zeros(len(rows), device=DEV, dtype=torch.long)
+    for c0 in range(0, N, 65536):
+        cn = torch.nn.functional.normalize(C[c0:c0 + 65536].float(), dim=-1)
+        beating += ((un @ cn.t()) > ss[:, -1:] + 4 * TOL).sum(dim=1)
+    assert int(beating.max()) <= k - 1, int(beating.max())
