@@ -204,3 +204,20 @@ def test_evaluate_reconstruction_matches_reference_golden():
     # squares dominated by the targets' own energy
     assert abs(got["val_recon_loss"] - float(z["val_recon_loss"])) <= 5e-3 * float(z["val_recon_loss"]), got
     assert abs(got["avg_cosine_similarity"] - float(z["avg_cosine_similarity"])) <= 2e-3, got
+
+
+def test_list_scores_more_users_than_one_grid():
+    """B > 65535 users (the grid's y limit): the wrapper slices the batch; padded and ragged forms agree with torch."""
+    from unirec_b200 import ops
+    B, C, D = 70_000, 5, 64
+    g = torch.Generator(device=DEV).manual_seed(2)
+    u = torch.randn(B, D, device=DEV, generator=g)
+    p = torch.randn(B, D, device=DEV, generator=g)
+    n = torch.randn(B, C, D, device=DEV, generator=g)
+    sims, _ = ops.list_scores(u, p, n)
+    ref = torch.einsum("bd,bcd->bc", torch.nn.functional.normalize(u, dim=-1),
+                       torch.nn.functional.normalize(torch.cat([p.unsqueeze(1), n], 1), dim=-1))
+    assert float((sims - ref).abs().max()) <= 3e-5
+    offs = torch.arange(B + 1, device=DEV, dtype=torch.int64) * C
+    sims_r, _ = ops.list_scores(u, p, n.view(B * C, D), offsets=offs, max_list=C)
+    assert torch.equal(sims_r, sims)

@@ -538,11 +538,19 @@ def list_scores(users: torch.Tensor, pos: torch.Tensor, cands: torch.Tensor, *, 
     sims = torch.empty(B, C + 1, device=users.device, dtype=torch.float32)
     inv = torch.empty(B, C + 1, device=users.device, dtype=torch.float32)
     es = users.element_size()
+    step = 65535                                    # users are the grid's y dimension: larger batches go in slices
     with _Timed("list_scores", float(B) * (C + 2) * D * es):
-        rc = _lib.load().unirec_list_scores(users.data_ptr(), users.stride(0), pos.data_ptr(), pos.stride(0),
-                                            cands.data_ptr(), ldc, 1 if users.dtype == torch.float32 else 0, _ptr(mask),
-                                            _ptr(offsets), B, C, D, float(eps), sims.data_ptr(), inv.data_ptr(), _stream())
-    _lib.check(rc, "unirec_list_scores")
+        for lo in range(0, B, step):
+            n = min(step, B - lo)
+            # padded lists: the slice's rows start at cands[lo]; ragged lists: offsets are absolute row numbers
+            c_ptr = cands.data_ptr() + (lo * C * ldc * es if offsets is None else 0)
+            rc = _lib.load().unirec_list_scores(
+                users.data_ptr() + lo * users.stride(0) * es, users.stride(0), pos.data_ptr() + lo * pos.stride(0) * es,
+                pos.stride(0), c_ptr, ldc, 1 if users.dtype == torch.float32 else 0,
+                None if mask is None else mask.data_ptr() + lo * C,
+                None if offsets is None else offsets.data_ptr() + lo * 8, n, C, D, float(eps),
+                sims.data_ptr() + lo * (C + 1) * 4, inv.data_ptr() + lo * (C + 1) * 4, _stream())
+            _lib.check(rc, "unirec_list_scores")
     return sims, inv
 
 
