@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--users-per-gpu", type=int, default=4096)
     ap.add_argument("--item-batch", type=int, default=4096)
     ap.add_argument("--history", type=int, default=50)
+    ap.add_argument("--fused-gather", type=int, default=0, help="1: the user K/V projection gathers the history tokens from "
+                    "the item-token table itself (no materialised user sequence; SURVEY 8f-2)")
     ap.add_argument("--kv-gb", type=float, default=0.0, help="user Q-Former: bytes of cross-attention K/V materialised per "
                     "chunk of users, in GiB (0 = the module's default)")
     ap.add_argument("--top-k", type=int, default=100)
@@ -66,6 +68,7 @@ def config_dict(args, n_gpus):
                     "(item-token table + pool produced by cfg3 item-token generation)",
         "users_per_gpu_per_step": args.users_per_gpu, "global_users_per_step": args.users_per_gpu * n_gpus,
         "user_chunk_kv_gib": args.kv_gb if args.kv_gb > 0 else "module default",
+        "user_sequence": "gathered inside the K/V projection" if args.fused_gather else "materialised per chunk",
         "history_items": args.history, "tokens_per_item": 32, "keys_per_user": args.history * 32,
         "user_qformer": "4 layers x 64 queries, hidden 1024, 16 heads, FFN 4096, cross-attn every layer",
         "item_qformer": "12 layers x 32 queries, 14 fields x 1024, cross-attn every 2nd layer",
@@ -513,7 +516,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ------------------------------------------------------------------ stage B: nested user encode + rank (cfg 5)
     Bu, Hh, k = args.users_per_gpu, args.history, args.top_k
-    ranker = NestedRanker(user, tokens, pooled, k=k, index_base=lo)
+    ranker = NestedRanker(user, tokens, pooled, k=k, index_base=lo, fused_gather=bool(args.fused_gather))
     hgen = torch.Generator(device=dev).manual_seed(99 + rank)
     hist_batches = [torch.randint(0, N, (Bu, Hh), device=dev, generator=hgen) for _ in range(3)]
     lengths = torch.full((Bu,), Hh, device=dev, dtype=torch.int32)

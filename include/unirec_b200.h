@@ -248,6 +248,21 @@ int unirec_inject_tokens(const int64_t* input_ids, int64_t B, int64_t S, const i
                          const void* tokens, int tokens_fp32, void* text_embeds, int text_fp32, int64_t ld_text,
                          int64_t Hd, void* stream);
 
+/* Cross-attention K/V projection of the user Q-Former straight from the item-token table: the user
+ * sequence of models/user_sequence_encoder.py:128-140 + training/user_qformer_training.py:153-161 is never materialised.
+ *   out[m, :] = A[m, :] W^T + bias + posbias[m % period, :],   m = (user * slots_per_user + slot) * 32 + token
+ *   A[m, :]   = table[ids[user, slot] * 32 + token, :]   if slot < lengths[user]   (an id outside the table reads zeros)
+ *             = pad_table[slot * 32 + token, :]           otherwise
+ * table = item tokens viewed 2-D [table_rows = items * 32, K]; posbias bf16 [>= period + 128, N] = PE W^T with its first
+ * 128 rows repeated after row `period` (a 128-row tile may run over a user boundary); pad_table bf16 [period, K] = -PE, so
+ * that padding rows come out as `bias` alone like the reference's zero-padded sequence.  period = slots_per_user * 32,
+ * M a multiple of period, N % 256 == 0, K % 64 == 0.  tcgen05 CTA-pair kernel, A tiles loaded as four 32-row TMA boxes. */
+int unirec_linear_gather_bf16(const void* table, int64_t ld_table, int64_t table_rows, const int64_t* ids,
+                              const int32_t* lengths, int64_t slots_per_user, const void* pad_table, int64_t ld_pad,
+                              int64_t pad_rows, const void* W, int64_t ldw, const float* bias, const void* posbias,
+                              int64_t ld_pos, int64_t pos_rows, int64_t period, void* out, int64_t ldo, int64_t M,
+                              int64_t N, int64_t K, void* stream);
+
 /* Reconstruction-quality metrics (evaluation/evaluate_item_qformer.py:66-95), one pass, no synchronisation:
  * over the rows (item, field) with mask != 0:  acc[0] += ||rec - orig||^2,  acc[1] += cosine(rec, orig),  acc[2] += 1.
  * rec [rows, E] fp32 (rec_fp32 = 1) or bf16, orig fp32 [rows, E], mask fp32 [rows], acc = 3 doubles on the device

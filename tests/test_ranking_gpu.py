@@ -223,3 +223,75 @@ def test_score_topk_multi_gpu_rank_shapes(B, N):
         cn = torch.nn.functional.normalize(C[c0:c0 + 65536].float(), dim=-1)
         beating += ((un @ cn.t()) > ss[:, -1:] + 4 * TOL).sum(dim=1)
     assert int(beating.max()) <= k - 1, int(beating.max())
+
+
+def test_linear_gather_matches_materialised_projection():
+    """The K/V projection with its A operand gathered from the item-token table: ragged histories with a
+    zero-length user, garbage ids in the padding slots, user boundaries that fall inside 128-row tiles, a row count that
+    is not a multiple of the 256-row tile - against fp32 torch on the same bf16 operands."""
+    from unirec_b200 import ops
+    N_items, K, Hmax, B, N = 500, 256, 6, 9, 1024
+    S = Hmax * 32
+    g = torch.Generator().manual_seed(55)
+    table = torch.randn(N_items, 32, K, generator=g).to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g)
+    pad = torch.randn(S, K, generator=g).to(torch.bfloat16)
+    posb = torch.randn(S, N, generator=g).to(torch.bfloat16)
+    posb_ext = torch.cat([posb, posb[:128]], 0).contiguous()
+    hist = torch.randint(0, N_items, (B, Hmax), generator=g)
+    lengths = torch.tensor([6, 0, 3, 1, 6, 2, 5, 6, 4], dtype=torch.int32)
+    for b in range(B):                                   # ids in padding slots are never read
+        hist[b, int(lengths[b]):] = torch.tensor([-1, 10 ** 12, N_items, -7, 3, 0])[: Hmax - int(lengths[b])]
+    A = torch.empty(B, Hmax, 32, K)
+    for b in range(B):
+        for j in range(Hmax):
+            A[b, j] = table[hist[b, j]].float() if j < int(lengths[b]) else pad[j * 32:(j + 1) * 32].float()
+    ref = A.view(B * S, K) @ W.float().t() + bias + posb.float().repeat(B, 1)
+    out = ops.linear_gather(table.to(DEV), hist.to(DEV), lengths.to(DEV), pad.to(DEV), W.to(DEV), bias.to(DEV),
+                            posb_ext.to(DEV))
+    assert tuple(out.shape) == (B * S, N)
+    torch.testing.assert_close(out.float().cpu(), ref, rtol=1e-2, atol=3e-2)
+    # a valid slot whose id lies outside the table reads zero rows (TMA out-of-bounds fill), like an empty item
+    hist2 = hist.clone()
+    hist2[0, 2] = N_items + 5
+    out2 = ops.linear_gather(table.to(DEV), hist2.to(DEV), lengths.to(DEV), pad.to(DEV), W.to(DEV), bias.to(DEV),
+                             posb_ext.to(DEV))
+    rows = slice(2 * 32, 3 * 32)
+    torch.testing.assert_close(out2[rows].float().cpu(), (bias + posb[rows].float()), rtol=1e-2, atol=3e-2)
+    assert torch.equal(out2[3 * 32:], out[3 * 32:])
+
+
+def test_nested_ranker_fused_gather_matches_builder_path_and_oracle():
+    """NestedRanker(fused_gather=True): user vectors from the gathered K/V projection against the oracle chain and
+    against the path that materialises the user sequence (including a user with an empty history: uniform attention
+    over all-padding keys)."""
+    from unirec_b200.modules import UserQFormer
+    from unirec_b200.pipeline import NestedRanker
+    mk = dict(hidden=256, layers=2, inter=512, num_query=64, input_dim=256, num_predict=8)
+    sd = synth.user_qformer_state_dict(**mk, seed=31, attn_std=0.1)
+    um = UserQFormer(hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=512,
+                     num_query_tokens=64, input_embedding_dim=256, num_item_tokens_to_predict=8)
+    um.load_state_dict(sd, strict=True)
+    um = um.to(DEV).eval()
+    N, Q, D, B, Hmax, k = 3000, 32, 256, 11, 6, 50
+    table = synth.normal("tok_table", (N, Q, D), 32).to(torch.bfloat16)
+    cands = table.float().mean(dim=1).to(torch.bfloat16)
+    gen = torch.Generator().manual_seed(34)
+    history = torch.randint(0, N, (B, Hmax), generator=gen)
+    lengths = torch.randint(1, Hmax + 1, (B,), generator=gen).to(torch.int32)
+    lengths[4] = 0
+    lengths[7] = Hmax
+    plain = NestedRanker(um, table.to(DEV), cands.to(DEV), k=k)
+    fused = NestedRanker(um, table.to(DEV), cands.to(DEV), k=k, fused_gather=True)
+    u_plain = plain.encode_users(history.to(DEV), lengths.to(DEV)).float().cpu()
+    u_fused = fused.encode_users(history.to(DEV), lengths.to(DEV)).float().cpu()
+    seq, mask = O.build_user_sequences(table.float(), history, lengths.long())
+    pred = O.user_qformer_forward(sd, seq, mask, num_heads=4, num_item_tokens_to_predict=8)
+    u_ref = O.pooled_scoring_vector(pred)
+    cos_ref = torch.nn.functional.cosine_similarity(u_fused, u_ref, dim=-1)
+    cos_plain = torch.nn.functional.cosine_similarity(u_fused, u_plain, dim=-1)
+    print("fused vs oracle:", cos_ref.min().item(), " fused vs builder path:", cos_plain.min().item())
+    assert float(cos_ref.min()) > 0.999 and float(cos_plain.min()) > 0.999
+    s, i = fused(history.to(DEV), lengths.to(DEV))
+    assert tuple(s.shape) == (B, k) and bool((s[:, :-1] >= s[:, 1:]).all())

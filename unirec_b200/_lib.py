@@ -73,6 +73,9 @@ _SIGNATURES = {
                                             c_float, c_void_p, c_void_p, c_void_p]),
     "unirec_inject_tokens": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int,
                                      c_int64, c_int64, c_void_p]),
+    "unirec_linear_gather_bf16": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64,
+                                          c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p,
+                                          c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "unirec_reconstruction_metrics": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p,
                                               c_void_p]),
 }

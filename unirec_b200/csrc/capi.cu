@@ -67,6 +67,11 @@ int inject_tokens(const long long* input_ids, long long B, long long S, const lo
                   const void* tokens, int tokens_fp32, void* text_embeds, int text_fp32, long long ld_text, long long Hd,
                   cudaStream_t stream);
 
+int gemm_bf16_cg2_gather(const void* table, long long ld_table, long long table_rows, const long long* ids,
+                         const int* lengths, long long slots_per_user, const void* pad_table, long long ld_pad,
+                         long long pad_rows, const void* W, long long ldw, const float* bias, const void* posbias,
+                         long long ld_pos, long long pos_rows, long long period, void* out, long long ldo, long long M,
+                         long long N, long long K, cudaStream_t stream);
 int reconstruction_metrics(const void* rec, int rec_fp32, const float* orig, const float* mask, long long rows, long long E,
                            float eps, double* acc, cudaStream_t stream);
 
@@ -249,6 +254,16 @@ int unirec_inject_tokens(const int64_t* input_ids, int64_t B, int64_t S, const i
 int unirec_reconstruction_metrics(const void* rec, int rec_fp32, const float* orig, const float* mask, int64_t rows,
                                   int64_t E, float eps, double* acc, void* stream) {
     COUNTED(reconstruction_metrics(rec, rec_fp32, orig, mask, rows, E, eps, acc, static_cast<cudaStream_t>(stream)));
+}
+
+int unirec_linear_gather_bf16(const void* table, int64_t ld_table, int64_t table_rows, const int64_t* ids,
+                              const int32_t* lengths, int64_t slots_per_user, const void* pad_table, int64_t ld_pad,
+                              int64_t pad_rows, const void* W, int64_t ldw, const float* bias, const void* posbias,
+                              int64_t ld_pos, int64_t pos_rows, int64_t period, void* out, int64_t ldo, int64_t M,
+                              int64_t N, int64_t K, void* stream) {
+    COUNTED(gemm_bf16_cg2_gather(table, ld_table, table_rows, reinterpret_cast<const long long*>(ids), lengths,
+                                 slots_per_user, pad_table, ld_pad, pad_rows, W, ldw, bias, posbias, ld_pos, pos_rows, period,
+                                 out, ldo, M, N, K, static_cast<cudaStream_t>(stream)));
 }
 
 }  // extern "C"

@@ -50,6 +50,14 @@ struct Gemm2Params {
     int M, N, K;
     const float* bias;      // [N] fp32 or nullptr
     int num_m_blocks, num_n_blocks;
+    // GATHER kernels only: the A operand is never materialised - every 32-row group g of the virtual
+    // [M, K] matrix is the 32 query tokens of item gather_ids[g] in the resident item-token table (tmap_a, box 32 rows), or,
+    // for history slots beyond the user's length, 32 rows of a padding table (tmap_pad) at the slot's position
+    const long long* gather_ids;    // [M / 32]
+    const int* gather_len;          // [users] valid slots per user
+    int slots_per_user;
+    int table_rows;                 // rows of the token table viewed 2-D: an out-of-bounds coordinate (TMA zero fill)
+    int res_period;                 // > 0: the residual tile of rows m.. is read at rows (m % res_period).. of its table
 };
 
 // ---- PTX specific to the CTA-pair pipeline -------------------------------------------------------
@@ -101,11 +109,11 @@ UNIREC_DEVICE void umma_commit_cg2_mc(uint64_t* bar, uint16_t cta_mask) {
                  : "memory");
 }
 
-template <int MODE>
+template <int MODE, bool GATHER = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
-                     const Gemm2Params p) {
+                     const __grid_constant__ CUtensorMap tmap_pad, const Gemm2Params p) {
     extern __shared__ uint8_t smem_raw[];
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -132,6 +140,7 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         tma_prefetch_desc(&tmap_b);
         tma_prefetch_desc(&tmap_out);
         if constexpr (MODE == G2_EPI_BIAS_RESIDUAL) tma_prefetch_desc(&tmap_res);
+        if constexpr (GATHER) tma_prefetch_desc(&tmap_pad);
     }
     if (warp_idx == 1 && lane == 0) {
         for (int i = 0; i < G2_STAGES; ++i) {
@@ -169,11 +178,42 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             const int n_blk = tile % p.num_n_blocks;
             const int m_coord = m_blk * G2_TILE_M + static_cast<int>(cta_rank) * 128;
             const int n_coord = n_blk * G2_TILE_N + static_cast<int>(cta_rank) * 128;
+            // GATHER: source row of each of this CTA's four 32-row groups (the same for every k-block of the tile)
+            int grow[4] = {0, 0, 0, 0};
+            bool gpad[4] = {false, false, false, false};
+            if constexpr (GATHER) {
+                if (lane == 0) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const long long g = (m_coord >> 5) + i;
+                        if (g * 32 >= p.M) {
+                            grow[i] = p.table_rows;                          // beyond the matrix: zero rows
+                        } else {
+                            const long long u = g / p.slots_per_user;
+                            const int j = static_cast<int>(g - u * p.slots_per_user);
+                            if (j < __ldg(p.gather_len + u)) {
+                                const long long id = __ldg(p.gather_ids + g);
+                                grow[i] = (id >= 0 && id * 32 < p.table_rows) ? static_cast<int>(id * 32) : p.table_rows;
+                            } else {
+                                grow[i] = j * 32;                            // padding slot: rows of the padding table
+                                gpad[i] = true;
+                            }
+                        }
+                    }
+                }
+            }
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 if (lane == 0) {
                     const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
                     if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
+                    if constexpr (GATHER) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            tma_load_2d_cg2(gpad[i] ? &tmap_pad : &tmap_a, full_leader,
+                                            smem_a + stage * G2_A_BYTES + i * (32 * G2_BLOCK_K * 2), kb * G2_BLOCK_K, grow[i],
+                                            kCacheEvictNormal);
+                    } else
                     tma_load_2d_cg2(&tmap_a, full_leader, smem_a + stage * G2_A_BYTES, kb * G2_BLOCK_K, m_coord,
                                     kCacheEvictNormal);
                     tma_load_2d_cg2(&tmap_b, full_leader, smem_b + stage * G2_B_BYTES, kb * G2_BLOCK_K, n_coord,
@@ -242,7 +282,7 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     if constexpr (MODE == G2_EPI_BIAS_RESIDUAL) {
                         mbar_arrive_expect_tx(&slab_ready_bar[slab], G2_SLAB_BYTES);
                         tma_load_2d(&tmap_res, &slab_ready_bar[slab], smem_c + slab * G2_SLAB_BYTES, n_coord + slab * 64,
-                                    m_coord);
+                                    p.res_period > 0 ? m_coord % p.res_period : m_coord);
                     } else {
                         mbar_arrive(&slab_ready_bar[slab]);
                     }
@@ -351,10 +391,10 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     }
 }
 
-template <int MODE>
+template <int MODE, bool GATHER = false>
 static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
-                        const Gemm2Params& p, int max_ctas, cudaStream_t stream) {
-    auto kern = gemm_bf16_cg2_kernel<MODE>;
+                        const Gemm2Params& p, int max_ctas, cudaStream_t stream, const CUtensorMap* tpad = nullptr) {
+    auto kern = gemm_bf16_cg2_kernel<MODE, GATHER>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES);
@@ -368,7 +408,7 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
     int clusters = num_sms() / 2;
     if (max_ctas > 0 && clusters > max_ctas / 2) clusters = max_ctas / 2 > 0 ? max_ctas / 2 : 1;
     if (clusters > tiles) clusters = tiles;
-    kern<<<2 * clusters, G2_THREADS, G2_SMEM_BYTES, stream>>>(ta, tb, to, tr, p);
+    kern<<<2 * clusters, G2_THREADS, G2_SMEM_BYTES, stream>>>(ta, tb, to, tr, tpad != nullptr ? *tpad : ta, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_last_error("gemm (cta pair) launch failed: %s", cudaGetErrorString(e));
@@ -396,6 +436,7 @@ int gemm_bf16_cg2(const void* A, long long lda, const void* W, long long ldw, co
     p.bias = bias;
     p.num_m_blocks = static_cast<int>((M + G2_TILE_M - 1) / G2_TILE_M);
     p.num_n_blocks = static_cast<int>(N / G2_TILE_N);
+    p.gather_ids = nullptr; p.gather_len = nullptr; p.slots_per_user = 0; p.table_rows = 0; p.res_period = 0;
     CUtensorMap ta, tb, to, tr;
     int rc = make_tmap_bf16_2d(&ta, A, M, K, lda, 128);
     if (rc != UNIREC_OK) return rc;
@@ -415,6 +456,51 @@ int gemm_bf16_cg2(const void* A, long long lda, const void* W, long long ldw, co
         case G2_EPI_BIAS_RESIDUAL: return launch_gemm2<G2_EPI_BIAS_RESIDUAL>(ta, tb, to, tr, p, max_ctas, stream);
         default: set_last_error("gemm_bf16: unknown epilogue %d", epilogue); return UNIREC_ERR_BAD_ARG;
     }
+}
+
+// out[M, N] = gather(table)[M, K] x W[N, K]^T + bias + posbias[m % period, :]   (bf16 out)
+// The cross-attention K/V projection of the user Q-Former straight from the resident item-token table: row group g of
+// the virtual user-sequence matrix (M = users x slots_per_user x 32 rows) is the 32 tokens of item ids[g]; the sinusoidal
+// position term of models/user_sequence_encoder.py:128-140 enters as the precomputed tile posbias = PE x W^T (linear in
+// A), and slots beyond a user's length read pad_table = -PE so that their rows come out as the bias alone - what the
+// reference's zero-padded sequence gives (training/user_qformer_training.py:153-161).
+int gemm_bf16_cg2_gather(const void* table, long long ld_table, long long table_rows, const long long* ids,
+                         const int* lengths, long long slots_per_user, const void* pad_table, long long ld_pad,
+                         long long pad_rows, const void* W, long long ldw, const float* bias, const void* posbias,
+                         long long ld_pos, long long pos_rows, long long period, void* out, long long ldo, long long M,
+                         long long N, long long K, cudaStream_t stream) {
+    if (table == nullptr || ids == nullptr || lengths == nullptr || pad_table == nullptr || W == nullptr ||
+        posbias == nullptr || out == nullptr || M <= 0 || slots_per_user <= 0) {
+        set_last_error("linear_gather: null pointer or empty shape");
+        return UNIREC_ERR_BAD_ARG;
+    }
+    if (N % G2_TILE_N != 0 || K % G2_BLOCK_K != 0 || M % 32 != 0 || period != slots_per_user * 32 ||
+        M % period != 0 || pos_rows < period + 128 || pad_rows < period || table_rows % 32 != 0 ||
+        table_rows >= 2147483647LL - 64 || ld_table % 8 != 0 || ld_pad % 8 != 0 || ldw % 8 != 0 || ld_pos % 8 != 0 ||
+        ldo % 8 != 0) {
+        set_last_error("linear_gather: needs N %% 256 == 0, K %% 64 == 0, 32-token slots, period = slots x 32, posbias with "
+                       "period + 128 rows, 16-byte aligned rows (M=%lld N=%lld K=%lld period=%lld)", M, N, K, period);
+        return UNIREC_ERR_BAD_ARG;
+    }
+    Gemm2Params p;
+    p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
+    p.bias = bias;
+    p.num_m_blocks = static_cast<int>((M + G2_TILE_M - 1) / G2_TILE_M);
+    p.num_n_blocks = static_cast<int>(N / G2_TILE_N);
+    p.gather_ids = ids; p.gather_len = lengths; p.slots_per_user = static_cast<int>(slots_per_user);
+    p.table_rows = static_cast<int>(table_rows); p.res_period = static_cast<int>(period);
+    CUtensorMap ta, tb, to, tr, tp;
+    int rc = make_tmap_bf16_2d(&ta, table, table_rows, K, ld_table, 32);
+    if (rc != UNIREC_OK) return rc;
+    rc = make_tmap_bf16_2d(&tp, pad_table, pad_rows, K, ld_pad, 32);
+    if (rc != UNIREC_OK) return rc;
+    rc = make_tmap_bf16_2d(&tb, W, N, K, ldw, 128);
+    if (rc != UNIREC_OK) return rc;
+    rc = make_tmap_bf16_2d(&to, out, M, N, ldo, 128);
+    if (rc != UNIREC_OK) return rc;
+    rc = make_tmap_bf16_2d(&tr, posbias, pos_rows, N, ld_pos, 128);
+    if (rc != UNIREC_OK) return rc;
+    return launch_gemm2<G2_EPI_BIAS_RESIDUAL, true>(ta, tb, to, tr, p, 0, stream, &tp);
 }
 
 }  // namespace unirec

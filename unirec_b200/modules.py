@@ -239,6 +239,17 @@ class QFormerBackbone(nn.Module):
             mask = encoder_attention_mask.to(device=enc.device, dtype=torch.float32).contiguous()
         # cross-attention K/V of every cross layer in one GEMM (the encoder input is layer-invariant)
         kv_all = ops.linear(enc, pk["w_kv_all"], pk["b_kv_all"]) if pk["w_kv_all"] is not None else None
+        return self.encode_from_kv(query_embeddings, kv_all, B, S, mask, out_dtype, prelayernorm_dtype)
+
+    def encode_from_kv(self, query_embeddings: torch.Tensor, kv_all: Optional[torch.Tensor], B: int, S: int,
+                       mask: Optional[torch.Tensor], out_dtype: torch.dtype = torch.float32,
+                       prelayernorm_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+        """The encoder behind the cross-attention K/V projection: kv_all bf16 [B * S, 2 H n_cross] (K and V of every
+        cross-attention layer side by side), mask fp32 [B, S] (1 attend / 0 masked) or None."""
+        cfg = self.config
+        H, heads = cfg.hidden_size, cfg.num_attention_heads
+        Q = query_embeddings.shape[1]
+        pk = self.packed()
 
         # BertEmbeddings query-only branch: LayerNorm of the learned tokens - batch-invariant, and so is everything up
         # to the first cross-attention: layer 0's whole self-attention block and its cross-attention QUERY projection
@@ -467,6 +478,53 @@ class UserQFormer(nn.Module):
             m = None if attention_mask is None else attention_mask[lo:lo + step]
             outs.append(self.qformer.encode(self.query_embeddings, user_sequence_tokens[lo:lo + step], m, out_dtype,
                                             self.prelayernorm_dtype))
+        return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+
+    def _position_tables(self, hmax: int, tokens_per_item: int, device) -> dict:
+        """Per (history length, weight version): posbias = PE W_kv^T (bf16 [S + 128, 2 H layers], the first 128 rows
+        repeated at the end) and pad = -PE (bf16 [S, E]) for `ops.linear_gather`.  PE is split into two bf16 terms so that
+        posbias carries fp32-accurate positions; it is rounded to bf16 once."""
+        pk = self.qformer.packed()
+        key = ("pos", hmax, tokens_per_item)
+        t = pk.get(key)
+        if t is None:
+            S, E = hmax * tokens_per_item, self.config.encoder_width
+            pe = ops.positional_encoding_table(S, E, device)
+            hi = pe.to(torch.bfloat16)
+            lo = (pe - hi.float()).to(torch.bfloat16)
+            w = pk["w_kv_all"]
+            posw = (ops.linear(hi, w, None, out_dtype=torch.float32) + ops.linear(lo, w, None, out_dtype=torch.float32))
+            posw = posw.to(torch.bfloat16)
+            t = {"posbias": torch.cat([posw, posw[:128]], 0).contiguous(), "pad": (-hi).contiguous()}
+            pk[key] = t
+        return t
+
+    @torch.no_grad()
+    def encode_queries_from_history(self, item_tokens: torch.Tensor, history: torch.Tensor, lengths: torch.Tensor,
+                                    out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+        """last_hidden_state [B, num_query_tokens, H] straight from the item-token table: the user
+        sequence (gather + sinusoidal PE + right padding, models/user_sequence_encoder.py:128-140,
+        training/user_qformer_training.py:153-161) is never built - the K/V projection gathers its A operand from the
+        table and adds the position term as a precomputed tile (`ops.linear_gather`).  item_tokens bf16 [N, 32, E],
+        history int64 [B, Hmax], lengths int32 [B].  No per-user context vector on this path (the builder path has it)."""
+        _check_inference_mode(self, self.config.hidden_dropout_prob)
+        if item_tokens.dim() != 3 or item_tokens.shape[1] != 32:
+            raise RuntimeError("encode_queries_from_history: needs an item-token table [N, 32, E]")
+        B, hmax = history.shape
+        Q_item = item_tokens.shape[1]
+        S = hmax * Q_item
+        pk = self.qformer.packed()
+        tabs = self._position_tables(hmax, Q_item, item_tokens.device)
+        step = self._chunk_users(S)
+        pos = torch.arange(S, device=item_tokens.device, dtype=torch.int32)
+        outs = []
+        for lo in range(0, B, step):
+            hi = min(lo + step, B)
+            hist, lens = history[lo:hi].contiguous(), lengths[lo:hi].contiguous()
+            kv_all = ops.linear_gather(item_tokens, hist, lens, tabs["pad"], pk["w_kv_all"], pk["b_kv_all"], tabs["posbias"])
+            mask = (pos.unsqueeze(0) < (lens * Q_item).unsqueeze(1)).to(torch.float32)
+            outs.append(self.qformer.encode_from_kv(self.query_embeddings, kv_all, hi - lo, S, mask, out_dtype,
+                                                    self.prelayernorm_dtype))
         return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
 
     @torch.no_grad()

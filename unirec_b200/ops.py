@@ -630,3 +630,37 @@ def reconstruction_metrics(reconstructed: torch.Tensor, original: torch.Tensor, 
                                                    acc.data_ptr(), _stream())
     _lib.check(rc, "unirec_reconstruction_metrics")
     return acc
+
+
+def linear_gather(table: torch.Tensor, history: torch.Tensor, lengths: torch.Tensor, pad_table: torch.Tensor,
+                  weight: torch.Tensor, bias: Optional[torch.Tensor], posbias: torch.Tensor) -> torch.Tensor:
+    """K/V projection of the (never materialised) user sequences: table bf16 [N_items, 32, K]; history int64 [B, Hmax];
+    lengths int32 [B]; pad_table bf16 [Hmax * 32, K] (= -PE); weight bf16 [N, K]; bias fp32 [N]; posbias bf16
+    [Hmax * 32 + 128, N] (= PE W^T, first 128 rows repeated at the end).  Returns bf16 [B * Hmax * 32, N]."""
+    _req(table, torch.bfloat16, "linear_gather.table")
+    _req(history, torch.int64, "linear_gather.history")
+    _req(lengths, torch.int32, "linear_gather.lengths")
+    _req(pad_table, torch.bfloat16, "linear_gather.pad_table")
+    _req(weight, torch.bfloat16, "linear_gather.weight")
+    _req(posbias, torch.bfloat16, "linear_gather.posbias")
+    if bias is not None:
+        _req(bias, torch.float32, "linear_gather.bias")
+    if table.dim() != 3 or table.shape[1] != 32 or not table.is_contiguous():
+        raise RuntimeError("linear_gather: table must be contiguous [N_items, 32, K]")
+    n_items, _, K = table.shape
+    B, Hmax = history.shape
+    N = weight.shape[0]
+    period = Hmax * 32
+    if not (history.is_contiguous() and lengths.is_contiguous()) or lengths.numel() != B:
+        raise RuntimeError("linear_gather: history [B, Hmax] and lengths [B] must be contiguous")
+    if tuple(pad_table.shape) != (period, K) or posbias.shape[0] < period + 128 or posbias.shape[1] != N:
+        raise RuntimeError("linear_gather: pad_table must be [Hmax * 32, K] and posbias [>= Hmax * 32 + 128, N]")
+    M = B * period
+    out = torch.empty(M, N, device=table.device, dtype=torch.bfloat16)
+    with _Timed("gemm", 2.0 * M * N * K, f"{M}x{N}x{K}"):
+        rc = _lib.load().unirec_linear_gather_bf16(table.data_ptr(), K, n_items * 32, history.data_ptr(), lengths.data_ptr(),
+                                                   Hmax, pad_table.data_ptr(), pad_table.stride(0), period, weight.data_ptr(),
+                                                   weight.stride(0), _ptr(bias), posbias.data_ptr(), posbias.stride(0),
+                                                   posbias.shape[0], period, out.data_ptr(), out.stride(0), M, N, K, _stream())
+    _lib.check(rc, "unirec_linear_gather_bf16")
+    return out

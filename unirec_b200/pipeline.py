@@ -155,7 +155,7 @@ class NestedRanker:
     """
 
     def __init__(self, user_model: UserQFormer, item_tokens: torch.Tensor, candidates: torch.Tensor, k: int = 100,
-                 index_base: int = 0, group=None):
+                 index_base: int = 0, group=None, fused_gather: bool = False):
         self.user_model = user_model
         self.item_tokens = item_tokens
         self.candidates = candidates
@@ -163,6 +163,9 @@ class NestedRanker:
         self.k = k
         self.index_base = index_base
         self.group = group
+        # True: the K/V projection gathers the history tokens itself (UserQFormer.encode_queries_from_history) instead of
+        # reading a materialised user sequence; used when no per-user context vector is given
+        self.fused_gather = fused_gather
 
     @torch.no_grad()
     def encode_users(self, history: torch.Tensor, lengths: torch.Tensor,
@@ -171,6 +174,9 @@ class NestedRanker:
         um = self.user_model
         B = history.shape[0]
         S = history.shape[1] * self.item_tokens.shape[1]
+        if self.fused_gather and context is None:
+            hidden = um.encode_queries_from_history(self.item_tokens, history, lengths, torch.bfloat16)
+            return ops.mean_tokens(um.predict_from_queries(hidden, out_dtype=torch.bfloat16))
         step = um._chunk_users(S)
         outs = []
         for lo in range(0, B, step):
