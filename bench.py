@@ -50,7 +50,8 @@ def parse_args():
     ap.add_argument("--kv-gb", type=float, default=0.0, help="user Q-Former: bytes of cross-attention K/V materialised per "
                     "chunk of users, in GiB (0 = the module's default)")
     ap.add_argument("--top-k", type=int, default=100)
-    ap.add_argument("--cpu-users", type=int, default=8, help="users in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-users", type=int, default=32, help="users in the bounded CPU-baseline sample (timed); the "
+                    "top-k parity check against the GPU result uses the first 8 of them")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--train-batch", type=int, default=1024, help="GLOBAL batch of the cfg-2 training block (0 = skip)")
     ap.add_argument("--train-steps", type=int, default=4)
@@ -648,24 +649,24 @@ def run_ours(args, rank, world, local_rank):
         got_s, got_i = cpu_in["got_s"], cpu_in["got_i"]
         overlap = sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(got_i, ref_i)) / (Bc * k)
         # top-k parity in the north_star's terms: a GPU pick that is not in the oracle's list must tie with the
-        # oracle's k-th score within the bf16 tolerance of the encoders (score_max_abs_diff is the measured one)
+        # oracle's k-th score within the bf16 tolerance of the encoders (score_max_abs_diff is the measured one);
+        # checked on the first 8 users of the sample (it needs their full score rows over the pool)
         tol = 4.0 * float((got_s - ref_s).abs().max()) + 1e-6
+        Bp = min(Bc, 8)
         full = O.cosine_scores(O.pooled_scoring_vector(
-            O.user_qformer_forward(usd, *O.build_user_sequences(tok_c, hist_local, len_c), num_heads=16,
-                                   num_item_tokens_to_predict=32)), cands_c) if Bc <= 8 else None
-        outside = None
-        if full is not None:
-            outside = 0
-            for u in range(Bc):
-                kth = float(ref_s[u, -1])
-                extra = set(got_i[u].tolist()) - set(ref_i[u].tolist())
-                outside += sum(1 for j in extra if float(full[u, j]) < kth - tol)
+            O.user_qformer_forward(usd, *O.build_user_sequences(tok_c[:Bp * Hh], hist_local[:Bp], len_c[:Bp]), num_heads=16,
+                                   num_item_tokens_to_predict=32)), cands_c)
+        outside = 0
+        for u in range(Bp):
+            kth = float(ref_s[u, -1])
+            extra = set(got_i[u].tolist()) - set(ref_i[u].tolist())
+            outside += sum(1 for j in extra if float(full[u, j]) < kth - tol)
         cpu_baseline = {"value": Bc / dt, "unit": "users/s", "cores": cores, "kind": "port",
                         "sample": f"{Bc} users of the timed workload (S={Hh * 32} keys, {N} candidates, top-{k}), "
                                   f"oracle fp32 on torch CPU, 1 pass after warm-up",
                         "parity_vs_gpu": {"score_max_abs_diff": float((got_s - ref_s).abs().max()),
                                           "topk_overlap": overlap, "tie_tolerance": tol,
-                                          "picks_outside_tie_tolerance": outside}}
+                                          "picks_outside_tie_tolerance": outside, "users_checked_for_ties": Bp}}
         isd, xi = cpu_in["isd"], cpu_in["xi"]
         O.item_qformer_forward(isd, xi[:2], None)
         t0 = time.perf_counter()
