@@ -394,6 +394,9 @@ class TrainStepGraph:
     Gradients land in static tensors (`.grads`); after `step()` they are attached to the parameters' `.grad`, so the
     caller averages them over the ranks (`GradientAllReducer.reduce_tensors(graph.grad_tensors())`) and runs the
     optimizer as usual.  Do not call `zero_grad(set_to_none=False)` between steps - a replay overwrites the gradients.
+    Precondition (torch's, not ours): no autograd graph of an EARLIER eager step of the same model may still be alive
+    when the graph is captured (e.g. a kept `loss` tensor) - it keeps the parameters' AccumulateGrad nodes bound to the
+    eager stream and the capture is invalidated (`cudaErrorStreamCaptureInvalidated`); `del loss` first.
     """
 
     SEED_STRIDE = 1024     # > the number of forward passes in one step: replays never reuse an effective seed
