@@ -156,3 +156,31 @@ def test_torch_custom_ops_are_registered_with_fake_impls_and_no_cpu_kernel():
     assert tuple(loss.shape) == (8,) and rank.dtype == torch.int32
     with pytest.raises(NotImplementedError):
         ns.linear(torch.zeros(4, 64, dtype=torch.bfloat16), torch.zeros(256, 64, dtype=torch.bfloat16), None, None, 0, False)
+
+
+def test_new_entry_points_refuse_cpu_inputs():
+    """The joint-trainer hooks, the evaluation loop and the streamed generation loop have no CPU path either: a CPU
+    tensor / CPU model raises instead of computing something somewhere else."""
+    import pytest
+    import torch
+    from unirec_b200.evaluation import evaluate_reconstruction
+    from unirec_b200.joint import InfoNCELoss, inject_history_tokens
+    from unirec_b200.modules import QFormerForItemRepresentation, UserQFormer
+    from unirec_b200.pipeline import generate_item_tokens_streamed
+    u, n = torch.randn(4, 64), torch.randn(4, 3, 64)
+    with pytest.raises(RuntimeError):
+        InfoNCELoss()(u, u, n)
+    with pytest.raises(RuntimeError):
+        inject_history_tokens(torch.zeros(1, 4, 64), torch.zeros(1, 4, dtype=torch.long), torch.arange(2).view(1, 2),
+                              torch.zeros(1, 1, 2, 64))
+    model = QFormerForItemRepresentation(hidden_size=128, num_hidden_layers=1, num_attention_heads=2,
+                                         intermediate_size=128, num_query_tokens=8, field_embedding_dim=128, num_fields=3)
+    with pytest.raises(RuntimeError):
+        evaluate_reconstruction(model.eval(), torch.zeros(2, 3, 128), torch.ones(2, 3))
+    with pytest.raises(RuntimeError):
+        generate_item_tokens_streamed(model.eval(), torch.zeros(2, 3, 128), None, torch.zeros(2, 8, 128, dtype=torch.bfloat16))
+    um = UserQFormer(hidden_size=128, num_hidden_layers=1, num_attention_heads=2, intermediate_size=128,
+                     num_query_tokens=8, input_embedding_dim=128, num_item_tokens_to_predict=2).eval()
+    with pytest.raises(RuntimeError):
+        um.encode_queries_from_history(torch.zeros(5, 16, 128, dtype=torch.bfloat16), torch.zeros(1, 2, dtype=torch.long),
+                                       torch.ones(1, dtype=torch.int32))
