@@ -184,3 +184,19 @@ def test_new_entry_points_refuse_cpu_inputs():
     with pytest.raises(RuntimeError):
         um.encode_queries_from_history(torch.zeros(5, 16, 128, dtype=torch.bfloat16), torch.zeros(1, 2, dtype=torch.long),
                                        torch.ones(1, dtype=torch.int32))
+
+
+def test_plain_c_program_binds_the_abi(tmp_path):
+    """include/unirec_b200.h compiles as C11 and a C program (examples/c_abi_probe.c) loads the library without Python,
+    finds the entry points, runs the host-only ones and gets an error CODE (not a crash) from a bad call."""
+    import shutil
+    import subprocess
+    from unirec_b200 import _lib
+    if shutil.which("gcc") is None:
+        import pytest
+        pytest.skip("gcc not available")
+    exe = str(tmp_path / "c_abi_probe")
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "c_abi_probe.c"), "-ldl", "-o", exe], check=True)
+    out = subprocess.run([exe, _lib.LIB_PATH], check=True, capture_output=True, text=True).stdout
+    assert out.startswith("abi 2,") and "rc 1" in out
