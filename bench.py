@@ -346,7 +346,7 @@ def run_train_block(args, rank, world, dev, barrier, max_over_ranks, pk):
 
             def gstep(i):
                 if faithful:
-                    loss_ = tg.step(fields[i % nb], mask, fields[(i + 1) % nb], fields[(i + 2) % nb])
+                    loss_ = tg.step(fields[i % nb], mask, fields[(i + 1) % nb], fields[(i + 2) % nb], mask, mask)
                 else:
                     loss_ = tg.step(fields[i % nb], mask, pos, neg)
                 red.reduce_tensors(tg.grad_tensors())

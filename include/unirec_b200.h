@@ -91,7 +91,8 @@ int unirec_field_projection(const void* rec, const float* Wp, const float* bp, v
  * + PE[h*Q+q, :] for h < lengths[b], 0 otherwise; mask[b,s] = s < lengths[b]*Q.
  * table bf16 [num_items, Q, D]; history int64 [B, Hmax]; lengths int32 [B]; ctx bf16 [B,Hmax,D] or NULL;
  * pe_table fp32 [Hmax*Q, D] from unirec_positional_encoding, or NULL (PE evaluated in the kernel: slower, same values);
- * seq bf16 [B, Hmax*Q, D]; mask fp32 [B, Hmax*Q]. */
+ * seq bf16 [B, Hmax*Q, D]; mask fp32 [B, Hmax*Q].  A history id outside [0, num_items) contributes a zero token row
+ * (the slot keeps ctx + PE and stays attended) - the same as unirec_linear_gather_bf16; never an out-of-bounds read. */
 int unirec_build_user_sequence(const void* table, int64_t num_items, const int64_t* history,
                                const int32_t* lengths, const void* ctx, const float* pe_table, void* seq, float* mask,
                                int64_t B, int64_t Hmax, int64_t Q, int64_t D, void* stream);
@@ -247,6 +248,34 @@ int unirec_list_scores_backward(const void* users, int64_t ldu, const void* pos,
 int unirec_inject_tokens(const int64_t* input_ids, int64_t B, int64_t S, const int64_t* token_ids, int64_t num_slots,
                          const void* tokens, int tokens_fp32, void* text_embeds, int text_fp32, int64_t ld_text,
                          int64_t Hd, void* stream);
+
+/* Backward of unirec_inject_tokens (the reference's overwrite is a differentiable index assignment - the only path by
+ * which the joint trainer's loss reaches the item Q-Former, training/train_item_individual_token_joint.py:160-171):
+ * d_text [B * S rows, stride ld_text] holds the upstream gradient and is edited IN PLACE (overwritten positions -> 0);
+ * d_tokens fp32 [B, num_slots, Hd] is ACCUMULATED (zero it first) with the upstream rows of the positions of each slot. */
+int unirec_inject_tokens_backward(const int64_t* input_ids, int64_t B, int64_t S, const int64_t* token_ids,
+                                  int64_t num_slots, void* d_text, int text_fp32, int64_t ld_text, float* d_tokens,
+                                  int64_t Hd, void* stream);
+
+/* Event-context encoders in front of the user-sequence builder (models/mwne.py:504-566 TimestampEncoder,
+ * :569-610 GeoCoordinateEncoder; summed per event at models/user_sequence_encoder.py:125-131).  First half of both MLPs:
+ *   out[e, 0:H]  = gelu(W1t f_time(timestamps[e]) + b1t)   f_time = 9 features (secular + 4 sin/cos pairs), W1t [H, 9]
+ *   out[e, H:2H] = gelu(W1g f_geo(coords[e]) + b1g)        f_geo = unit-sphere xyz of (lat, lon) degrees, W1g [H, 3]
+ * H = `hidden` = 2 x embedding_dim; out bf16 [n, >= 2H] with row stride ldo.  The second Linear of both encoders and their
+ * sum is then ONE unirec_linear_bf16 call with W = [W2t | W2g] ([D, 2H]) and bias b2t + b2g.  timestamps: fp32, or int64
+ * converted like torch's .float() (ts_int64 = 1); either input may be NULL (its half is written as zeros).
+ * feats (may be NULL): fp32 [n, 12], the raw features (9 time + 3 geo), for tests. */
+int unirec_context_hidden(const void* timestamps, int ts_int64, const float* coords, const float* w1t, const float* b1t,
+                          const float* w1g, const float* b1g, int64_t n, int64_t hidden, void* out, int64_t ldo,
+                          float* feats, void* stream);
+
+/* ImprovedMathematicalEncoder.forward (models/mwne.py:134-183): out[i, :] = [interleaved (cos, sin)(x f_k) o fourier_w |
+ * (x, sign x) o raw_scale | x * extra_w], times `scale` when given (eval-mode MathematicallyAwareNormalizer, :55-62:
+ * scale = clamp(target_std / (running_std + 1e-8), 0.1, 10)).  numbers fp32 [n]; freqs [F]; fourier_w [2F]; raw_scale
+ * [2] or NULL (include_raw = False); extra_w [D - 2F - raw] or NULL; out fp32 / bf16 [n, D]. */
+int unirec_mwne_encode(const float* numbers, int64_t n, const float* freqs, int64_t F, const float* fourier_w,
+                       const float* raw_scale, const float* extra_w, const float* scale, int64_t D, void* out,
+                       int out_fp32, void* stream);
 
 /* Cross-attention K/V projection of the user Q-Former straight from the item-token table: the user
  * sequence of models/user_sequence_encoder.py:128-140 + training/user_qformer_training.py:153-161 is never materialised.

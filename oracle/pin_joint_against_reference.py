@@ -6,8 +6,8 @@ Run in the authoring container only (needs /root/reference):
     python -m oracle.pin_joint_against_reference --check    # check only
 
 training/train_item_individual_token_joint.py cannot be imported (peft is absent and the module calls
-torch.cuda.set_device(0) at import time, :33), so the source text of its `InfoNCELoss` and `MRREvaluator` classes is cut
-out with `ast` and executed as is in a namespace that provides the names those classes use (torch, nn, F, np, List,
+torch.cuda.set_device(0) at import time, :33), so the source text of its `InfoNCELoss`, `MRREvaluator` and
+`MultiModalQwenEmbedding` classes is cut out with `ast` and executed as is in a namespace that provides the names those classes use (torch, nn, F, np, List,
 tqdm, device='cpu').  No reference code is copied into this repository; only the classes' OUTPUTS are stored.
 """
 from __future__ import annotations
@@ -40,6 +40,84 @@ def load_reference_classes():
         if isinstance(node, ast.ClassDef) and node.name in ("InfoNCELoss", "MRREvaluator"):
             exec(compile(ast.Module(body=[node], type_ignores=[]), REF_FILE, "exec"), ns)
     return ns["InfoNCELoss"], ns["MRREvaluator"]
+
+
+def load_reference_joint_model_class():
+    """`MultiModalQwenEmbedding` (:88-181) cut out unmodified; its __init__ (Qwen3 download, LoRA) is never called - the
+    pin builds the object with __new__ and gives it stub collaborators, then runs the UNMODIFIED forward (:134-181)."""
+    src = open(REF_FILE).read()
+    tree = ast.parse(src)
+    from typing import Optional
+    ns = {"torch": torch, "nn": torch.nn, "F": torch.nn.functional, "np": np, "List": List, "Optional": Optional,
+          "LoraConfig": object, "device": torch.device("cpu"), "os": os}
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name == "MultiModalQwenEmbedding":
+            exec(compile(ast.Module(body=[node], type_ignores=[]), REF_FILE, "exec"), ns)
+    return ns["MultiModalQwenEmbedding"]
+
+
+class _StubTokenizer:
+    def __init__(self, ids):
+        self.ids = ids
+
+    def convert_tokens_to_ids(self, name):
+        return self.ids[name]
+
+
+class _StubLLM(torch.nn.Module):
+    """Stands in for Qwen3: an embedding table + an identity 'transformer' that records the embeddings it was given."""
+
+    def __init__(self, vocab, hidden, seed):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        self.emb = torch.nn.Embedding(vocab, hidden)
+        self.emb.weight.data = torch.randn(vocab, hidden, generator=g)
+        self.seen = None
+
+    def get_input_embeddings(self):
+        return self.emb
+
+    def forward(self, inputs_embeds=None, attention_mask=None, output_hidden_states=True):
+        self.seen = inputs_embeds.detach().clone()
+        from types import SimpleNamespace
+        return SimpleNamespace(hidden_states=[inputs_embeds])
+
+
+def injection_case():
+    """Seeded inputs of the token-injection pin: every placeholder once, three of them twice, one user missing four."""
+    g = torch.Generator().manual_seed(77)
+    B, S, nh, Q, Hd, vocab = 4, 160, 5, 8, 32, 400
+    token_ids = (300 + torch.randperm(nh * Q, generator=g)).view(nh, Q)
+    input_ids = torch.randint(0, 290, (B, S), generator=g)
+    for b in range(B):
+        perm = torch.randperm(S, generator=g)[: nh * Q + 3]
+        input_ids[b, perm[: nh * Q]] = token_ids.reshape(-1)
+        input_ids[b, perm[nh * Q:]] = token_ids.reshape(-1)[:3]
+        if b == 2:
+            input_ids[b, perm[5:9]] = 11
+    tokens = torch.randn(B, nh, Q, Hd, generator=g)
+    return B, S, nh, Q, Hd, vocab, token_ids, input_ids, tokens
+
+
+def pin_injection():
+    """Runs the reference's forward with stubs and returns (inputs, the embeddings the LLM received)."""
+    B, S, nh, Q, Hd, vocab, token_ids, input_ids, tokens = injection_case()
+    Model = load_reference_joint_model_class()
+    m = Model.__new__(Model)
+    torch.nn.Module.__init__(m)
+    m.base_model = _StubLLM(vocab, Hd, seed=5)
+    m.tokenizer = _StubTokenizer({f"<|history_item_{i}_query_{j}|>": int(token_ids[i, j]) for i in range(nh) for j in range(Q)})
+    m.num_history_items, m.num_query_tokens_per_item = nh, Q
+    m.qformer_model = lambda x, mask: {"query_outputs": tokens.view(B * nh, Q, Hd)}
+    with torch.no_grad():
+        pooled = m.forward(input_ids, torch.ones(B, S), torch.zeros(B, nh, 1, 1), torch.ones(B, nh, 1))
+    seen = m.base_model.seen
+    text = m.base_model.emb.weight.data[input_ids]
+    mine = JO.inject_tokens(text, input_ids, token_ids, tokens)
+    assert torch.equal(mine, seen), "oracle inject_tokens differs from the reference forward"
+    assert torch.equal(pooled, seen.mean(dim=1))
+    return {"inj_token_ids": token_ids.numpy(), "inj_input_ids": input_ids.numpy(), "inj_tokens": tokens.numpy(),
+            "inj_text": text.numpy(), "inj_out": seen.numpy()}
 
 
 def make_inputs():
@@ -87,6 +165,8 @@ def main():
         ref_mrr = ev._compute_batch_mrr(batch)
     assert ref_mrr == JO.reciprocal_ranks(users, pos, neg_list), (ref_mrr, JO.reciprocal_ranks(users, pos, neg_list))
     out["mrr"] = np.asarray(ref_mrr, dtype=np.float64)
+    out.update(pin_injection())
+    print("token injection: oracle == unmodified MultiModalQwenEmbedding.forward (stub LLM / tokenizer), bit-exact")
     print(f"oracle vs reference classes: max |diff| = {worst:.2e}; reciprocal ranks identical: {ref_mrr}")
     assert worst <= TOL, worst
     if not args.check:

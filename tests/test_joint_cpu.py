@@ -45,6 +45,18 @@ def test_inject_tokens_oracle_semantics():
     assert float(out[0, 0].abs().sum()) == 0 and float(out[1, 1:8].abs().sum()) == 0
 
 
+def test_inject_tokens_oracle_matches_reference_forward_golden():
+    """tests/golden/joint_scoring.npz `inj_*`: the embeddings the (stub) LLM received from the UNMODIFIED
+    MultiModalQwenEmbedding.forward (training/train_item_individual_token_joint.py:134-181) - the oracle's loop must
+    reproduce them bit for bit."""
+    from oracle import joint_oracle as JO
+    z = np.load(GOLDEN)
+    got = JO.inject_tokens(torch.from_numpy(z["inj_text"]), torch.from_numpy(z["inj_input_ids"]),
+                           torch.from_numpy(z["inj_token_ids"]), torch.from_numpy(z["inj_tokens"]))
+    assert torch.equal(got, torch.from_numpy(z["inj_out"]))
+    assert not torch.equal(got, torch.from_numpy(z["inj_text"]))
+
+
 def test_eval_oracle_matches_reference_golden():
     """oracle/eval_oracle.py over the CPU item-Q-Former oracle reproduces the two numbers the UNMODIFIED reference
     function evaluate_reconstruction_quality returned (oracle/pin_eval_against_reference.py)."""

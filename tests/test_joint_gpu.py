@@ -135,6 +135,53 @@ def test_inject_history_tokens_bit_exact(src, dst):
     assert torch.equal(got.cpu(), ref)
 
 
+def test_inject_history_tokens_matches_reference_forward_golden():
+    """Golden `inj_*` = what the unmodified reference forward handed to the LLM (stub tokenizer / LLM, see
+    oracle/pin_joint_against_reference.py::pin_injection): the kernel must reproduce it bit for bit."""
+    from unirec_b200.joint import inject_history_tokens
+    z = np.load(GOLDEN)
+    got = inject_history_tokens(torch.from_numpy(z["inj_text"]).to(DEV), torch.from_numpy(z["inj_input_ids"]).to(DEV),
+                                torch.from_numpy(z["inj_token_ids"]), torch.from_numpy(z["inj_tokens"]).to(DEV))
+    assert torch.equal(got.cpu(), torch.from_numpy(z["inj_out"]))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_inject_history_tokens_gradients_match_index_assign(dtype):
+    """The overwrite is differentiable in the reference (:160-171, `text_embeds[b, positions] = query_embeddings[b]`):
+    gradients of a downstream loss must reach the query tokens (the only path to the item Q-Former) and vanish at the
+    overwritten rows of the text embeddings.  Compared with torch autograd through the oracle's loop, exactly (fp32)."""
+    from oracle import joint_oracle as JO
+    from unirec_b200.joint import inject_history_tokens
+    B, S, nh, Q, Hd = 3, 200, 4, 8, 64
+    g = torch.Generator().manual_seed(11)
+    token_ids = (151_700 + torch.randperm(nh * Q, generator=g)).view(nh, Q)
+    input_ids = torch.randint(0, 151_000, (B, S), generator=g)
+    for b in range(B):
+        perm = torch.randperm(S, generator=g)[: nh * Q + 3]
+        input_ids[b, perm[: nh * Q]] = token_ids.reshape(-1)
+        input_ids[b, perm[nh * Q:]] = token_ids.reshape(-1)[:3]          # three placeholders appear twice
+        if b == 1:
+            input_ids[b, perm[2:6]] = 7                                  # this user misses four placeholders
+    base = torch.randn(B, S, Hd, generator=g).to(dtype)
+    toks = torch.randn(B, nh, Q, Hd, generator=g).to(dtype)
+    w = torch.randn(B, S, Hd, generator=g)
+
+    def run(dev, inject):
+        e = base.to(dev).clone().requires_grad_(True)
+        t = toks.to(dev).clone().requires_grad_(True)
+        out = inject(e * 1.0, input_ids.to(dev), token_ids, t)           # e * 1.0: a non-leaf, like an embedding lookup
+        (out.float() * w.to(dev)).sum().backward()
+        return out.detach().cpu(), e.grad.cpu(), t.grad.cpu()
+
+    ref_out, ref_de, ref_dt = run("cpu", JO.inject_tokens)
+    out, de, dt = run(DEV, inject_history_tokens)
+    assert torch.equal(out, ref_out)
+    tol = 0 if dtype == torch.float32 else 2e-2
+    assert float((de.float() - ref_de.float()).abs().max()) <= tol
+    assert float((dt.float() - ref_dt.float()).abs().max()) <= tol * 4 + 1e-6    # duplicates: two fp32 adds, order-free
+    assert float(dt.abs().sum()) > 0            # the Q-Former side does get a gradient
+
+
 def test_history_query_tokens_is_the_item_qformer_on_flattened_history():
     from unirec_b200 import synth
     from unirec_b200.joint import history_query_tokens

@@ -295,3 +295,54 @@ def test_nested_ranker_fused_gather_matches_builder_path_and_oracle():
     assert float(cos_ref.min()) > 0.999 and float(cos_plain.min()) > 0.999
     s, i = fused(history.to(DEV), lengths.to(DEV))
     assert tuple(s.shape) == (B, k) and bool((s[:, :-1] >= s[:, 1:]).all())
+
+
+def test_unknown_history_ids_are_zero_rows_on_both_user_paths():
+    """Ids outside [0, num_items) (-1 sentinels, items missing from the token table): the sequence builder treats them
+    as a ZERO token row whose slot keeps its position term and stays attended - never an out-of-bounds read - and the
+    gathered K/V projection does the same, so the two user-encoding paths agree on bad ids."""
+    from unirec_b200.modules import UserQFormer
+    from unirec_b200.pipeline import NestedRanker
+    N, Q, D, B, Hmax = 500, 32, 256, 6, 5
+    table = synth.normal("tok_table_bad", (N, Q, D), 35).to(torch.bfloat16)
+    gen = torch.Generator().manual_seed(36)
+    history = torch.randint(0, N, (B, Hmax), generator=gen)
+    history[0, 1], history[2, 0], history[3, 4], history[5, 2] = -1, N, N + 12345, -(2 ** 40)
+    lengths = torch.tensor([5, 3, 5, 5, 2, 4], dtype=torch.int32)
+    seq, mask = ops.build_user_sequence(table.to(DEV), history.to(DEV), lengths.to(DEV))
+    # oracle with a zero item appended for the unknown ids
+    table0 = torch.cat([table.float(), torch.zeros(1, Q, D)], 0)
+    known = (history >= 0) & (history < N)
+    ref_seq, ref_mask = O.build_user_sequences(table0, torch.where(known, history, torch.full_like(history, N)), lengths.long())
+    assert torch.equal(mask.cpu(), ref_mask.float())
+    assert float((seq.float().cpu() - ref_seq).abs().max()) <= 0.04
+    mk = dict(hidden=256, layers=2, inter=512, num_query=64, input_dim=256, num_predict=8)
+    um = UserQFormer(hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=512,
+                     num_query_tokens=64, input_embedding_dim=256, num_item_tokens_to_predict=8)
+    um.load_state_dict(synth.user_qformer_state_dict(**mk, seed=31, attn_std=0.1), strict=True)
+    um = um.to(DEV).eval()
+    cands = table.float().mean(dim=1).to(torch.bfloat16).to(DEV)
+    u_plain = NestedRanker(um, table.to(DEV), cands, k=10).encode_users(history.to(DEV), lengths.to(DEV)).float()
+    u_fused = NestedRanker(um, table.to(DEV), cands, k=10, fused_gather=True).encode_users(history.to(DEV), lengths.to(DEV)).float()
+    assert float(torch.nn.functional.cosine_similarity(u_plain, u_fused, dim=-1).min()) > 0.999
+
+
+def test_invalidate_packed_picks_up_data_writes():
+    """In-place writes through `.data` do not bump the version counter the bf16 weight cache is keyed on; the explicit
+    `invalidate_packed()` (also run by load_state_dict and .to()) makes the next forward use the new weights."""
+    from unirec_b200.modules import UserQFormer
+    mk = dict(hidden=256, layers=2, inter=512, num_query=64, input_dim=256, num_predict=8)
+    um = UserQFormer(hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=512,
+                     num_query_tokens=64, input_embedding_dim=256, num_item_tokens_to_predict=8)
+    um.load_state_dict(synth.user_qformer_state_dict(**mk, seed=31, attn_std=0.1), strict=True)
+    um = um.to(DEV).eval()
+    x = torch.randn(3, 64, 256, device=DEV)
+    m = torch.ones(3, 64, device=DEV)
+    a = um(x, m).clone()
+    um.qformer.encoder.layer[1].output_query.dense.weight.data.mul_(0.5)       # no version bump
+    um.invalidate_packed()
+    b = um(x, m).clone()
+    assert float((a - b).abs().max()) > 1e-3
+    sd2 = synth.user_qformer_state_dict(**mk, seed=31, attn_std=0.1)
+    um.load_state_dict(sd2, strict=True)                                       # the post-hook invalidates
+    assert torch.equal(um(x, m), a)

@@ -412,15 +412,47 @@ def test_train_step_graph_draws_fresh_dropout_masks_per_replay():
     model.dropout_seed = 999
     tg = TrainStepGraph(model, x, m, faithful=True)
     tg.seed_offset.zero_()
-    a = float(tg.step(x, m, x, x))
+    a = float(tg.step(x, m, x, x, m, m))
     grad_a = tg.grad_tensors()[5].clone()
-    b = float(tg.step(x, m, x, x))
+    b = float(tg.step(x, m, x, x, m, m))
     assert int(tg.seed_offset) == 2 * TrainStepGraph.SEED_STRIDE
     assert abs(a - b) > 1e-4 * abs(a), (a, b)          # different masks
     tg.seed_offset.zero_()
-    c = float(tg.step(x, m, x, x))
+    c = float(tg.step(x, m, x, x, m, m))
     assert abs(a - c) <= 1e-5 * abs(a) + 1e-6, (a, c)  # same masks (split-K atomics reorder fp32 sums only)
     torch.testing.assert_close(tg.grad_tensors()[5], grad_a, rtol=1e-3, atol=1e-5)
+
+
+def test_train_step_graph_faithful_uses_each_items_own_mask():
+    """The reference's step masks the positive and the negative item with THEIR attention masks
+    (training/item_qformer_training.py:123-124).  Dropout 0: the faithful graph step equals the eager step that runs
+    the three forwards with three different masks, and differs from the one that reuses the anchor's mask."""
+    from unirec_b200 import synth
+    from unirec_b200.training import TrainStepGraph, qformer_loss
+    B = 64
+    xs, ms = [], []
+    for sd_ in (91, 92, 93):
+        x_, m_ = synth.item_fields(batch=B, num_fields=6, dim=256, seed=sd_, clip_field=2, presence=0.6)
+        xs.append(x_.to(DEV))
+        ms.append(m_.to(DEV))
+    model = _small_train_model(0.0)
+
+    def eager_loss(mp, mn):
+        out = model(xs[0], ms[0])
+        with torch.no_grad():
+            p = model(xs[1], mp)["item_representation"]
+            n = model(xs[2], mn)["item_representation"]
+        return float(qformer_loss(out, xs[0], ms[0], p, n))
+
+    own, anchors = eager_loss(ms[1], ms[2]), eager_loss(ms[0], ms[0])
+    assert abs(own - anchors) > 1e-4 * abs(own)            # the masks matter on this input
+    import gc
+    gc.collect()                                           # no eager autograd graph may be alive at capture time
+    tg = TrainStepGraph(model, xs[0], ms[0], faithful=True)
+    got = float(tg.step(xs[0], ms[0], xs[1], xs[2], ms[1], ms[2]))
+    assert abs(got - own) <= 2e-3 * abs(own), (got, own, anchors)
+    with pytest.raises(ValueError):
+        tg.step(xs[0], ms[0], xs[1], xs[2])                # masks of the positive / negative items are required
 
 
 @pytest.mark.parametrize("H", [256, 1024])

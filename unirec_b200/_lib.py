@@ -73,6 +73,12 @@ _SIGNATURES = {
                                             c_float, c_void_p, c_void_p, c_void_p]),
     "unirec_inject_tokens": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int,
                                      c_int64, c_int64, c_void_p]),
+    "unirec_inject_tokens_backward": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int64,
+                                              c_void_p, c_int64, c_void_p]),
+    "unirec_context_hidden": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                      c_void_p, c_int64, c_void_p, c_void_p]),
+    "unirec_mwne_encode": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                   c_void_p, c_int, c_void_p]),
     "unirec_linear_gather_bf16": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64,
                                           c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p,
                                           c_int64, c_int64, c_int64, c_int64, c_void_p]),

@@ -67,6 +67,17 @@ int inject_tokens(const long long* input_ids, long long B, long long S, const lo
                   const void* tokens, int tokens_fp32, void* text_embeds, int text_fp32, long long ld_text, long long Hd,
                   cudaStream_t stream);
 
+int inject_tokens_backward(const long long* input_ids, long long B, long long S, const long long* token_ids,
+                           long long num_slots, void* d_text, int text_fp32, long long ld_text, float* d_tokens,
+                           long long Hd, cudaStream_t stream);
+
+int context_hidden(const void* timestamps, int ts_int64, const float* coords, const float* w1t, const float* b1t,
+                   const float* w1g, const float* b1g, long long n, long long hidden, void* out, long long ldo,
+                   float* feats, cudaStream_t stream);
+int mwne_encode(const float* numbers, long long n, const float* freqs, long long F, const float* fourier_w,
+                const float* raw_scale, const float* extra_w, const float* scale, long long D, void* out, int out_fp32,
+                cudaStream_t stream);
+
 int gemm_bf16_cg2_gather(const void* table, long long ld_table, long long table_rows, const long long* ids,
                          const int* lengths, long long slots_per_user, const void* pad_table, long long ld_pad,
                          long long pad_rows, const void* W, long long ldw, const float* bias, const void* posbias,
@@ -249,6 +260,28 @@ int unirec_inject_tokens(const int64_t* input_ids, int64_t B, int64_t S, const i
     COUNTED(inject_tokens(reinterpret_cast<const long long*>(input_ids), B, S, reinterpret_cast<const long long*>(token_ids),
                           num_slots, tokens, tokens_fp32, text_embeds, text_fp32, ld_text, Hd,
                           static_cast<cudaStream_t>(stream)));
+}
+
+int unirec_inject_tokens_backward(const int64_t* input_ids, int64_t B, int64_t S, const int64_t* token_ids,
+                                  int64_t num_slots, void* d_text, int text_fp32, int64_t ld_text, float* d_tokens,
+                                  int64_t Hd, void* stream) {
+    COUNTED(inject_tokens_backward(reinterpret_cast<const long long*>(input_ids), B, S,
+                                   reinterpret_cast<const long long*>(token_ids), num_slots, d_text, text_fp32, ld_text,
+                                   d_tokens, Hd, static_cast<cudaStream_t>(stream)));
+}
+
+int unirec_context_hidden(const void* timestamps, int ts_int64, const float* coords, const float* w1t, const float* b1t,
+                          const float* w1g, const float* b1g, int64_t n, int64_t hidden, void* out, int64_t ldo,
+                          float* feats, void* stream) {
+    COUNTED(context_hidden(timestamps, ts_int64, coords, w1t, b1t, w1g, b1g, n, hidden, out, ldo, feats,
+                           static_cast<cudaStream_t>(stream)));
+}
+
+int unirec_mwne_encode(const float* numbers, int64_t n, const float* freqs, int64_t F, const float* fourier_w,
+                       const float* raw_scale, const float* extra_w, const float* scale, int64_t D, void* out,
+                       int out_fp32, void* stream) {
+    COUNTED(mwne_encode(numbers, n, freqs, F, fourier_w, raw_scale, extra_w, scale, D, out, out_fp32,
+                        static_cast<cudaStream_t>(stream)));
 }
 
 int unirec_reconstruction_metrics(const void* rec, int rec_fp32, const float* orig, const float* mask, int64_t rows,

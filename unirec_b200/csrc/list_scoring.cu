@@ -336,6 +336,44 @@ inject_tokens_kernel(const long long* __restrict__ input_ids, long long rows, in
     }
 }
 
+
+// Backward of the injection: the gradient of an overwritten position flows to the token that replaced it and NOT to the
+// text embedding it replaced.  d_text (in place) = upstream gradient with the overwritten rows zeroed; d_tokens fp32
+// [B, num_slots, Hd] (zeroed by the caller) += the upstream rows of every position holding that slot's placeholder.
+template <bool TEXT_FP32>
+__global__ void __launch_bounds__(LS_THREADS)
+inject_tokens_backward_kernel(const long long* __restrict__ input_ids, long long rows, int S,
+                              const long long* __restrict__ token_ids, int num_slots, void* __restrict__ d_text,
+                              long long ld_text, float* __restrict__ d_tokens, int Hd) {
+    const long long row = (static_cast<long long>(blockIdx.x) * LS_THREADS + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const long long id = __ldg(input_ids + row);
+    int slot = -1;
+    for (int k0 = 0; k0 < num_slots; k0 += 32) {
+        const int k = k0 + lane;
+        const bool hit = k < num_slots && __ldg(token_ids + k) == id;
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (bal != 0u) slot = k0 + (31 - __clz(bal));       // same winner as the forward kernel
+    }
+    if (slot < 0) return;
+    const long long b = row / S;
+    unsigned char* g = reinterpret_cast<unsigned char*>(d_text) + static_cast<size_t>(row) * ld_text * (TEXT_FP32 ? 4 : 2);
+    float* dt = d_tokens + (static_cast<size_t>(b) * num_slots + slot) * Hd;
+    for (int vi = lane; vi < Hd / 8; vi += 32) {
+        float f[8];
+        load8<TEXT_FP32>(g, vi, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(dt + vi * 8 + j, f[j]);
+        if constexpr (TEXT_FP32) {
+            reinterpret_cast<float4*>(g)[2 * vi] = make_float4(0.f, 0.f, 0.f, 0.f);
+            reinterpret_cast<float4*>(g)[2 * vi + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            reinterpret_cast<uint4*>(g)[vi] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------- host launchers
 static int check_list_args(const char* what, const void* users, const void* pos, const void* cands, long long ldu,
                            long long ldp, long long ldc, long long B, long long C, long long D, int fp32,
@@ -448,6 +486,28 @@ int inject_tokens(const long long* input_ids, long long B, long long S, const lo
                                                                               text_embeds, ld_text, hd);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_last_error("inject_tokens launch: %s", cudaGetErrorString(e)); return UNIREC_ERR_CUDA; }
+    return UNIREC_OK;
+}
+
+int inject_tokens_backward(const long long* input_ids, long long B, long long S, const long long* token_ids,
+                           long long num_slots, void* d_text, int text_fp32, long long ld_text, float* d_tokens,
+                           long long Hd, cudaStream_t stream) {
+    if (input_ids == nullptr || token_ids == nullptr || d_text == nullptr || d_tokens == nullptr || B <= 0 || S <= 0 ||
+        num_slots <= 0 || Hd <= 0 || Hd % 8 != 0 || ld_text % (text_fp32 ? 4 : 8) != 0) {
+        set_last_error("inject_tokens_backward: null pointer, empty shape, Hd %% 8 != 0 or unaligned rows (Hd=%lld)", Hd);
+        return UNIREC_ERR_BAD_ARG;
+    }
+    const long long rows = B * S;
+    const unsigned blocks = static_cast<unsigned>((rows * 32 + LS_THREADS - 1) / LS_THREADS);
+    const int s = static_cast<int>(S), ns = static_cast<int>(num_slots), hd = static_cast<int>(Hd);
+    if (text_fp32)
+        inject_tokens_backward_kernel<true><<<blocks, LS_THREADS, 0, stream>>>(input_ids, rows, s, token_ids, ns, d_text,
+                                                                               ld_text, d_tokens, hd);
+    else
+        inject_tokens_backward_kernel<false><<<blocks, LS_THREADS, 0, stream>>>(input_ids, rows, s, token_ids, ns, d_text,
+                                                                                ld_text, d_tokens, hd);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_last_error("inject_tokens_backward launch: %s", cudaGetErrorString(e)); return UNIREC_ERR_CUDA; }
     return UNIREC_OK;
 }
 

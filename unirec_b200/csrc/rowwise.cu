@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(256)
 build_user_sequence_kernel(const __nv_bfloat16* __restrict__ table, const long long* __restrict__ history,
                            const int* __restrict__ lengths, const __nv_bfloat16* __restrict__ ctx,
                            const float* __restrict__ pe, __nv_bfloat16* __restrict__ seq, float* __restrict__ mask,
-                           int Hmax, int Q, int D, long long rows_total) {
+                           int Hmax, int Q, int D, long long rows_total, long long num_items) {
     const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= rows_total) return;
@@ -459,11 +459,15 @@ build_user_sequence_kernel(const __nv_bfloat16* __restrict__ table, const long l
         for (int vi = lane; vi < D / 8; vi += 32) reinterpret_cast<uint4*>(o)[vi] = make_uint4(0, 0, 0, 0);
         return;
     }
+    // ids outside [0, num_items) (sentinels, items missing from the token table) contribute a ZERO token row - the slot
+    // keeps its context / position terms and stays attended - exactly what the gathered K/V projection does for them
+    // (gemm_cg2.cu: TMA out-of-bounds fill); never an out-of-bounds read
     const long long item = history[b * Hmax + h];
-    const __nv_bfloat16* src = table + (item * Q + q) * D;
+    const bool known = item >= 0 && item < num_items;
+    const __nv_bfloat16* src = table + ((known ? item : 0) * Q + q) * D;
     const float neg_ln1e4_over_d = -9.210340371976184f / static_cast<float>(D);
     for (int vi = lane; vi < D / 8; vi += 32) {
-        const uint4 a = __ldg(reinterpret_cast<const uint4*>(src) + vi);
+        const uint4 a = known ? __ldg(reinterpret_cast<const uint4*>(src) + vi) : make_uint4(0, 0, 0, 0);
         float x[8] = {bf16_lo(a.x), bf16_hi(a.x), bf16_lo(a.y), bf16_hi(a.y),
                       bf16_lo(a.z), bf16_hi(a.z), bf16_lo(a.w), bf16_hi(a.w)};
         if (ctx != nullptr) {
@@ -494,9 +498,8 @@ build_user_sequence_kernel(const __nv_bfloat16* __restrict__ table, const long l
 int build_user_sequence(const void* table, long long num_items, const long long* history, const int* lengths,
                         const void* ctx, const float* pe, void* seq, float* mask, long long B, long long Hmax, long long Q,
                         long long D, cudaStream_t stream) {
-    (void)num_items;
     if (table == nullptr || history == nullptr || lengths == nullptr || seq == nullptr || mask == nullptr || B <= 0 ||
-        Hmax <= 0 || Q <= 0 || D % 8 != 0) {
+        Hmax <= 0 || Q <= 0 || D % 8 != 0 || num_items <= 0) {
         set_last_error("build_user_sequence: bad arguments (B=%lld Hmax=%lld Q=%lld D=%lld)", B, Hmax, Q, D);
         return UNIREC_ERR_BAD_ARG;
     }
@@ -504,7 +507,7 @@ int build_user_sequence(const void* table, long long num_items, const long long*
     const long long blocks = (rows * 32 + 255) / 256;
     build_user_sequence_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(table), history, lengths, reinterpret_cast<const __nv_bfloat16*>(ctx), pe,
-        reinterpret_cast<__nv_bfloat16*>(seq), mask, (int)Hmax, (int)Q, (int)D, rows);
+        reinterpret_cast<__nv_bfloat16*>(seq), mask, (int)Hmax, (int)Q, (int)D, rows, num_items);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_last_error("build_user_sequence launch: %s", cudaGetErrorString(e));

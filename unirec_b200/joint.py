@@ -33,13 +33,41 @@ def history_query_tokens(qformer_model, history_field_embeddings: torch.Tensor,
     return out.view(bh, num_hist, out.shape[1], out.shape[2])
 
 
+class _InjectFn(torch.autograd.Function):
+    """The reference's overwrite `text_embeds[b, positions] = query_embeddings[b]` (:160-171) is a differentiable
+    index assignment: it is the only path by which the joint trainer's loss reaches the item Q-Former.  Forward = the
+    in-place kernel (text_embeds is marked dirty, so autograd sees the version bump); backward = one kernel that moves the
+    gradient of every overwritten position to the token that replaced it and zeroes it for the text embedding."""
+
+    @staticmethod
+    def forward(ctx, text_embeds, input_ids, token_ids, tokens):
+        ctx.mark_dirty(text_embeds)
+        ctx.save_for_backward(input_ids, token_ids)
+        ctx.tok_dtype = tokens.dtype
+        ops.inject_tokens(text_embeds, input_ids, token_ids, tokens.detach())
+        return text_embeds
+
+    @staticmethod
+    def backward(ctx, d_out):
+        input_ids, token_ids = ctx.saved_tensors
+        d_text = d_out.contiguous().clone()
+        d_tokens = ops.inject_tokens_backward(d_text, input_ids, token_ids)
+        return (d_text if ctx.needs_input_grad[0] else None), None, None, \
+            (d_tokens.to(ctx.tok_dtype) if ctx.needs_input_grad[3] else None)
+
+
 def inject_history_tokens(text_embeds: torch.Tensor, input_ids: torch.Tensor, token_ids: torch.Tensor,
                           history_item_query_tokens: torch.Tensor) -> torch.Tensor:
     """text_embeds[b, positions of <|history_item_i_query_j|>] = history_item_query_tokens[b, i, j] for every (i, j)
-    (:160-171), in place.  token_ids int64 [num_hist, Q] (or flat): tokenizer ids of the placeholder tokens."""
+    (:160-171), in place and differentiable: gradients reach `history_item_query_tokens` (hence the item Q-Former) and
+    stop at the overwritten rows of `text_embeds`, exactly like the reference's indexed assignment.
+    token_ids int64 [num_hist, Q] (or flat): tokenizer ids of the placeholder tokens."""
     B, nh, Q, Hd = history_item_query_tokens.shape
     toks = history_item_query_tokens.reshape(B, nh * Q, Hd)
-    return ops.inject_tokens(text_embeds, input_ids, token_ids.reshape(-1).to(text_embeds.device), toks)
+    tids = token_ids.reshape(-1).to(text_embeds.device)
+    if torch.is_grad_enabled() and (text_embeds.requires_grad or toks.requires_grad):
+        return _InjectFn.apply(text_embeds, input_ids, tids, toks)
+    return ops.inject_tokens(text_embeds, input_ids, tids, toks)
 
 
 class _InfoNCEFn(torch.autograd.Function):

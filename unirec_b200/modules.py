@@ -115,6 +115,7 @@ class QFormerBackbone(nn.Module):
         self._pack: Optional[dict] = None
         self._pack_key = None
         self.hoist_layer0 = True        # compute the batch-invariant head of the encoder once (see `encode`)
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
 
     def _init_weights(self):
         # reference rule, models/qformer.py:664-674: N(0, initializer_range) weights, zero bias, LN (1, 0)
@@ -143,10 +144,20 @@ class QFormerBackbone(nn.Module):
                    lyr.output_query.LayerNorm.weight, lyr.output_query.LayerNorm.bias]
         return ps
 
+    def invalidate_packed(self):
+        """Drop the cached bf16 weight pack.  The cache key is the parameters' autograd version counters, which in-place
+        writes through `.data` do NOT bump (`dist.broadcast(p.data, 0)`, `p.data.copy_()`, EMA weight swaps): call this
+        after such an update.  `load_state_dict` and `.to()` / `.half()`-style `_apply` calls do it automatically."""
+        self._pack = self._pack_key = None
+
+    def _apply(self, fn, *a, **k):
+        self.invalidate_packed()
+        return super()._apply(fn, *a, **k)
+
     def packed(self) -> dict:
-        """bf16 / fused copies of the live weights, rebuilt only when a parameter changed."""
+        """bf16 / fused copies of the live weights, rebuilt only when a parameter changed (see `invalidate_packed`)."""
         live = self._live_params()
-        key = (live[0].device, tuple(p._version for p in live), tuple(p.data_ptr() for p in live[:4]))
+        key = (live[0].device, tuple(p._version for p in live), tuple(p.data_ptr() for p in live))
         if self._pack is not None and self._pack_key == key:
             return self._pack
         bf = torch.bfloat16
@@ -323,6 +334,7 @@ class QFormerForItemRepresentation(nn.Module):
         self.item_representation_head = nn.Linear(hidden_size, field_embedding_dim)
         self.reconstruction_head = nn.Linear(hidden_size, field_embedding_dim)
         self.field_projection = nn.Linear(num_query_tokens, num_fields)
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
         self.output_dtype = torch.float32          # the reference returns fp32 tensors
         self.prelayernorm_dtype = torch.float32
         self._head_pack = None
@@ -351,6 +363,15 @@ class QFormerForItemRepresentation(nn.Module):
         if self.dropout_seed_offset is not None:
             return self.last_dropout + (self.dropout_seed_offset,)
         return self.last_dropout
+
+    def invalidate_packed(self):
+        """Forget every cached bf16 weight copy (backbone and heads); see QFormerBackbone.invalidate_packed."""
+        self._head_pack = self._head_key = None
+        self.qformer.invalidate_packed()
+
+    def _apply(self, fn, *a, **k):
+        self._head_pack = self._head_key = None
+        return super()._apply(fn, *a, **k)
 
     def _heads(self):
         ps = [self.item_representation_head.weight, self.item_representation_head.bias,
@@ -437,6 +458,7 @@ class UserQFormer(nn.Module):
             nn.Linear(hidden_size, num_item_tokens_to_predict * input_embedding_dim))
         self.num_item_tokens_to_predict = num_item_tokens_to_predict
         self.input_embedding_dim = input_embedding_dim
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
         self.output_dtype = torch.float32
         self.prelayernorm_dtype = torch.float32
         # cross-attention K/V for all layers are materialised per chunk of users:
@@ -444,6 +466,15 @@ class UserQFormer(nn.Module):
         self.max_kv_bytes = 14 << 30               # K/V of all layers for one chunk of users (512 users at S = 1600)
         self._head_pack = None
         self._head_key = None
+
+    def invalidate_packed(self):
+        """Forget every cached bf16 weight copy (backbone and head); see QFormerBackbone.invalidate_packed."""
+        self._head_pack = self._head_key = None
+        self.qformer.invalidate_packed()
+
+    def _apply(self, fn, *a, **k):
+        self._head_pack = self._head_key = None
+        return super()._apply(fn, *a, **k)
 
     def _heads(self):
         ph = self.prediction_head

@@ -607,6 +607,93 @@ def inject_tokens(text_embeds: torch.Tensor, input_ids: torch.Tensor, token_ids:
     return text_embeds
 
 
+def inject_tokens_backward(d_text: torch.Tensor, input_ids: torch.Tensor, token_ids: torch.Tensor) -> torch.Tensor:
+    """Backward of `inject_tokens`: d_text [B, S, Hd] (fp32 / bf16, contiguous) is the upstream gradient and is edited in
+    place (rows of overwritten positions -> 0); returns d_tokens fp32 [B, slots, Hd]."""
+    if d_text.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError("inject_tokens_backward: d_text must be fp32 or bf16")
+    _req(d_text, d_text.dtype, "inject_tokens_backward.d_text")
+    _req(input_ids, torch.int64, "inject_tokens_backward.input_ids")
+    _req(token_ids, torch.int64, "inject_tokens_backward.token_ids")
+    B, S, Hd = d_text.shape
+    slots = token_ids.numel()
+    if not d_text.is_contiguous() or tuple(input_ids.shape) != (B, S):
+        raise RuntimeError("inject_tokens_backward: expected contiguous d_text [B, S, Hd] and input_ids [B, S]")
+    d_tokens = torch.zeros(B, slots, Hd, device=d_text.device, dtype=torch.float32)
+    rc = _lib.load().unirec_inject_tokens_backward(input_ids.contiguous().data_ptr(), B, S, token_ids.contiguous().data_ptr(),
+                                                   slots, d_text.data_ptr(), 1 if d_text.dtype == torch.float32 else 0, Hd,
+                                                   d_tokens.data_ptr(), Hd, _stream())
+    _lib.check(rc, "unirec_inject_tokens_backward")
+    return d_tokens
+
+
+def context_hidden(timestamps: Optional[torch.Tensor], coords: Optional[torch.Tensor], w1t, b1t, w1g, b1g, hidden: int,
+                   want_features: bool = False):
+    """First halves of the Timestamp / GeoCoordinate encoders (models/mwne.py:504-610) for n events: returns bf16
+    [n, 2 * hidden] = [gelu(W1t f_time + b1t) | gelu(W1g f_geo + b1g)] (and the fp32 [n, 12] raw features if asked).
+    timestamps [n] fp32 / int64 or None; coords fp32 [n, 2] (lat, lon degrees) or None."""
+    if timestamps is None and coords is None:
+        raise RuntimeError("context_hidden: timestamps and coords are both None")
+    ref = timestamps if timestamps is not None else coords
+    if not ref.is_cuda:
+        raise RuntimeError("context_hidden: expected CUDA tensors (unirec_b200 has no CPU path)")
+    ts_int64 = 0
+    if timestamps is not None:
+        if timestamps.dtype in (torch.float64, torch.int32):
+            timestamps = timestamps.float()          # the reference's `.float()` (models/mwne.py:527)
+        if timestamps.dtype not in (torch.float32, torch.int64):
+            raise RuntimeError("context_hidden: timestamps must be fp32 / fp64 / int32 / int64")
+        ts_int64 = 1 if timestamps.dtype == torch.int64 else 0
+        timestamps = timestamps.contiguous().view(-1)
+        n = timestamps.numel()
+        for t, nm in ((w1t, "w1t"), (b1t, "b1t")):
+            _req(t, torch.float32, f"context_hidden.{nm}")
+        if tuple(w1t.shape) != (hidden, 9) or not w1t.is_contiguous():
+            raise RuntimeError("context_hidden: w1t must be contiguous [hidden, 9]")
+    if coords is not None:
+        _req(coords, torch.float32, "context_hidden.coords")
+        if coords.dim() != 2 or coords.shape[1] != 2:
+            raise ValueError("Input coordinates must be of shape [batch_size, 2]")      # models/mwne.py:593-594
+        coords = coords.contiguous()
+        n = coords.shape[0]
+        for t, nm in ((w1g, "w1g"), (b1g, "b1g")):
+            _req(t, torch.float32, f"context_hidden.{nm}")
+        if tuple(w1g.shape) != (hidden, 3) or not w1g.is_contiguous():
+            raise RuntimeError("context_hidden: w1g must be contiguous [hidden, 3]")
+    if timestamps is not None and coords is not None and timestamps.numel() != coords.shape[0]:
+        raise RuntimeError("context_hidden: timestamps and coords describe different numbers of events")
+    out = torch.empty(n, 2 * hidden, device=ref.device, dtype=torch.bfloat16)
+    feats = torch.zeros(n, 12, device=ref.device, dtype=torch.float32) if want_features else None
+    rc = _lib.load().unirec_context_hidden(_ptr(timestamps), ts_int64, _ptr(coords), _ptr(w1t) if timestamps is not None else None,
+                                           _ptr(b1t) if timestamps is not None else None,
+                                           _ptr(w1g) if coords is not None else None,
+                                           _ptr(b1g) if coords is not None else None, n, hidden, out.data_ptr(), 2 * hidden,
+                                           _ptr(feats), _stream())
+    _lib.check(rc, "unirec_context_hidden")
+    return (out, feats) if want_features else out
+
+
+def mwne_encode(numbers: torch.Tensor, freqs: torch.Tensor, fourier_w: torch.Tensor, raw_scale: Optional[torch.Tensor],
+                extra_w: Optional[torch.Tensor], scale: Optional[torch.Tensor], dim: int,
+                out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """ImprovedMathematicalEncoder.forward (+ optional eval-mode normaliser scale); numbers fp32 [n] -> [n, dim]."""
+    _req(numbers, torch.float32, "mwne_encode.numbers")
+    for t, nm in ((freqs, "freqs"), (fourier_w, "fourier_w"), (raw_scale, "raw_scale"), (extra_w, "extra_w"),
+                  (scale, "scale")):
+        if t is not None:
+            _req(t, torch.float32, f"mwne_encode.{nm}")
+            if not t.is_contiguous():
+                raise RuntimeError(f"mwne_encode.{nm} must be contiguous")
+    x = numbers.contiguous().view(-1)
+    n = x.numel()
+    out = torch.empty(n, dim, device=numbers.device, dtype=out_dtype)
+    rc = _lib.load().unirec_mwne_encode(x.data_ptr(), n, freqs.data_ptr(), freqs.numel(), fourier_w.data_ptr(),
+                                        _ptr(raw_scale), _ptr(extra_w), _ptr(scale), dim, out.data_ptr(),
+                                        1 if out_dtype == torch.float32 else 0, _stream())
+    _lib.check(rc, "unirec_mwne_encode")
+    return out
+
+
 def reconstruction_metrics(reconstructed: torch.Tensor, original: torch.Tensor, attention_mask: torch.Tensor,
                            acc: Optional[torch.Tensor] = None, eps: float = 1e-12) -> torch.Tensor:
     """acc (float64 [3], created zeroed if None) += [sum of squared errors, sum of cosine similarities, count] over the

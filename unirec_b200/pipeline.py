@@ -83,7 +83,8 @@ def generate_item_tokens_streamed(model: QFormerForItemRepresentation, fields_ho
     run on their own streams while chunk i is encoded (the reference serialises copy -> model -> copy and synchronises
     per batch).  fields_host [N, F, E] fp32 and tokens_host_out [N, Q, H] bf16 should be PINNED for the copies to be
     asynchronous; at most `depth` chunks are in flight.  Returns pooled candidate vectors bf16 [N, H] on the device
-    (`pooled_out` if given).  The caller's stream is synchronised with the last copy on return."""
+    (`pooled_out` if given).  On return `tokens_host_out` is COMPLETE: the last device-to-host copy has been waited for on
+    the host (the reference's `.cpu()` is host-synchronous too); `pooled_out` is ordered on the caller's stream."""
     dev = device or next(model.parameters()).device
     if dev.type != "cuda":
         raise RuntimeError("generate_item_tokens_streamed: the model must live on a CUDA device (no CPU path)")
@@ -117,6 +118,8 @@ def generate_item_tokens_streamed(model: QFormerForItemRepresentation, fields_ho
             done.append(s_out.record_event())
         tok.record_stream(s_out)
     cur.wait_stream(s_out)
+    if done:
+        done[-1].synchronize()          # copies on s_out complete in order: the host buffer is fully written
     return pooled_out
 
 

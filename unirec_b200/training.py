@@ -259,19 +259,41 @@ class BackboneTrainFn(torch.autograd.Function):
         return (None, None, None, None, d_query) + tuple(grads)
 
 
+class QFormerLoss(torch.nn.Module):
+    """Drop-in for the reference's QFormerLoss (training/item_qformer_training.py:41-56): same constructor defaults
+    (`reconstruction_weight=1.0, contrastive_weight=0.5, margin=0.5`), same call
+    `criterion(model_output, input_embeddings, pos_rep, neg_rep, attention_mask)` with `model_output` / `input_embeddings`
+    dicts (`reconstructed_fields`, `item_representation` / `field_embeddings`) and the same 3-tuple
+    `(total, masked_recon_loss, cont_loss)`.  Masked MSE summed over fields and embedding dimension, divided by the number
+    of valid FIELDS (:50-52 - not by fields x dimension); TripletMarginLoss(margin, p=2, eps=1e-6, mean) on
+    item_representation (:45, :54).  Stays in PyTorch (0.003 % of the step's FLOPs); fp32."""
+
+    def __init__(self, reconstruction_weight=1.0, contrastive_weight=0.5, margin=0.5):
+        super().__init__()
+        self.recon_w = reconstruction_weight
+        self.cont_w = contrastive_weight
+        self.margin = margin
+
+    def forward(self, model_output, input_embeddings, pos_rep, neg_rep, attention_mask):
+        rec = model_output["reconstructed_fields"].float()
+        target = input_embeddings["field_embeddings"].float()
+        mask = attention_mask.to(rec.dtype)
+        masked_recon_loss = (((rec - target) ** 2) * mask.unsqueeze(-1)).sum() / mask.sum()
+        cont_loss = torch.nn.functional.triplet_margin_loss(model_output["item_representation"].float(), pos_rep.float(),
+                                                            neg_rep.float(), margin=self.margin, p=2)
+        return self.recon_w * masked_recon_loss + self.cont_w * cont_loss, masked_recon_loss, cont_loss
+
+
 def qformer_loss(outputs, field_embeddings, attention_mask, pos_rep=None, neg_rep=None, recon_weight: float = 1.0,
-                 contrastive_weight: float = 0.25, margin: float = 0.5):
-    """QFormerLoss of the reference (training/item_qformer_training.py:41-56): masked MSE summed over the embedding
-    dimension and divided by the number of valid fields, plus contrastive_weight * TripletMarginLoss(margin, p=2)
-    on item_representation when positive / negative representations are given."""
-    rec = outputs["reconstructed_fields"].float()
-    mask = attention_mask.to(rec.dtype)
-    mse = (rec - field_embeddings.float()) ** 2
-    loss = recon_weight * (mse * mask.unsqueeze(-1)).sum() / mask.sum()
-    if pos_rep is not None and neg_rep is not None:
-        loss = loss + contrastive_weight * torch.nn.functional.triplet_margin_loss(
-            outputs["item_representation"].float(), pos_rep.float(), neg_rep.float(), margin=margin, p=2)
-    return loss
+                 contrastive_weight: float = 0.5, margin: float = 0.5):
+    """Total loss of `QFormerLoss` (reference defaults) as a plain function; without positive / negative representations
+    only the reconstruction term (what a validation pass logs, training/item_qformer_training.py:150-155)."""
+    if pos_rep is None or neg_rep is None:
+        rec = outputs["reconstructed_fields"].float()
+        mask = attention_mask.to(rec.dtype)
+        return recon_weight * (((rec - field_embeddings.float()) ** 2) * mask.unsqueeze(-1)).sum() / mask.sum()
+    return QFormerLoss(recon_weight, contrastive_weight, margin)(outputs, {"field_embeddings": field_embeddings},
+                                                                pos_rep, neg_rep, attention_mask)[0]
 
 
 class GradientAllReducer:
@@ -415,8 +437,11 @@ class TrainStepGraph:
         self.fields = field_embeddings.detach().clone()
         self.mask = attention_mask.detach().clone()
         if faithful:
+            # the positive / negative items are masked with THEIR OWN attention masks (item_qformer_training.py:123-124)
             self.fields_pos = torch.zeros_like(self.fields)
             self.fields_neg = torch.zeros_like(self.fields)
+            self.mask_pos = self.mask.clone()
+            self.mask_neg = self.mask.clone()
         else:
             self.pos = torch.zeros(B, E, device=dev)
             self.neg = torch.zeros(B, E, device=dev)
@@ -458,8 +483,8 @@ class TrainStepGraph:
         out = model(self.fields, self.mask)
         if self.faithful:
             with torch.no_grad():
-                p_rep = model(self.fields_pos, self.mask)["item_representation"]
-                n_rep = model(self.fields_neg, self.mask)["item_representation"]
+                p_rep = model(self.fields_pos, self.mask_pos)["item_representation"]
+                n_rep = model(self.fields_neg, self.mask_neg)["item_representation"]
         else:
             p_rep, n_rep = self.pos, self.neg
         loss = qformer_loss(out, self.fields, self.mask, p_rep, n_rep, **self.loss_kwargs)
@@ -470,10 +495,18 @@ class TrainStepGraph:
         return [g for _, g in self.grads]
 
     def step(self, field_embeddings: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
-             pos: Optional[torch.Tensor] = None, neg: Optional[torch.Tensor] = None) -> torch.Tensor:
+             pos: Optional[torch.Tensor] = None, neg: Optional[torch.Tensor] = None,
+             pos_mask: Optional[torch.Tensor] = None, neg_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Copies the batch into the graph's static inputs (device-to-device, on the current stream), replays the graph
         and returns the loss (a static tensor: read it before the next step).  `pos` / `neg` are the positive / negative
-        REPRESENTATIONS [B, E] (faithful=False) or their FIELD EMBEDDINGS [B, F, E] (faithful=True)."""
+        REPRESENTATIONS [B, E] (faithful=False) or their FIELD EMBEDDINGS [B, F, E] (faithful=True); in the faithful step
+        `pos_mask` / `neg_mask` [B, F] are those items' own attention masks (item_qformer_training.py:123-124) and are
+        required whenever `pos` / `neg` are given."""
+        if self.faithful and ((pos is not None and pos_mask is None) or (neg is not None and neg_mask is None)):
+            raise ValueError("TrainStepGraph(faithful=True).step: pass pos_mask / neg_mask with pos / neg (the reference "
+                             "masks the positive and negative items with their own attention masks)")
+        if not self.faithful and (pos_mask is not None or neg_mask is not None):
+            raise ValueError("TrainStepGraph(faithful=False).step: pos / neg are representations and take no mask")
         self.fields.copy_(field_embeddings, non_blocking=True)
         if attention_mask is not None:
             self.mask.copy_(attention_mask, non_blocking=True)
@@ -481,6 +514,10 @@ class TrainStepGraph:
             (self.fields_pos if self.faithful else self.pos).copy_(pos, non_blocking=True)
         if neg is not None:
             (self.fields_neg if self.faithful else self.neg).copy_(neg, non_blocking=True)
+        if pos_mask is not None:
+            self.mask_pos.copy_(pos_mask, non_blocking=True)
+        if neg_mask is not None:
+            self.mask_neg.copy_(neg_mask, non_blocking=True)
         self.graph.replay()
         self.replays += 1
         for p, g in self.grads:
