@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define UNIREC_B200_ABI_VERSION 2
+#define UNIREC_B200_ABI_VERSION 3
 
 #define UNIREC_OK 0
 #define UNIREC_ERR_BAD_ARG 1

@@ -1,9 +1,10 @@
-"""In-container shim that imports the UNMODIFIED reference from /root/reference.
+"""Shim that imports the UNMODIFIED reference - from /root/reference in the authoring container, or from the verbatim
+copy oracle/_ref/ (oracle/build_ref.py; git-ignored, travels with the gpurun snapshot) on the GPU box.
 
-TEST INFRASTRUCTURE ONLY.  Used by oracle/pin_against_reference.py to (a) pin the
-CPU restatement in oracle/qformer_oracle.py against the reference's own code and
-(b) generate the golden vectors under tests/golden/.  /root/reference does not
-exist on the GPU box, so nothing in tests/, bench.py or smoke() imports this file.
+TEST / BASELINE INFRASTRUCTURE ONLY.  Used by oracle/pin_*_against_reference.py to (a) pin the CPU restatement in
+oracle/qformer_oracle.py against the reference's own code and (b) generate the golden vectors under tests/golden/, and
+by bench.py's `--impl reference` arm and same-GPU eager comparator (oracle/reference_runner.py).  Nothing under
+unirec_b200/ imports it.
 
 The reference was written against transformers ~4.x (models/qformer.py:39-44);
 this image has 5.5.0, so a few moved / removed helpers are patched in before the
@@ -12,7 +13,14 @@ import.  No reference file is modified.
 import sys
 import types
 
-REFERENCE_ROOT = "/root/reference"
+import os
+
+_REF_COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REFERENCE_ROOT = "/root/reference" if os.path.isdir("/root/reference/models") else _REF_COPY
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "models", "qformer.py"))
 
 
 def install():

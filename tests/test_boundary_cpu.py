@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/unirec_b200.h but not exported"
     # the ctypes binding covers exactly the declared surface
     assert set(_lib.EXPORTED_SYMBOLS) == declared
-    assert _lib.load().unirec_abi_version() == 2
+    assert _lib.load().unirec_abi_version() == 3
 
 
 def test_workspace_query_is_host_only():
@@ -199,4 +199,4 @@ def test_plain_c_program_binds_the_abi(tmp_path):
     subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
                     os.path.join(ROOT, "examples", "c_abi_probe.c"), "-ldl", "-o", exe], check=True)
     out = subprocess.run([exe, _lib.LIB_PATH], check=True, capture_output=True, text=True).stdout
-    assert out.startswith("abi 2,") and "rc 1" in out
+    assert out.startswith("abi 3,") and "rc 1" in out

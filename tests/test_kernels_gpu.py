@@ -325,3 +325,54 @@ def test_torch_ops_match_direct_wrappers():
         assert tuple(fy.shape) == (300, 512) and fy.dtype == torch.float32 and fy.device.type == "cuda"
     with pytest.raises(NotImplementedError):
         ns.mean_tokens(torch.zeros(2, 4, 64, dtype=torch.bfloat16), False)
+
+
+def test_torch_ops_autograd():
+    """`register_autograd` of torch.ops.unirec_b200.{linear, layernorm, attention}: a small attention block written
+    against the dispatcher ops trains under eager autograd; gradients against torch fp32 autograd of the same math on
+    the same (bf16-rounded) inputs.  Tolerance: bf16 gradients - cosine >= 0.999, relative error <= 3 %."""
+    import unirec_b200.torch_ops  # noqa: F401
+    ns = torch.ops.unirec_b200
+    g = torch.Generator(device="cpu").manual_seed(9)
+    B, heads, nq, nk, H = 5, 4, 32, 14, 256
+
+    def leaf(*shape, scale=1.0, dtype=torch.bfloat16):
+        return (torch.randn(*shape, generator=g) * scale).to(dtype).to(_dev()).requires_grad_(True)
+
+    x, enc = leaf(B * nq, H), leaf(B * nk, H)
+    wq, wk, wv, wo = (leaf(H, H, scale=0.06) for _ in range(4))
+    bq, bo = leaf(H, dtype=torch.float32), leaf(H, dtype=torch.float32)
+    gam, bet = leaf(H, dtype=torch.float32), leaf(H, dtype=torch.float32)
+    w1 = leaf(2 * H, H, scale=0.06)
+    b1 = leaf(2 * H, dtype=torch.float32)
+    mask = (torch.rand(B, nk, generator=g) < 0.8).float().to(_dev())
+    wsum = torch.randn(B * nq, 2 * H, generator=g).to(_dev())
+    params = [x, enc, wq, wk, wv, wo, bq, bo, gam, bet, w1, b1]
+
+    q = ns.linear(x, wq, bq, None, 0, False)
+    k = ns.linear(enc, wk, None, None, 0, False)
+    v = ns.linear(enc, wv, None, None, 0, False)
+    ctx = ns.attention(q, k, v, mask, B, heads, nq, nk, False)
+    pre = ns.linear(ctx, wo, bo, x, 2, False)                       # bias + residual epilogue
+    h = ns.layernorm(pre, gam, bet, 1e-12, None, 0, 0, False)
+    y = ns.linear(h, w1, b1, None, 1, True)                         # bias + erf-GELU epilogue, fp32 out
+    (y * wsum).sum().backward()
+    got = [p.grad.float().cpu() for p in params]
+
+    ref_p = [p.detach().float().cpu().requires_grad_(True) for p in params]
+    rx, renc, rwq, rwk, rwv, rwo, rbq, rbo, rgam, rbet, rw1, rb1 = ref_p
+    F = torch.nn.functional
+    rq = F.linear(rx, rwq, rbq).view(B, nq, heads, 64).transpose(1, 2)
+    rk = F.linear(renc, rwk).view(B, nk, heads, 64).transpose(1, 2)
+    rv = F.linear(renc, rwv).view(B, nk, heads, 64).transpose(1, 2)
+    sc = rq @ rk.transpose(-1, -2) / 8.0 + ((1.0 - mask.cpu()) * torch.finfo(torch.float32).min)[:, None, None, :]
+    rctx = (torch.softmax(sc, dim=-1) @ rv).transpose(1, 2).reshape(B * nq, H)
+    rh = F.layer_norm(F.linear(rctx, rwo, rbo) + rx, (H,), rgam, rbet, 1e-12)
+    ry = F.gelu(F.linear(rh, rw1, rb1))
+    (ry * wsum.cpu()).sum().backward()
+    names = ["x", "enc", "wq", "wk", "wv", "wo", "bq", "bo", "gamma", "beta", "w1", "b1"]
+    for n, a, r in zip(names, got, ref_p):
+        cos = float(F.cosine_similarity(a.flatten(), r.grad.flatten(), dim=0))
+        rel = float((a - r.grad).norm() / (r.grad.norm() + 1e-12))
+        print(f"{n:6s} cos={cos:.5f} rel={rel:.4f}")
+        assert cos >= 0.999 and rel <= 0.03, (n, cos, rel)

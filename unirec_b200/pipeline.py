@@ -169,6 +169,7 @@ class NestedRanker:
         # True: the K/V projection gathers the history tokens itself (UserQFormer.encode_queries_from_history) instead of
         # reading a materialised user sequence; used when no per-user context vector is given
         self.fused_gather = fused_gather
+        self.last_user_vectors: Optional[torch.Tensor] = None
 
     @torch.no_grad()
     def encode_users(self, history: torch.Tensor, lengths: torch.Tensor,
@@ -197,6 +198,7 @@ class NestedRanker:
         """user_vectors bf16 [B_local, D] (this rank's users).  Returns (scores fp32 [B, k], idx int64
         [B, k]) for ALL users of the group, identical on every rank."""
         u_all = gather_rows(user_vectors, self.group)
+        self.last_user_vectors = u_all          # kept for parity checks on rows of a timed call (bench.py, tests)
         s, i = ops.score_topk(u_all, self.candidates, self.k, cand_inv=self.cand_inv, index_base=self.index_base)
         s_all, i_all = gather_lists(s, i, self.group)
         if s_all.shape[0] == 1:

@@ -5,8 +5,11 @@ The reference has no custom ops of its own; this layer is what BA
 (CUDA only - there is no CPU kernel to dispatch to, a CPU tensor raises NotImplementedError) together with a fake /
 meta implementation for shape inference, so the ops can be used under FakeTensorMode / `torch.export` and from code
 that only knows the dispatcher.  Each op body is the ctypes wrapper of `unirec_b200.ops` (one kernel launch on the
-current stream).  The nn.Module mirrors in `modules.py` call those wrappers directly - the same launches without the
-dispatcher's per-call cost; `tests/test_kernels_gpu.py::test_torch_ops_match_direct_wrappers` pins the two together.
+current stream).  `linear`, `layernorm` and `attention` also carry `register_autograd` backward formulas on the C ABI's
+backward kernels, so a model written against `torch.ops.unirec_b200.*` trains under eager autograd.  The nn.Module
+mirrors in `modules.py` call the ctypes wrappers directly - the same launches without the dispatcher's per-call cost
+(~10 us x ~435 launches per training step), with the whole backbone as ONE autograd.Function;
+`tests/test_kernels_gpu.py::test_torch_ops_match_direct_wrappers` / `::test_torch_ops_autograd` pin the two together.
 
     import unirec_b200.torch_ops                      # registers the namespace
     y = torch.ops.unirec_b200.linear(x, w, b, None, 0, False)
@@ -68,6 +71,88 @@ def attention(q: Tensor, k: Tensor, v: Tensor, key_mask: Optional[Tensor], batch
 @attention.register_fake
 def _(q, k, v, key_mask, batch, num_heads, nq, nk, q_broadcast):
     return q.new_empty(batch * nq, num_heads * 64, dtype=_BF16)
+
+
+# ------------------------------------------------------------------------------------------------ autograd
+# Backward formulas of the three differentiable building blocks, on the backward kernels of the C ABI (the same ones
+# training.BackboneTrainFn drives): tcgen05 dgrad / split-K wgrad GEMMs that read operands in place, the LayerNorm and
+# small-tile attention backward kernels.  Eager autograd only (the backward bodies launch kernels through ctypes).
+def _linear_setup(ctx, inputs, output):
+    a, weight, bias, residual, epilogue, out_fp32 = inputs
+    ctx.save_for_backward(a, weight, bias)
+    ctx.epilogue, ctx.has_bias, ctx.has_res = epilogue, bias is not None, residual is not None
+    ctx.res_dtype = None if residual is None else residual.dtype
+
+
+def _linear_backward(ctx, dy):
+    a, weight, bias = ctx.saved_tensors
+    N, K = weight.shape
+    dy2 = dy.reshape(-1, N).to(_BF16).contiguous()
+    a2 = a.reshape(-1, K)
+    if ctx.epilogue == ops.EPI_BIAS_GELU:
+        # the fused forward does not keep the pre-activation: recompute it (one GEMM) and apply gelu'(z)
+        dy2 = ops.gelu_backward(ops.linear(a2, weight, bias), dy2)
+    da = dw = db = dres = None
+    if ctx.needs_input_grad[0]:
+        da = ops.linear_dgrad(dy2, weight).view(a.shape)
+    if ctx.needs_input_grad[1]:
+        acc = torch.zeros(N, K, device=dy.device, dtype=_F32)
+        ops.linear_wgrad(dy2, a2, acc)
+        dw = acc.to(weight.dtype)
+    if ctx.has_bias and ctx.needs_input_grad[2]:
+        db = ops.colsum(dy2, torch.zeros(N, device=dy.device, dtype=_F32))
+    if ctx.has_res and ctx.needs_input_grad[3]:
+        dres = dy.to(ctx.res_dtype)
+    return da, dw, db, dres, None, None
+
+
+torch.library.register_autograd(f"{NAMESPACE}::linear", _linear_backward, setup_context=_linear_setup)
+
+
+def _layernorm_setup(ctx, inputs, output):
+    x, gamma, beta, eps, residual, rows, in_row_mod, out_fp32 = inputs
+    if in_row_mod > 0:
+        raise NotImplementedError("unirec_b200::layernorm: autograd of the row-broadcast form is not registered")
+    ctx.save_for_backward(x, gamma, residual)
+    ctx.eps, ctx.x_dtype = eps, x.dtype
+
+
+def _layernorm_backward(ctx, dy):
+    x, gamma, residual = ctx.saved_tensors
+    H = x.shape[-1]
+    pre = x.reshape(-1, H)
+    if residual is not None:
+        pre = (pre.float() + residual.reshape(-1, H).float())
+    pre = pre.to(_BF16).contiguous()
+    dgamma = torch.zeros(H, device=dy.device, dtype=_F32)
+    dbeta = torch.zeros(H, device=dy.device, dtype=_F32)
+    dx = ops.layernorm_backward(pre, dy.reshape(-1, H).to(_BF16).contiguous(), gamma, ctx.eps, dgamma, dbeta)
+    dres = dx.view(residual.shape) if (residual is not None and ctx.needs_input_grad[4]) else None
+    return dx.view(x.shape).to(ctx.x_dtype), dgamma, dbeta, None, dres, None, None, None
+
+
+torch.library.register_autograd(f"{NAMESPACE}::layernorm", _layernorm_backward, setup_context=_layernorm_setup)
+
+
+def _attention_setup(ctx, inputs, output):
+    q, k, v, key_mask, batch, num_heads, nq, nk, q_broadcast = inputs
+    if q_broadcast or nq > 64 or nk > 64:
+        raise NotImplementedError("unirec_b200::attention: autograd is registered for per-batch queries and nq, nk <= 64 "
+                                  "(the item Q-Former's shapes; the training path of SURVEY.md 8e cfg 2)")
+    ctx.save_for_backward(q, k, v, key_mask)
+    ctx.dims = (batch, num_heads, nq, nk)
+
+
+def _attention_backward(ctx, dout):
+    q, k, v, key_mask = ctx.saved_tensors
+    batch, num_heads, nq, nk = ctx.dims
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    ops.attention_backward(q, k, v, dout.to(_BF16).contiguous(), dq, dk, dv, batch=batch, num_heads=num_heads, nq=nq,
+                           nk=nk, key_mask=key_mask)
+    return dq, dk, dv, None, None, None, None, None, None
+
+
+torch.library.register_autograd(f"{NAMESPACE}::attention", _attention_backward, setup_context=_attention_setup)
 
 
 # ------------------------------------------------------------------------------------------------ row-wise
