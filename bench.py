@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--history", type=int, default=50)
     ap.add_argument("--fused-gather", type=int, default=0, help="1: the user K/V projection gathers the history tokens from "
                     "the item-token table itself (no materialised user sequence; SURVEY 8f-2)")
+    ap.add_argument("--fused-kv", type=int, default=0, help="1: the user cross-attention projects K / V inside the attention "
+                    "kernel (csrc/kv_attention_fused.cu): no K/V buffer, one chunk of users per step")
     ap.add_argument("--kv-gb", type=float, default=0.0, help="user Q-Former: bytes of cross-attention K/V materialised per "
                     "chunk of users, in GiB (0 = the module's default)")
     ap.add_argument("--top-k", type=int, default=100)
@@ -70,6 +72,8 @@ def config_dict(args, n_gpus):
         "users_per_gpu_per_step": args.users_per_gpu, "global_users_per_step": args.users_per_gpu * n_gpus,
         "user_chunk_kv_gib": args.kv_gb if args.kv_gb > 0 else "module default",
         "user_sequence": "gathered inside the K/V projection" if args.fused_gather else "materialised per chunk",
+        "user_cross_attention": ("K/V projected inside the attention kernel (no K/V in HBM)" if args.fused_kv
+                                 else "K/V of all layers materialised per chunk, then attention"),
         "history_items": args.history, "tokens_per_item": 32, "keys_per_user": args.history * 32,
         "user_qformer": "4 layers x 64 queries, hidden 1024, 16 heads, FFN 4096, cross-attn every layer",
         "item_qformer": "12 layers x 32 queries, 14 fields x 1024, cross-attn every 2nd layer",
@@ -545,6 +549,7 @@ def run_ours(args, rank, world, local_rank):
     user.prelayernorm_dtype = torch.bfloat16
     if args.kv_gb > 0:
         user.max_kv_bytes = int(args.kv_gb * (1 << 30))
+    user.fused_kv_attention = bool(args.fused_kv)
 
     # ------------------------------------------------------------------ stage A: item-token generation (cfg 3)
     N, Bi = args.pool_items, args.item_batch
@@ -844,6 +849,7 @@ def run_ours(args, rank, world, local_rank):
                 "attention": roof(user_stats, "attention", pk["hbm"], 1e9),
                 "attention_by_shape": attn_shapes,
                 "score_topk": roof(user_stats, "score_topk", pk["bf16_sustained"], 1e12),
+                "kv_attention_fused": roof(user_stats, "kv_attention", pk["bf16_sustained"], 1e12),
             },
         },
         "cpu_baseline": cpu_baseline,

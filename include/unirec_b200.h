@@ -257,6 +257,21 @@ int unirec_inject_tokens_backward(const int64_t* input_ids, int64_t B, int64_t S
                                   int64_t num_slots, void* d_text, int text_fp32, int64_t ld_text, float* d_tokens,
                                   int64_t Hd, void* stream);
 
+/* User cross-attention with the K/V projection fused in (models/qformer.py:185-188 key / value
+ * projections of the encoder states + :205, :244-268 attention): no K or V is written to memory.
+ *   out[u, q, h*64:(h+1)*64] = softmax_k(Q[u,q,h,:] . (x[u,k,:] Wk_h^T) * scale + mask[u,k]) (x[u,k,:] Wv_h^T) + bv_h
+ * x bf16 [users * S, K] (row stride ldx); w_packed bf16 [2 H, K], H = num_heads * 64, packed per head PAIR j:
+ * rows [256 j, 256 j + 128) = Wk[128 j : 128 j + 128], rows [256 j + 128, 256 j + 256) = Wv[128 j : 128 j + 128];
+ * q bf16: projected queries [users * 64, H] (q_batch_rows = 64) or one shared set [64, H] (q_batch_rows = 0);
+ * key_mask fp32 [users, S] (1 attend / 0 masked) or NULL; v_bias fp32 [H] or NULL (the key bias cancels in the softmax);
+ * out bf16 [users * 64, H].  Needs S % 64 == 0, 64 queries per user, head_dim 64, an even number of heads, K % 64 == 0.
+ * workspace: unirec_kv_attention_workspace_bytes(users, num_heads) bytes of device memory, 16-byte aligned. */
+int64_t unirec_kv_attention_workspace_bytes(int64_t users, int64_t num_heads);
+int unirec_kv_attention_fused(const void* x, int64_t ldx, const void* w_packed, int64_t ldw, const void* q, int64_t ldq,
+                              int64_t q_batch_rows, const float* key_mask, const float* v_bias, void* out, int64_t ldo,
+                              void* workspace, int64_t workspace_bytes, int64_t users, int64_t S, int64_t num_heads,
+                              int64_t K, float scale, void* stream);
+
 /* Event-context encoders in front of the user-sequence builder (models/mwne.py:504-566 TimestampEncoder,
  * :569-610 GeoCoordinateEncoder; summed per event at models/user_sequence_encoder.py:125-131).  First half of both MLPs:
  *   out[e, 0:H]  = gelu(W1t f_time(timestamps[e]) + b1t)   f_time = 9 features (secular + 4 sin/cos pairs), W1t [H, 9]

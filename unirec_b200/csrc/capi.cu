@@ -78,6 +78,12 @@ int mwne_encode(const float* numbers, long long n, const float* freqs, long long
                 const float* raw_scale, const float* extra_w, const float* scale, long long D, void* out, int out_fp32,
                 cudaStream_t stream);
 
+long long kv_attention_workspace_bytes(long long users, long long num_heads);
+int kv_attention_fused(const void* x, long long ldx, const void* w_packed, long long ldw, const void* q, long long ldq,
+                       long long q_batch_rows, const float* key_mask, const float* v_bias, void* out, long long ldo,
+                       void* workspace, long long workspace_bytes, long long users, long long S, long long num_heads,
+                       long long K, float scale, cudaStream_t stream);
+
 int gemm_bf16_cg2_gather(const void* table, long long ld_table, long long table_rows, const long long* ids,
                          const int* lengths, long long slots_per_user, const void* pad_table, long long ld_pad,
                          long long pad_rows, const void* W, long long ldw, const float* bias, const void* posbias,
@@ -282,6 +288,18 @@ int unirec_mwne_encode(const float* numbers, int64_t n, const float* freqs, int6
                        int out_fp32, void* stream) {
     COUNTED(mwne_encode(numbers, n, freqs, F, fourier_w, raw_scale, extra_w, scale, D, out, out_fp32,
                         static_cast<cudaStream_t>(stream)));
+}
+
+int64_t unirec_kv_attention_workspace_bytes(int64_t users, int64_t num_heads) {
+    return kv_attention_workspace_bytes(users, num_heads);
+}
+
+int unirec_kv_attention_fused(const void* x, int64_t ldx, const void* w_packed, int64_t ldw, const void* q, int64_t ldq,
+                              int64_t q_batch_rows, const float* key_mask, const float* v_bias, void* out, int64_t ldo,
+                              void* workspace, int64_t workspace_bytes, int64_t users, int64_t S, int64_t num_heads,
+                              int64_t K, float scale, void* stream) {
+    COUNTED(kv_attention_fused(x, ldx, w_packed, ldw, q, ldq, q_batch_rows, key_mask, v_bias, out, ldo, workspace,
+                               workspace_bytes, users, S, num_heads, K, scale, static_cast<cudaStream_t>(stream)));
 }
 
 int unirec_reconstruction_metrics(const void* rec, int rec_fp32, const float* orig, const float* mask, int64_t rows,

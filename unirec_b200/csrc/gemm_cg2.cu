@@ -24,6 +24,7 @@
 // Replaces the same reference lines as gemm_tcgen05.cu (every nn.Linear of the path: models/qformer.py:185-198,
 // :286, :359-360, :372; heads models/qformer_utils.py:50,53, training/user_qformer_training.py:38-43).
 #include "common.cuh"
+#include "cg2_ptx.cuh"
 #include "umma_pipe.cuh"
 
 namespace unirec {
@@ -59,55 +60,6 @@ struct Gemm2Params {
     int table_rows;                 // rows of the token table viewed 2-D: an out-of-bounds coordinate (TMA zero fill)
     int res_period;                 // > 0: the residual tile of rows m.. is read at rows (m % res_period).. of its table
 };
-
-// ---- PTX specific to the CTA-pair pipeline -------------------------------------------------------
-UNIREC_DEVICE void tma_load_2d_cg2(const CUtensorMap* map, uint32_t bar_cluster_addr, void* smem_dst, int32_t c0,
-                                   int32_t c1, uint64_t hint) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-        " [%0], [%1, {%3, %4}], [%2], %5;"
-        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1),
-        "l"(hint)
-        : "memory");
-}
-UNIREC_DEVICE void tma_store_2d(const CUtensorMap* map, const void* smem_src, int32_t c0, int32_t c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
-                 : "memory");
-}
-UNIREC_DEVICE void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-UNIREC_DEVICE void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-UNIREC_DEVICE void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
-UNIREC_DEVICE void tmem_alloc_cg2(uint32_t* smem_result, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
-                 "r"(ncols)
-                 : "memory");
-}
-UNIREC_DEVICE void tmem_relinquish_cg2() {
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-UNIREC_DEVICE void tmem_dealloc_cg2(uint32_t tmem_addr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_addr), "r"(ncols) : "memory");
-}
-UNIREC_DEVICE void umma_bf16_ss_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                    uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// Arrive (once all previously issued MMAs of this thread completed) on the barrier at the same shared-memory
-// offset in every CTA of cta_mask.
-UNIREC_DEVICE void umma_commit_cg2_mc(uint64_t* bar, uint16_t cta_mask) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"(cta_mask)
-                 : "memory");
-}
 
 template <int MODE, bool GATHER = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)

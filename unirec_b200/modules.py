@@ -115,6 +115,9 @@ class QFormerBackbone(nn.Module):
         self._pack: Optional[dict] = None
         self._pack_key = None
         self.hoist_layer0 = True        # compute the batch-invariant head of the encoder once (see `encode`)
+        # True: cross-attention over long key sequences (64 queries, S % 64 == 0) projects K / V inside the attention
+        # kernel (csrc/kv_attention_fused.cu) instead of materialising them; UserQFormer switches it on
+        self.fused_kv_attention = False
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
 
     def _init_weights(self):
@@ -164,6 +167,7 @@ class QFormerBackbone(nn.Module):
         f32 = lambda t: t.detach().float().contiguous()
         layers = []
         kv_w, kv_b = [], []
+        h_ = self.config.hidden_size
         for lyr in self.encoder.layer:
             a = getattr(lyr.attention, "self")
             d = {
@@ -188,7 +192,10 @@ class QFormerBackbone(nn.Module):
                     "ln2_g": f32(lyr.crossattention.output.LayerNorm.weight),
                     "ln2_b": f32(lyr.crossattention.output.LayerNorm.bias),
                     "kv_slot": len(kv_w),
+                    "b_v": f32(c.value.bias),
                 })
+                if h_ % 128 == 0:        # an even number of heads: operand of the fused K/V-projection + attention kernel
+                    d["w_kvp"] = ops.pack_kv_weights(c.key.weight, c.value.weight)
                 kv_w.append(torch.cat([c.key.weight, c.value.weight], 0))
                 kv_b.append(torch.cat([c.key.bias, c.value.bias], 0))
             layers.append(d)
@@ -225,6 +232,12 @@ class QFormerBackbone(nn.Module):
         return inv
 
     # -------------------------------------------------------------------------------------- forward
+    def fused_kv_supported(self, S: int) -> bool:
+        """The fused K/V-projection + cross-attention kernel (csrc/kv_attention_fused.cu) covers this model / sequence."""
+        cfg = self.config
+        return (self.fused_kv_attention and not self.training and
+                ops.kv_attention_supported(cfg.query_length, S, cfg.num_attention_heads, cfg.encoder_width))
+
     def encode(self, query_embeddings: torch.Tensor, encoder_hidden_states: torch.Tensor,
                encoder_attention_mask: Optional[torch.Tensor], out_dtype: torch.dtype = torch.float32,
                prelayernorm_dtype: torch.dtype = torch.float32) -> torch.Tensor:
@@ -248,15 +261,20 @@ class QFormerBackbone(nn.Module):
         mask = None
         if encoder_attention_mask is not None:
             mask = encoder_attention_mask.to(device=enc.device, dtype=torch.float32).contiguous()
+        if Q == cfg.query_length and self.fused_kv_supported(S):
+            # long key sequences (the user model): every cross-attention layer projects its K/V tile by tile INSIDE the
+            # attention kernel - no K/V buffer (13.4 GB per 512 users) is written to or read from HBM
+            return self.encode_from_kv(query_embeddings, None, B, S, mask, out_dtype, prelayernorm_dtype, enc=enc)
         # cross-attention K/V of every cross layer in one GEMM (the encoder input is layer-invariant)
         kv_all = ops.linear(enc, pk["w_kv_all"], pk["b_kv_all"]) if pk["w_kv_all"] is not None else None
         return self.encode_from_kv(query_embeddings, kv_all, B, S, mask, out_dtype, prelayernorm_dtype)
 
     def encode_from_kv(self, query_embeddings: torch.Tensor, kv_all: Optional[torch.Tensor], B: int, S: int,
                        mask: Optional[torch.Tensor], out_dtype: torch.dtype = torch.float32,
-                       prelayernorm_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+                       prelayernorm_dtype: torch.dtype = torch.float32, enc: Optional[torch.Tensor] = None) -> torch.Tensor:
         """The encoder behind the cross-attention K/V projection: kv_all bf16 [B * S, 2 H n_cross] (K and V of every
-        cross-attention layer side by side), mask fp32 [B, S] (1 attend / 0 masked) or None."""
+        cross-attention layer side by side), mask fp32 [B, S] (1 attend / 0 masked) or None.  With `enc` (bf16
+        [B * S, E], kv_all = None) the cross-attention layers run the fused K/V-projection + attention kernel on it."""
         cfg = self.config
         H, heads = cfg.hidden_size, cfg.num_attention_heads
         Q = query_embeddings.shape[1]
@@ -289,7 +307,14 @@ class QFormerBackbone(nn.Module):
                 h = ops.layernorm(pre, L["ln1_g"], L["ln1_b"], cfg.layer_norm_eps)
             if L["cross"]:
                 off = L["kv_slot"] * 2 * H
-                if li == 0 and hoist:
+                if enc is not None:
+                    if li == 0 and hoist:
+                        ctx = ops.kv_attention(enc, L["w_kvp"], inv["qc"], L["b_v"], batch=B, num_heads=heads, nk=S,
+                                               key_mask=mask, q_broadcast=True)
+                    else:
+                        ctx = ops.kv_attention(enc, L["w_kvp"], ops.linear(h, L["w_qc"], L["b_qc"]), L["b_v"], batch=B,
+                                               num_heads=heads, nk=S, key_mask=mask)
+                elif li == 0 and hoist:
                     ctx = ops.attention(inv["qc"], kv_all[:, off:off + H], kv_all[:, off + H:off + 2 * H], batch=B,
                                         num_heads=heads, nq=Q, nk=S, key_mask=mask, q_broadcast=True)
                 else:
@@ -464,6 +489,8 @@ class UserQFormer(nn.Module):
         # cross-attention K/V for all layers are materialised per chunk of users:
         # chunk * S * layers * 2 * H * 2 bytes (6.7 GB for 256 users x 1600 keys x 4 layers)
         self.max_kv_bytes = 14 << 30               # K/V of all layers for one chunk of users (512 users at S = 1600)
+        # fused K/V projection + cross-attention (no K/V buffer): then a chunk is bounded by the user sequence itself
+        self.max_seq_bytes = 14 << 30              # 4096 users at S = 1600 (13.4 GB of bf16 sequence)
         self._head_pack = None
         self._head_key = None
 
@@ -489,8 +516,19 @@ class UserQFormer(nn.Module):
             self._head_key = key
         return self._head_pack
 
+    @property
+    def fused_kv_attention(self) -> bool:
+        return self.qformer.fused_kv_attention
+
+    @fused_kv_attention.setter
+    def fused_kv_attention(self, on: bool):
+        self.qformer.fused_kv_attention = bool(on)
+
     def _chunk_users(self, S: int) -> int:
         cfg = self.config
+        if self.qformer.fused_kv_supported(S):
+            n = max(1, int(self.max_seq_bytes // max(S * cfg.encoder_width * 2, 1)))
+            return (n // 128) * 128 if n >= 128 else n
         per_user = S * cfg.num_hidden_layers * 2 * cfg.hidden_size * 2
         n = max(1, int(self.max_kv_bytes // max(per_user, 1)))
         # multiples of 128 users keep every GEMM's row count a multiple of the 256-row CTA-pair tile and the tile

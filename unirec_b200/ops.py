@@ -186,6 +186,60 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, batch: int, 
     return out
 
 
+def pack_kv_weights(wk: torch.Tensor, wv: torch.Tensor) -> torch.Tensor:
+    """[H, E] key and value weights -> the [2 H, E] bf16 operand of `kv_attention`: per head PAIR j, the 128 key rows of
+    heads 2j, 2j+1 followed by their 128 value rows (one 256-column tile of the fused kernel = one head pair's K | V)."""
+    H, E = wk.shape
+    if H % 128 != 0 or tuple(wv.shape) != (H, E):
+        raise RuntimeError("pack_kv_weights: needs [H, E] key / value weights with an even number of 64-wide heads")
+    k = wk.detach().reshape(H // 128, 128, E)
+    v = wv.detach().reshape(H // 128, 128, E)
+    return torch.cat([k, v], dim=1).reshape(2 * H, E).to(torch.bfloat16).contiguous()
+
+
+def kv_attention_supported(nq: int, nk: int, num_heads: int, enc_width: int) -> bool:
+    return nq == 64 and nk >= 64 and nk % 64 == 0 and num_heads % 2 == 0 and enc_width % 64 == 0
+
+
+def kv_attention(x: torch.Tensor, w_packed: torch.Tensor, q: torch.Tensor, v_bias: Optional[torch.Tensor], *, batch: int,
+                 num_heads: int, nk: int, key_mask: Optional[torch.Tensor] = None, q_broadcast: bool = False,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Cross-attention of 64 queries per user over nk keys with the key / value projection fused in (no K / V in memory):
+    x bf16 [batch * nk, E] encoder states, w_packed = pack_kv_weights(Wk, Wv), q bf16 [batch * 64 (or 64), H] projected
+    queries, v_bias fp32 [H].  Returns bf16 [batch * 64, H]."""
+    _req(x, torch.bfloat16, "kv_attention.x")
+    _req(w_packed, torch.bfloat16, "kv_attention.w_packed")
+    _req(q, torch.bfloat16, "kv_attention.q")
+    if x.dim() != 2 or q.dim() != 2 or w_packed.dim() != 2:
+        raise RuntimeError("kv_attention: x, q and w_packed must be 2-D row views")
+    H = num_heads * 64
+    E = x.shape[1]
+    if x.shape[0] != batch * nk or tuple(w_packed.shape) != (2 * H, E) or q.shape[1] != H or \
+            q.shape[0] != (64 if q_broadcast else batch * 64):
+        raise RuntimeError("kv_attention: shapes do not match (x [batch * nk, E], w_packed [2 H, E], q [batch * 64, H])")
+    if not kv_attention_supported(64, nk, num_heads, E):
+        raise RuntimeError(f"kv_attention: needs nk % 64 == 0, an even head count, E % 64 == 0 (nk={nk} heads={num_heads})")
+    if v_bias is not None:
+        _req(v_bias, torch.float32, "kv_attention.v_bias")
+    if key_mask is not None:
+        _req(key_mask, torch.float32, "kv_attention.key_mask")
+        if tuple(key_mask.shape) != (batch, nk) or not key_mask.is_contiguous():
+            raise RuntimeError("kv_attention: key_mask must be contiguous [batch, nk]")
+    if out is None:
+        out = torch.empty(batch * 64, H, device=x.device, dtype=torch.bfloat16)
+    lib = _lib.load()
+    ws_bytes = int(lib.unirec_kv_attention_workspace_bytes(batch, num_heads))
+    ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
+    flops = 2.0 * batch * nk * (2 * H) * E + 4.0 * batch * num_heads * 64 * nk * 64
+    with _Timed("kv_attention", flops, f"{batch * nk}x{2 * H}x{E}"):
+        rc = lib.unirec_kv_attention_fused(x.data_ptr(), x.stride(0), w_packed.data_ptr(), w_packed.stride(0), q.data_ptr(),
+                                           q.stride(0), 0 if q_broadcast else 64, _ptr(key_mask), _ptr(v_bias),
+                                           out.data_ptr(), out.stride(0), ws.data_ptr(), ws_bytes, batch, nk, num_heads, E,
+                                           0.125, _stream())
+    _lib.check(rc, "unirec_kv_attention_fused")
+    return out
+
+
 def _drop_args(dropout):
     """(thr16, seed, site[, seed_offset]) -> (thr16, seed, site, device pointer of the uint64 seed offset or None).
     seed_offset: int64 CUDA tensor with one element, added to `seed` by the kernels when they run (CUDA-graph replays)."""
