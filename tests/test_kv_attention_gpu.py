@@ -97,7 +97,7 @@ def test_kv_attention_key_bias_cancels_and_value_bias_adds():
     wp = ops.pack_kv_weights(wk, wv)
     a = ops.kv_attention(x, wp, q, bv, batch=B, num_heads=heads, nk=S, key_mask=mask)
     b = ops.kv_attention(x, wp, q, None, batch=B, num_heads=heads, nk=S, key_mask=mask)
-    torch.testing.assert_close(a.float() - b.float(), bv.expand(B * 64, -1), rtol=0, atol=0.02)
+    torch.testing.assert_close(a.float() - b.float(), bv.expand(B * 64, -1), rtol=0, atol=0.035)
     ref = _reference(x, wk, bk * 7.0, wv, bv, q, mask, B, S, heads, False)
     _check(a, ref, "fused vs fp32 with a 7x key bias")
 
