@@ -99,4 +99,6 @@ def test_event_context_full_width_feeds_the_sequence_builder():
     seq, mask = ops.build_user_sequence(table.to(DEV), hist.to(DEV), lens.to(DEV), ctx)
     ref_seq, ref_mask = O.build_user_sequences(table.float(), hist, lens.long(), context=ctx.float().cpu())
     assert torch.equal(mask.cpu(), ref_mask.float())
-    assert float((seq.float().cpu() - ref_seq).abs().max()) <= 0.04        # one bf16 rounding of |x| <= ~4
+    # the context reaches the builder as bf16 and the sum is stored as bf16: two roundings of 2^-9 relative each
+    err = (seq.float().cpu() - ref_seq).abs()
+    assert bool((err <= 2 * 2.0 ** -8 * ref_seq.abs() + 1e-3).all()), float(err.max())

@@ -301,6 +301,7 @@ def test_unknown_history_ids_are_zero_rows_on_both_user_paths():
     """Ids outside [0, num_items) (-1 sentinels, items missing from the token table): the sequence builder treats them
     as a ZERO token row whose slot keeps its position term and stays attended - never an out-of-bounds read - and the
     gathered K/V projection does the same, so the two user-encoding paths agree on bad ids."""
+    from unirec_b200 import ops
     from unirec_b200.modules import UserQFormer
     from unirec_b200.pipeline import NestedRanker
     N, Q, D, B, Hmax = 500, 32, 256, 6, 5

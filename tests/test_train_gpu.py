@@ -437,20 +437,24 @@ def test_train_step_graph_faithful_uses_each_items_own_mask():
         ms.append(m_.to(DEV))
     model = _small_train_model(0.0)
 
+    # the triplet term alone: the reconstruction term (two orders of magnitude larger) does not depend on these masks
+    lk = dict(recon_weight=0.0, contrastive_weight=1.0)
+
     def eager_loss(mp, mn):
         out = model(xs[0], ms[0])
         with torch.no_grad():
             p = model(xs[1], mp)["item_representation"]
             n = model(xs[2], mn)["item_representation"]
-        return float(qformer_loss(out, xs[0], ms[0], p, n))
+        return float(qformer_loss(out, xs[0], ms[0], p, n, **lk))
 
     own, anchors = eager_loss(ms[1], ms[2]), eager_loss(ms[0], ms[0])
-    assert abs(own - anchors) > 1e-4 * abs(own)            # the masks matter on this input
+    gap = abs(own - anchors)
+    assert gap > 1e-3 * abs(own), (own, anchors)           # the masks matter on this input
     import gc
     gc.collect()                                           # no eager autograd graph may be alive at capture time
-    tg = TrainStepGraph(model, xs[0], ms[0], faithful=True)
+    tg = TrainStepGraph(model, xs[0], ms[0], faithful=True, loss_kwargs=lk)
     got = float(tg.step(xs[0], ms[0], xs[1], xs[2], ms[1], ms[2]))
-    assert abs(got - own) <= 2e-3 * abs(own), (got, own, anchors)
+    assert abs(got - own) <= 0.05 * gap, (got, own, anchors)
     with pytest.raises(ValueError):
         tg.step(xs[0], ms[0], xs[1], xs[2])                # masks of the positive / negative items are required
 

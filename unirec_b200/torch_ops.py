@@ -97,7 +97,13 @@ def _linear_backward(ctx, dy):
         da = ops.linear_dgrad(dy2, weight).view(a.shape)
     if ctx.needs_input_grad[1]:
         acc = torch.zeros(N, K, device=dy.device, dtype=_F32)
-        ops.linear_wgrad(dy2, a2, acc)
+        rows = dy2.shape[0]
+        if rows % 8:
+            # the wgrad GEMM contracts over rows in 16-byte steps: zero rows add nothing to dW
+            pad = 8 - rows % 8
+            ops.linear_wgrad(torch.nn.functional.pad(dy2, (0, 0, 0, pad)), torch.nn.functional.pad(a2, (0, 0, 0, pad)), acc)
+        else:
+            ops.linear_wgrad(dy2, a2, acc)
         dw = acc.to(weight.dtype)
     if ctx.has_bias and ctx.needs_input_grad[2]:
         db = ops.colsum(dy2, torch.zeros(N, device=dy.device, dtype=_F32))
