@@ -51,6 +51,9 @@ def parse_args():
                     "kernel (csrc/kv_attention_fused.cu): no K/V buffer, one chunk of users per step")
     ap.add_argument("--kv-gb", type=float, default=0.0, help="user Q-Former: bytes of cross-attention K/V materialised per "
                     "chunk of users, in GiB (0 = the module's default)")
+    ap.add_argument("--users-per-call", type=int, default=0, help="user Q-Former: users per encoder call (0 = the module's "
+                    "default: all 4096 users of a step in one call, K/V chunked per layer inside it; 512 = the chunk-major "
+                    "loop of round 1: K/V of all 4 layers per 512-user chunk)")
     ap.add_argument("--top-k", type=int, default=100)
     ap.add_argument("--cpu-users", type=int, default=32, help="users in the bounded CPU-baseline sample (timed); the "
                     "top-k parity check against the GPU result uses the first 8 of them")
@@ -59,6 +62,8 @@ def parse_args():
     ap.add_argument("--train-steps", type=int, default=4)
     ap.add_argument("--train-dropout", type=float, default=0.2, help="dropout of the cfg-2 training block "
                     "(reference default 0.2, models/qformer_utils.py:19)")
+    ap.add_argument("--train-wire", default="bf16", choices=["bf16", "fp32"], help="dtype of the gradient buckets on the "
+                    "wire (bf16: cast once per bucket, half the NVLink bytes; accumulation inside a rank stays fp32)")
     ap.add_argument("--train-only", action="store_true", help="run only the cfg-2 training block (diagnostics)")
     ap.add_argument("--profile-range", default="", choices=["", "items", "users", "train"],
                     help="bracket that timed region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
@@ -71,9 +76,11 @@ def config_dict(args, n_gpus):
                     "(item-token table + pool produced by cfg3 item-token generation)",
         "users_per_gpu_per_step": args.users_per_gpu, "global_users_per_step": args.users_per_gpu * n_gpus,
         "user_chunk_kv_gib": args.kv_gb if args.kv_gb > 0 else "module default",
-        "user_sequence": "gathered inside the K/V projection" if args.fused_gather else "materialised per chunk",
+        "user_sequence": "gathered inside the K/V projection" if args.fused_gather else "materialised per encoder call",
+        "users_per_encoder_call": args.users_per_call if args.users_per_call > 0 else "module default (4096 at S = 1600)",
         "user_cross_attention": ("K/V projected inside the attention kernel (no K/V in HBM)" if args.fused_kv
-                                 else "K/V of all layers materialised per chunk, then attention"),
+                                 else "layer-major: K/V of one layer materialised per chunk of users (<= 14 GiB), then "
+                                      "attention; all other ops of a layer on every user of the call"),
         "history_items": args.history, "tokens_per_item": 32, "keys_per_user": args.history * 32,
         "user_qformer": "4 layers x 64 queries, hidden 1024, 16 heads, FFN 4096, cross-attn every layer",
         "item_qformer": "12 layers x 32 queries, 14 fields x 1024, cross-attn every 2nd layer",
@@ -341,7 +348,8 @@ def run_train_block(args, rank, world, dev, barrier, max_over_ranks, pk):
         model = QFormerForItemRepresentation(num_fields=14, dropout=args.train_dropout).train()
     model.dropout_seed = 1000 + rank * 1_000_003
     opt = torch.optim.AdamW([p for p in model.parameters()], lr=1e-4, fused=True)
-    red = GradientAllReducer().attach(model.qformer)
+    wire = torch.bfloat16 if args.train_wire == "bf16" else torch.float32
+    red = GradientAllReducer(bucket_dtype=wire).attach(model.qformer)
     head_params = (list(model.item_representation_head.parameters()) + list(model.reconstruction_head.parameters()) +
                    list(model.field_projection.parameters()))
     gen = torch.Generator(device=dev).manual_seed(4321 + rank)
@@ -369,6 +377,9 @@ def run_train_block(args, rank, world, dev, barrier, max_over_ranks, pk):
     for i in range(2):
         step(i)
     barrier()
+    bytes0 = red.bytes_reduced
+    step(2)
+    eager_allreduce_bytes = red.bytes_reduced - bytes0          # one eager step's wire bytes
     l0 = _lib.launch_count()
     if world == 1:
         ops.start_timing()      # per-launch CUDA events cost the host ~5 ms per step: only for the 1-GPU roofline
@@ -426,21 +437,26 @@ def run_train_block(args, rank, world, dev, barrier, max_over_ranks, pk):
         from unirec_b200.training import TrainStepGraph
         opt.zero_grad(set_to_none=True)
 
-        def timed_graph(faithful):
-            tg = TrainStepGraph(model, fields[0], mask, faithful=faithful)
+        def timed_graph(faithful, captured_collectives):
+            # data-parallel runs: the per-layer gradient all-reduces are captured INTO the graph (they overlap the rest
+            # of the captured backward on NCCL's stream); otherwise one flat bucket is reduced behind the replay
+            tg = TrainStepGraph(model, fields[0], mask, faithful=faithful,
+                                reducer=red if captured_collectives else None)
 
             def gstep(i):
                 if faithful:
                     loss_ = tg.step(fields[i % nb], mask, fields[(i + 1) % nb], fields[(i + 2) % nb], mask, mask)
                 else:
                     loss_ = tg.step(fields[i % nb], mask, pos, neg)
-                red.reduce_tensors(tg.grad_tensors())
+                if not captured_collectives:
+                    red.reduce_tensors(tg.grad_tensors())
                 opt.step()
                 return loss_
 
             for i in range(2):
                 gstep(i)
             barrier()
+            b0 = red.bytes_reduced
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g0.record()
             t_h = time.perf_counter()
@@ -451,17 +467,33 @@ def run_train_block(args, rank, world, dev, barrier, max_over_ranks, pk):
             barrier()
             ms_ = max_over_ranks(g0.elapsed_time(g1)) / args.train_steps
             val = float(loss_)
+            wire_bytes = tg.allreduce_bytes_per_step if captured_collectives else \
+                (red.bytes_reduced - b0) // max(args.train_steps, 1)
             opt.zero_grad(set_to_none=True)
             del tg
             torch.cuda.empty_cache()
-            return ms_, h_ms, val
+            return ms_, h_ms, val, wire_bytes
 
-        g_ms, g_host_ms, g_loss = timed_graph(False)
-        gf_ms, _, _ = timed_graph(True)
+        variants = {}
+        if world > 1:
+            try:
+                variants["collectives_in_graph"] = timed_graph(False, True)
+            except Exception as e:      # e.g. a NCCL / torch build that cannot capture collectives
+                variants["collectives_in_graph_error"] = f"{type(e).__name__}: {e}"[:300]
+                torch.cuda.synchronize()
+        variants["reduce_after_replay"] = timed_graph(False, False)
+        timed = {k: v for k, v in variants.items() if isinstance(v, tuple)}
+        best = min(timed, key=lambda k: timed[k][0])
+        g_ms, g_host_ms, g_loss, g_wire = timed[best]
+        gf_ms, _, _, _ = timed_graph(True, best == "collectives_in_graph")
         graph_info = {"used": True, "ms_per_step": g_ms, "host_enqueue_ms_per_step": g_host_ms,
-                      "faithful_ms_per_step": gf_ms, "final_loss": g_loss,
+                      "faithful_ms_per_step": gf_ms, "final_loss": g_loss, "gradient_exchange": best,
+                      "allreduce_bytes_per_step": g_wire,
+                      "variants_ms_per_step": {k: (v[0] if isinstance(v, tuple) else v) for k, v in variants.items()},
                       "what": "forward + loss + backward replayed from one CUDA graph (device-resident dropout seed "
-                              "offset); flat gradient all-reduce and fused AdamW outside the graph"}
+                              "offset); data-parallel: per-layer gradient buckets all-reduced INSIDE the graph on NCCL's "
+                              "stream, overlapping the captured backward (or one flat bucket behind the replay, whichever "
+                              "is faster); fused AdamW outside the graph"}
         if g_ms < eager_ms:       # the headline of the block is the faster mode; both are reported
             ms, ms_faithful, host_ms = g_ms, gf_ms, g_host_ms
         else:
@@ -484,7 +516,9 @@ def run_train_block(args, rank, world, dev, barrier, max_over_ranks, pk):
         "cuda_graph": graph_info,
         "eager": {"ms_per_step": eager_ms, "items_per_s": Bg / (eager_ms * 1e-3), "host_enqueue_ms_per_step": eager_host_ms,
                   "faithful_ms_per_step": eager_faithful_ms},
-        "allreduce_bytes_per_step": red.bytes_reduced // max(args.train_steps + 2, 1),
+        "allreduce_bytes_per_step": (graph_info.get("allreduce_bytes_per_step", 0)
+                                     if (graph_info.get("used") and ms < eager_ms) else eager_allreduce_bytes),
+        "allreduce_wire_dtype": args.train_wire,
         "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                      "frac": (ach / pk["bf16_sustained"]) if ach else None,
                      "share_of_step": (gemm[2] / (eager_ms * args.train_steps)) if gemm else None,
@@ -550,6 +584,8 @@ def run_ours(args, rank, world, local_rank):
     if args.kv_gb > 0:
         user.max_kv_bytes = int(args.kv_gb * (1 << 30))
     user.fused_kv_attention = bool(args.fused_kv)
+    if args.users_per_call > 0:
+        user.max_seq_bytes = args.users_per_call * args.history * 32 * 1024 * 2
 
     # ------------------------------------------------------------------ stage A: item-token generation (cfg 3)
     N, Bi = args.pool_items, args.item_batch
@@ -832,8 +868,9 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e_users, "unit": "users/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": user_launches,
         "roofline": {
-            "kernel": f"gemm_bf16_cg2_kernel<bias>, cross-attention K/V projection of all 4 layers, M x N x K = {dom_shape} "
-                      "(one launch per chunk of users; tcgen05 cta_group::2, 256 x 256 tiles)",
+            "kernel": f"gemm_bf16_cg2_kernel<bias>, cross-attention K/V projection, M x N x K = {dom_shape} "
+                      "(M = users of a K/V chunk x 1600 keys, N = 2 x 1024 per layer [x 4 layers in the chunk-major loop]; "
+                      "tcgen05 cta_group::2, 256 x 256 tiles)",
             "bound": "tensor", "achieved": dom["achieved"] if dom else None, "peak": pk["bf16_sustained"],
             "unit": "TFLOP/s", "frac": dom["frac"] if dom else None,
             "traffic": traffic, "traffic_source": traffic_src,

@@ -68,12 +68,20 @@ def _values16(row, group, j, site: int, seed: int):
 
 
 def keep_mask_rows(seed: int, site: int, rows: int, width: int, thr16: int) -> np.ndarray:
-    """bool [rows, width]: True where the element is kept (hidden-state sites)."""
+    """bool [rows, width]: True where the element is kept (hidden-state sites).  One Philox call per (row, group of 8
+    columns), its 4 words split into the 8 16-bit values of the group (the definition above, evaluated once per call
+    instead of once per element)."""
+    groups = (width + 7) // 8
     r = np.arange(rows, dtype=np.uint64)[:, None]
-    c = np.arange(width, dtype=np.uint32)[None, :]
-    r, c = np.broadcast_arrays(r, c)
-    v = _values16(r, (c >> 3).astype(np.uint32), (c & 7).astype(np.uint32), site, seed)
-    return v >= np.uint32(thr16)
+    gidx = np.arange(groups, dtype=np.uint32)[None, :]
+    r, gidx = np.broadcast_arrays(r, gidx)
+    w = philox4x32_10(r & np.uint64(0xFFFFFFFF), gidx, np.uint32(site), r >> np.uint64(32),
+                      seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    v = np.empty((rows, groups, 8), dtype=np.uint32)
+    for i, word in enumerate(w):                       # v[j] = (words[j >> 1] >> (16 * (j & 1))) & 0xffff
+        v[:, :, 2 * i] = word & np.uint32(0xFFFF)
+        v[:, :, 2 * i + 1] = word >> np.uint32(16)
+    return v.reshape(rows, groups * 8)[:, :width] >= np.uint32(thr16)
 
 
 def keep_mask_attention(seed: int, site: int, batch: int, heads: int, nq: int, nk: int, thr16: int) -> np.ndarray:

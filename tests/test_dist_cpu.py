@@ -122,6 +122,24 @@ def _allreduce_worker(rank, world, port, q):
             gathered = [torch.empty_like(m) for _ in range(world)]
             dist.all_gather(gathered, m)
             ok = ok and torch.allclose(t, sum(gathered) / world, atol=1e-6)
+        # bf16 wire: the fp32 gradient buffer is cast once, reduced as bf16 and written back as fp32 - the mean of the
+        # bf16-rounded per-rank values, i.e. within 2^-7 of the mean magnitude (bf16 keeps 8 significant bits: 2^-8 per rounding, inputs and sum)
+        red16 = GradientAllReducer(bucket_dtype=torch.bfloat16)
+        buf16 = torch.randn(64, generator=g)
+        keep16 = buf16.clone()
+        lone16 = torch.randn(9, generator=g)
+        lone_keep = lone16.clone()
+        before = red16.bytes_reduced
+        red16.layer_ready(0, [buf16[:40].view(8, 5), buf16[40:]], buf16)
+        red16.layer_ready(-3, [lone16])
+        red16.finish()
+        assert red16.bytes_reduced - before == (64 + 9) * 2 and buf16.dtype == torch.float32
+        for t, m in ((buf16, keep16), (lone16, lone_keep)):
+            gathered = [torch.empty_like(m) for _ in range(world)]
+            dist.all_gather(gathered, m)
+            mean = sum(gathered) / world
+            bound = 2.0 ** -7 * sum(x.abs() for x in gathered) / world + 1e-6   # one rounding per rank value (2^-8) + one of the sum
+            ok = ok and bool(((t - mean).abs() <= bound).all())
         p = torch.nn.Parameter(torch.zeros(3))
         p.grad = torch.full((3,), float(rank + 1))
         red.reduce_params([p, torch.nn.Parameter(torch.zeros(2))])      # second one has no grad: skipped

@@ -280,6 +280,90 @@ def test_item_training_step_gradients_match_oracle_autograd(dropout):
     assert loss_err <= 2e-4 * term_scale + 0.02 * abs(ref_loss), (float(loss), ref_loss, term_scale)
 
 
+def _compare_grads(model, ref, what, cos_tol, rel_tol):
+    checked, bad, worst_cos, worst_rel = 0, [], 1.0, 0.0
+    for name, prm in model.named_parameters():
+        if name not in ref:
+            continue
+        if prm.grad is None:
+            assert float(ref[name].abs().max()) == 0.0, name       # dead (text-branch) tensors get no gradient
+            continue
+        gref, got = ref[name], prm.grad.float().cpu()
+        if name.endswith("self.key.bias"):                         # d loss / d key.bias == 0 exactly (softmax shift)
+            assert float(got.abs().max()) <= 2e-2 * max(1.0, float(got.abs().max() + gref.abs().max())), name
+            continue
+        cos = float(F.cosine_similarity(got.flatten(), gref.flatten(), dim=0))
+        rel = float((got - gref).norm() / (gref.norm() + 1e-12))
+        worst_cos, worst_rel = min(worst_cos, cos), max(worst_rel, rel)
+        if not (cos >= cos_tol and rel <= rel_tol):
+            bad.append((name, cos, rel))
+        checked += 1
+    print(f"{what}: {checked} tensors, worst cos {worst_cos:.5f}, worst rel {worst_rel:.4f}")
+    assert not bad, (what, bad[:8])
+    return checked
+
+
+@pytest.mark.parametrize("dropout", [0.0, 0.2])
+def test_full_size_training_step_gradients_match_oracle_eager_and_graph(dropout):
+    """The BENCHED training model - 12 layers, hidden 1024, 16 heads, FFN 4096, 14 fields, B = 256 items (8192 query rows:
+    the split-K wgrad contracts over 8192 / 3584 rows, layernorm_bwd runs at H = 1024 inside the chain) - with the
+    reference's loss (QFormerLoss, training/item_qformer_training.py:41-56): gradients of EVERY live tensor through the
+    eager path and through one replay of `TrainStepGraph` against fp32 autograd through the CPU oracle, with dropout 0
+    and with the reference's dropout 0.2 (the oracle regenerates the kernels' Philox masks from the seed each path used).
+    Tolerance: cosine >= 0.999 and relative L2 error <= 6 % per tensor (bf16 activations over 12 layers)."""
+    import gc
+    from tests.golden_cases import ITEM_CASES
+    from oracle import qformer_oracle as O
+    from unirec_b200 import synth
+    from unirec_b200.modules import QFormerForItemRepresentation
+    from unirec_b200.training import QFormerLoss, TrainStepGraph, qformer_loss
+    c = ITEM_CASES["full"]
+    mk = c["model"]
+    sd = synth.item_qformer_state_dict(**mk, seed=71, attn_std=0.02)
+    model = QFormerForItemRepresentation(hidden_size=mk["hidden"], num_hidden_layers=mk["layers"],
+                                         num_attention_heads=c["heads"], intermediate_size=mk["inter"],
+                                         num_query_tokens=mk["num_query"], field_embedding_dim=mk["field_dim"],
+                                         num_fields=mk["num_fields"], dropout=dropout)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).train()
+    model.dropout_seed = 424242
+    B = 256
+    x, mask = synth.item_fields(batch=B, num_fields=14, dim=1024, seed=72, presence=0.8)
+    g = torch.Generator().manual_seed(73)
+    pos, neg = torch.randn(B, 1024, generator=g), torch.randn(B, 1024, generator=g)
+    xd, md, pd, nd = x.to(DEV), mask.to(DEV), pos.to(DEV), neg.to(DEV)
+
+    def oracle(drop):
+        leaf = {k: v.clone().float().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+        out = O.item_qformer_forward(leaf, x, mask, num_heads=c["heads"], drop=drop)
+        loss = QFormerLoss()(out, {"field_embeddings": x}, pos, neg, mask)[0]
+        loss.backward()
+        return float(loss), {k: v.grad for k, v in leaf.items() if v.requires_grad and v.grad is not None}
+
+    # ---- eager path
+    loss = qformer_loss(model(xd, md), xd, md, pd, nd)
+    loss.backward()
+    drop_e = model.last_dropout
+    ref_loss, ref = oracle(drop_e)
+    print(f"eager loss {float(loss):.4f} vs oracle {ref_loss:.4f}")
+    assert abs(float(loss) - ref_loss) <= 5e-3 * abs(ref_loss)
+    assert _compare_grads(model, ref, f"eager, dropout {dropout}", 0.999, 0.06) > 250
+    # ---- one replay of the captured step
+    loss_e = float(loss)
+    del loss
+    model.zero_grad(set_to_none=True)
+    gc.collect()
+    tg = TrainStepGraph(model, xd, md)
+    frozen = model.last_dropout                    # (thr16, seed) frozen into the captured launches
+    got = float(tg.step(xd, md, pd, nd))
+    if dropout > 0:
+        # a replay advances the device-resident seed offset by SEED_STRIDE before the forward runs
+        ref_loss, ref = oracle((frozen[0], frozen[1] + TrainStepGraph.SEED_STRIDE))
+    print(f"graph loss {got:.4f} vs oracle {ref_loss:.4f} (eager {loss_e:.4f})")
+    assert abs(got - ref_loss) <= 5e-3 * abs(ref_loss)
+    assert _compare_grads(model, ref, f"graph, dropout {dropout}", 0.999, 0.06) > 250
+
+
 def test_train_mode_no_grad_forward_uses_dropout_and_eval_does_not():
     """The reference's step runs the positive / negative forwards under no_grad with the module in train():
     dropout stays active there (training/item_qformer_training.py:122-125); eval() is deterministic."""

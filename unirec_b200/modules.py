@@ -118,6 +118,10 @@ class QFormerBackbone(nn.Module):
         # True: cross-attention over long key sequences (64 queries, S % 64 == 0) projects K / V inside the attention
         # kernel (csrc/kv_attention_fused.cu) instead of materialising them; UserQFormer switches it on
         self.fused_kv_attention = False
+        # Long key sequences (the user model): the K/V of ONE cross-attention layer are materialised for at most this many
+        # bytes at a time (a chunk of users) while every other op of the layer runs on ALL users of the call - see
+        # `encode`.  None: K/V of all layers and all users in one GEMM (the item model: 14 keys per item).
+        self.kv_chunk_bytes: Optional[int] = None
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
 
     def _init_weights(self):
@@ -265,16 +269,37 @@ class QFormerBackbone(nn.Module):
             # long key sequences (the user model): every cross-attention layer projects its K/V tile by tile INSIDE the
             # attention kernel - no K/V buffer (13.4 GB per 512 users) is written to or read from HBM
             return self.encode_from_kv(query_embeddings, None, B, S, mask, out_dtype, prelayernorm_dtype, enc=enc)
+        n_cross = sum(1 for L in pk["layers"] if L["cross"])
+        if self.kv_chunk_bytes is not None and n_cross and B * S * 2 * H * n_cross * 2 > self.kv_chunk_bytes:
+            # layer-major: K/V of one layer for a chunk of users at a time, everything else on all B users at once
+            return self.encode_from_kv(query_embeddings, None, B, S, mask, out_dtype, prelayernorm_dtype, enc=enc,
+                                       kv_chunk_users=self.kv_chunk_users(B, S))
         # cross-attention K/V of every cross layer in one GEMM (the encoder input is layer-invariant)
         kv_all = ops.linear(enc, pk["w_kv_all"], pk["b_kv_all"]) if pk["w_kv_all"] is not None else None
         return self.encode_from_kv(query_embeddings, kv_all, B, S, mask, out_dtype, prelayernorm_dtype)
 
+    def kv_chunk_users(self, B: int, S: int) -> int:
+        """Users per K/V chunk of the layer-major path: as many as fit `kv_chunk_bytes` for one layer, in multiples of 128
+        users (every GEMM row count stays a multiple of the 256-row CTA-pair tile), split evenly over the call."""
+        per_user = S * 2 * self.config.hidden_size * 2
+        n = max(1, int(self.kv_chunk_bytes // max(per_user, 1)))
+        if n >= B:
+            return B
+        chunks = -(-B // n)
+        n = -(-B // chunks)
+        return -(-n // 128) * 128 if n >= 128 else n
+
     def encode_from_kv(self, query_embeddings: torch.Tensor, kv_all: Optional[torch.Tensor], B: int, S: int,
                        mask: Optional[torch.Tensor], out_dtype: torch.dtype = torch.float32,
-                       prelayernorm_dtype: torch.dtype = torch.float32, enc: Optional[torch.Tensor] = None) -> torch.Tensor:
+                       prelayernorm_dtype: torch.dtype = torch.float32, enc: Optional[torch.Tensor] = None,
+                       kv_chunk_users: Optional[int] = None) -> torch.Tensor:
         """The encoder behind the cross-attention K/V projection: kv_all bf16 [B * S, 2 H n_cross] (K and V of every
         cross-attention layer side by side), mask fp32 [B, S] (1 attend / 0 masked) or None.  With `enc` (bf16
-        [B * S, E], kv_all = None) the cross-attention layers run the fused K/V-projection + attention kernel on it."""
+        [B * S, E], kv_all = None) the cross-attention layers project K / V themselves: `kv_chunk_users` = None runs the
+        fused K/V-projection + attention kernel on it; `kv_chunk_users` = n materialises one layer's K/V for n users at a
+        time (GEMM + attention per chunk) - the LAYER-MAJOR order of the user model: the K/V buffer stays bounded while the
+        self-attention / output / FFN GEMMs of the layer see all B * Q rows in one launch (at B = 4096 they run at 0.92-1.03
+        of the sustained bf16 peak against 0.66-0.85 at the 512-user chunks of a chunk-major loop)."""
         cfg = self.config
         H, heads = cfg.hidden_size, cfg.num_attention_heads
         Q = query_embeddings.shape[1]
@@ -307,7 +332,19 @@ class QFormerBackbone(nn.Module):
                 h = ops.layernorm(pre, L["ln1_g"], L["ln1_b"], cfg.layer_norm_eps)
             if L["cross"]:
                 off = L["kv_slot"] * 2 * H
-                if enc is not None:
+                if enc is not None and kv_chunk_users is not None:
+                    shared_q = li == 0 and hoist
+                    qc = inv["qc"] if shared_q else ops.linear(h, L["w_qc"], L["b_qc"])
+                    ctx = torch.empty(B * Q, H, device=enc.device, dtype=torch.bfloat16)
+                    w_kv, b_kv = pk["w_kv_all"][off:off + 2 * H], pk["b_kv_all"][off:off + 2 * H]
+                    for lo in range(0, B, kv_chunk_users):
+                        hi = min(lo + kv_chunk_users, B)
+                        kv = ops.linear(enc[lo * S:hi * S], w_kv, b_kv)
+                        ops.attention(qc if shared_q else qc[lo * Q:hi * Q], kv[:, :H], kv[:, H:], batch=hi - lo,
+                                      num_heads=heads, nq=Q, nk=S, key_mask=None if mask is None else mask[lo:hi],
+                                      q_broadcast=shared_q, out=ctx[lo * Q:hi * Q])
+                        del kv
+                elif enc is not None:
                     if li == 0 and hoist:
                         ctx = ops.kv_attention(enc, L["w_kvp"], inv["qc"], L["b_v"], batch=B, num_heads=heads, nk=S,
                                                key_mask=mask, q_broadcast=True)
@@ -486,11 +523,11 @@ class UserQFormer(nn.Module):
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
         self.output_dtype = torch.float32
         self.prelayernorm_dtype = torch.float32
-        # cross-attention K/V for all layers are materialised per chunk of users:
-        # chunk * S * layers * 2 * H * 2 bytes (6.7 GB for 256 users x 1600 keys x 4 layers)
-        self.max_kv_bytes = 14 << 30               # K/V of all layers for one chunk of users (512 users at S = 1600)
-        # fused K/V projection + cross-attention (no K/V buffer): then a chunk is bounded by the user sequence itself
-        self.max_seq_bytes = 14 << 30              # 4096 users at S = 1600 (13.4 GB of bf16 sequence)
+        # Layer-major encoding (QFormerBackbone.encode): the K/V of ONE cross-attention layer are materialised for a chunk
+        # of users, chunk * S * 2 * H * 2 bytes (13.4 GB for 2048 users x 1600 keys); all other ops see every user of a call
+        self.max_kv_bytes = 14 << 30
+        # a call itself is bounded by the user sequence: 4096 users at S = 1600 are 13.4 GB of bf16 sequence
+        self.max_seq_bytes = 14 << 30
         self._head_pack = None
         self._head_key = None
 
@@ -525,14 +562,12 @@ class UserQFormer(nn.Module):
         self.qformer.fused_kv_attention = bool(on)
 
     def _chunk_users(self, S: int) -> int:
+        """Users per encoder call: bounded by the bf16 user sequence (`max_seq_bytes`), in multiples of 128 users (every
+        GEMM row count stays a multiple of the 256-row CTA-pair tile).  Inside a call the K/V of one layer are chunked by
+        `max_kv_bytes` (layer-major order, QFormerBackbone.encode)."""
         cfg = self.config
-        if self.qformer.fused_kv_supported(S):
-            n = max(1, int(self.max_seq_bytes // max(S * cfg.encoder_width * 2, 1)))
-            return (n // 128) * 128 if n >= 128 else n
-        per_user = S * cfg.num_hidden_layers * 2 * cfg.hidden_size * 2
-        n = max(1, int(self.max_kv_bytes // max(per_user, 1)))
-        # multiples of 128 users keep every GEMM's row count a multiple of the 256-row CTA-pair tile and the tile
-        # counts of the small per-chunk GEMMs close to whole waves of 74 clusters
+        self.qformer.kv_chunk_bytes = self.max_kv_bytes
+        n = max(1, int(self.max_seq_bytes // max(S * cfg.encoder_width * 2, 1)))
         return (n // 128) * 128 if n >= 128 else n
 
     @torch.no_grad()
@@ -584,7 +619,10 @@ class UserQFormer(nn.Module):
         S = hmax * Q_item
         pk = self.qformer.packed()
         tabs = self._position_tables(hmax, Q_item, item_tokens.device)
-        step = self._chunk_users(S)
+        # this path materialises the K/V of ALL layers per chunk of users (one gathered GEMM): 512 users at S = 1600
+        cfg = self.config
+        step = max(1, int(self.max_kv_bytes // max(S * cfg.num_hidden_layers * 2 * cfg.hidden_size * 2, 1)))
+        step = (step // 128) * 128 if step >= 128 else step
         pos = torch.arange(S, device=item_tokens.device, dtype=torch.int32)
         outs = []
         for lo in range(0, B, step):

@@ -298,19 +298,28 @@ def qformer_loss(outputs, field_embeddings, attention_mask, pos_rep=None, neg_re
 
 class GradientAllReducer:
     """Data-parallel gradient averaging for the training step.  The backbone's backward
-    calls `layer_ready` as soon as a layer's parameter gradients are complete; each call packs them into one flat
-    bucket and starts an asynchronous all-reduce (NCCL on GPUs, gloo in the CPU tests), so communication overlaps
-    the backward of the remaining layers; `finish` (called at the end of the backbone's backward) waits, averages
-    and writes the results back in place.  Head gradients (2.1 M parameters) are reduced after backward with
-    `reduce_params`.  The 132.5 M never-executed parameters (text branch, word / position embeddings) have no
-    gradients and are never communicated."""
+    calls `layer_ready` as soon as a layer's parameter gradients are complete; each call starts an asynchronous
+    all-reduce of that layer's bucket (NCCL on GPUs, gloo in the CPU tests), so communication overlaps the backward of
+    the remaining layers; `finish` (called at the end of the backbone's backward) waits and writes the results back in
+    place.  Head gradients (2.1 M parameters) are reduced after backward with `reduce_params`.  The 132.5 M
+    never-executed parameters (text branch, word / position embeddings) have no gradients and are never communicated.
+
+    bucket_dtype: the WIRE dtype.  fp32: the backbone's flat fp32 gradient buffer is reduced in place (no copies).
+    bf16: a bucket is cast to bf16 (one streaming pass), reduced, and cast back into the fp32 gradients - half the
+    bytes over NVLink (357 MB instead of 714 MB per step); the accumulation inside a rank stays fp32, only the
+    exchanged partial sums are rounded (2^-9 relative per rank).
+    Averaging: NCCL reduces with ReduceOp.AVG (no separate divide pass); gloo has no AVG: SUM, then one divide.
+    Every call is stream-ordered and allocates through torch's caching allocator only, so a step that contains these
+    collectives can be captured into a CUDA graph (TrainStepGraph(reducer=...))."""
 
     def __init__(self, group=None, bucket_dtype: torch.dtype = torch.float32):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
-        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        ready = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if ready else 1
         self.bucket_dtype = bucket_dtype
+        self.avg_in_collective = bool(ready and dist.get_backend(group) == "nccl")
         self.pending = []
         self.bytes_reduced = 0
 
@@ -319,30 +328,43 @@ class GradientAllReducer:
         backbone.grad_finish_hook = self.finish
         return self
 
+    def _start(self, wire: torch.Tensor, async_op: bool = True):
+        op = self.dist.ReduceOp.AVG if self.avg_in_collective else self.dist.ReduceOp.SUM
+        self.bytes_reduced += wire.numel() * wire.element_size()
+        return self.dist.all_reduce(wire, op=op, group=self.group, async_op=async_op)
+
+    def _settle(self, wire: torch.Tensor):
+        if not self.avg_in_collective:
+            wire.div_(self.world)
+
     def layer_ready(self, layer_index: int, tensors: List[torch.Tensor], flat: Optional[torch.Tensor] = None):
-        """`flat`: the tensors are views that tile this contiguous buffer exactly (the backbone's gradient buffer) -
-        it is reduced in place, without the pack / unpack copies."""
+        """`flat`: the tensors are views that tile this contiguous buffer exactly (the backbone's gradient buffer) - with
+        a matching wire dtype it is reduced in place, without the pack / unpack copies; with a bf16 wire it is cast once."""
         tensors = [t for t in tensors if t is not None]
         if self.world == 1 or not tensors:
             return
-        in_place = flat is not None and flat.dtype == self.bucket_dtype
-        if not in_place:
-            flat = torch.cat([t.reshape(-1).to(self.bucket_dtype) for t in tensors])
-        work = self.dist.all_reduce(flat, group=self.group, async_op=True)
-        self.bytes_reduced += flat.numel() * flat.element_size()
-        self.pending.append((work, flat, None if in_place else tensors))
+        if flat is not None and flat.dtype == self.bucket_dtype:
+            self.pending.append((self._start(flat), flat, None, None))
+        elif flat is not None:
+            wire = flat.to(self.bucket_dtype)
+            self.pending.append((self._start(wire), wire, flat, None))
+        else:
+            wire = torch.cat([t.reshape(-1).to(self.bucket_dtype) for t in tensors])
+            self.pending.append((self._start(wire), wire, None, tensors))
 
     def finish(self):
-        for work, flat, tensors in self.pending:
+        for work, wire, flat, tensors in self.pending:
             work.wait()
-            flat.div_(self.world)
-            if tensors is None:
-                continue
-            off = 0
-            for t in tensors:
-                n = t.numel()
-                t.copy_(flat[off:off + n].view_as(t))
-                off += n
+            self._settle(wire)
+            if flat is not None:
+                flat.copy_(wire)
+            if tensors is not None:
+                views, off = [], 0
+                for t in tensors:
+                    n = t.numel()
+                    views.append(wire[off:off + n].view_as(t))
+                    off += n
+                torch._foreach_copy_(tensors, views)
         self.pending = []
 
     def reduce_params(self, params):
@@ -375,28 +397,18 @@ class GradientAllReducer:
 
     def reduce_tensors(self, tensors: List[torch.Tensor]):
         """Average `tensors` over the ranks in place.  Tensors that are views of one buffer are reduced as that buffer
-        (one all-reduce, no copies); the others are packed into one flat bucket, reduced and unpacked with a single
-        multi-tensor copy.  Used behind a CUDA-graph step, whose gradients all exist when the graph has run."""
+        (one all-reduce; in place when the wire dtype matches, through one cast otherwise); the others are packed into
+        one flat bucket, reduced and unpacked with a single multi-tensor copy.  Used behind a CUDA-graph step that was
+        captured without collectives, whose gradients all exist when the graph has run."""
         tensors = [t for t in tensors if t is not None]
         if self.world == 1 or not tensors:
             return
         buckets, rest = self.alias_buckets(tensors)
         for bkt in buckets:
-            self.dist.all_reduce(bkt, group=self.group)
-            self.bytes_reduced += bkt.numel() * bkt.element_size()
-            bkt.div_(self.world)
-        if not rest:
-            return
-        flat = torch.cat([t.reshape(-1).to(self.bucket_dtype) for t in rest])
-        self.dist.all_reduce(flat, group=self.group)
-        self.bytes_reduced += flat.numel() * flat.element_size()
-        flat.div_(self.world)
-        views, off = [], 0
-        for t in rest:
-            n = t.numel()
-            views.append(flat[off:off + n].view_as(t))
-            off += n
-        torch._foreach_copy_(rest, views)
+            self.layer_ready(-4, [bkt], bkt)
+        if rest:
+            self.layer_ready(-5, rest)
+        self.finish()
 
 
 class TrainStepGraph:
@@ -424,14 +436,22 @@ class TrainStepGraph:
     SEED_STRIDE = 1024     # > the number of forward passes in one step: replays never reuse an effective seed
 
     def __init__(self, model, field_embeddings: torch.Tensor, attention_mask: torch.Tensor, *,
-                 faithful: bool = False, loss_kwargs: Optional[dict] = None, warmup: int = 3):
+                 faithful: bool = False, loss_kwargs: Optional[dict] = None, warmup: int = 3,
+                 reducer: Optional["GradientAllReducer"] = None):
         """field_embeddings [B, F, E] / attention_mask [B, F]: example inputs (shape, dtype and device of every later
         step).  faithful: also run the two no-grad train-mode forwards that produce the positive / negative
-        representations (item_qformer_training.py:122-125) inside the graph; otherwise they are inputs of `step`."""
+        representations (item_qformer_training.py:122-125) inside the graph; otherwise they are inputs of `step`.
+        reducer (data-parallel runs): the gradient averaging becomes PART OF THE GRAPH - the backbone's backward hands
+        every layer's gradient bucket to `reducer.layer_ready` as soon as it is complete, the asynchronous NCCL all-reduce
+        of layer l runs on NCCL's stream while the captured backward of layers l-1 .. 0 continues (the fork / join of the
+        two streams is captured as graph dependencies), the head gradients follow at the end; after a replay every
+        gradient is already averaged and the caller runs the optimizer directly.  Without it the caller reduces
+        `grad_tensors()` behind the replay (one bucket, nothing to overlap with)."""
         if not field_embeddings.is_cuda:
             raise RuntimeError("TrainStepGraph: inputs must be CUDA tensors (unirec_b200 has no CPU path)")
         dev = field_embeddings.device
         self.model, self.faithful = model, faithful
+        self.reducer = reducer if (reducer is not None and reducer.world > 1) else None
         self.loss_kwargs = dict(loss_kwargs or {})
         B, E = field_embeddings.shape[0], model.item_representation_head.out_features
         self.fields = field_embeddings.detach().clone()
@@ -447,10 +467,15 @@ class TrainStepGraph:
             self.neg = torch.zeros(B, E, device=dev)
         self.seed_offset = torch.zeros(1, dtype=torch.int64, device=dev)
         self.params = [p for p in model.parameters() if p.requires_grad]
+        in_backbone = {id(p) for p in model.qformer.parameters()} | {id(model.query_embeddings)}
+        self.head_params = [p for p in self.params if id(p) not in in_backbone]
         saved_offset = model.dropout_seed_offset
         saved_hooks = (getattr(model.qformer, "grad_ready_hook", None), getattr(model.qformer, "grad_finish_hook", None))
         model.dropout_seed_offset = self.seed_offset
-        model.qformer.grad_ready_hook = model.qformer.grad_finish_hook = None     # no collectives inside the graph
+        if self.reducer is not None:          # collectives inside the graph (the warm-up passes create the communicator)
+            model.qformer.grad_ready_hook, model.qformer.grad_finish_hook = self.reducer.layer_ready, self.reducer.finish
+        else:
+            model.qformer.grad_ready_hook = model.qformer.grad_finish_hook = None
         try:
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -465,9 +490,15 @@ class TrainStepGraph:
             model.qformer._pack = model.qformer._pack_key = None
             model._head_pack = model._head_key = None
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            bytes_before = self.reducer.bytes_reduced if self.reducer is not None else 0
+            # with collectives inside, NCCL's watchdog thread may query events while this thread captures: only calls
+            # made by THIS thread may invalidate the capture
+            mode = {"capture_error_mode": "thread_local"} if self.reducer is not None else {}
+            with torch.cuda.graph(self.graph, **mode):
                 self.seed_offset.add_(self.SEED_STRIDE)
                 self.loss = self._body()
+            # bytes every replay puts on the wire (the reducer's own counter only sees the capture)
+            self.allreduce_bytes_per_step = (self.reducer.bytes_reduced - bytes_before) if self.reducer is not None else 0
         finally:
             model.dropout_seed_offset = saved_offset
             model.qformer.grad_ready_hook, model.qformer.grad_finish_hook = saved_hooks
@@ -489,6 +520,8 @@ class TrainStepGraph:
             p_rep, n_rep = self.pos, self.neg
         loss = qformer_loss(out, self.fields, self.mask, p_rep, n_rep, **self.loss_kwargs)
         loss.backward()
+        if self.reducer is not None:
+            self.reducer.reduce_params(self.head_params)
         return loss.detach()
 
     def grad_tensors(self) -> List[torch.Tensor]:
