@@ -51,9 +51,11 @@ def parse_args():
                     "kernel (csrc/kv_attention_fused.cu): no K/V buffer, one chunk of users per step")
     ap.add_argument("--kv-gb", type=float, default=0.0, help="user Q-Former: bytes of cross-attention K/V materialised per "
                     "chunk of users, in GiB (0 = the module's default)")
-    ap.add_argument("--users-per-call", type=int, default=0, help="user Q-Former: users per encoder call (0 = the module's "
-                    "default: all 4096 users of a step in one call, K/V chunked per layer inside it; 512 = the chunk-major "
-                    "loop of round 1: K/V of all 4 layers per 512-user chunk)")
+    ap.add_argument("--layer-major", type=int, default=0, help="1: user Q-Former in layer-major order (one encoder call per "
+                    "step, K/V of ONE layer materialised per chunk of users inside it); 0: chunk-major (K/V of all 4 layers "
+                    "per 512-user chunk, the sequence is read once)")
+    ap.add_argument("--exchange", default="alltoall", choices=["alltoall", "allgather"], help="N > 1: how the per-rank top-k "
+                    "lists travel (alltoall: every rank merges and returns its own users; allgather: every rank merges all)")
     ap.add_argument("--top-k", type=int, default=100)
     ap.add_argument("--cpu-users", type=int, default=32, help="users in the bounded CPU-baseline sample (timed); the "
                     "top-k parity check against the GPU result uses the first 8 of them")
@@ -76,16 +78,17 @@ def config_dict(args, n_gpus):
                     "(item-token table + pool produced by cfg3 item-token generation)",
         "users_per_gpu_per_step": args.users_per_gpu, "global_users_per_step": args.users_per_gpu * n_gpus,
         "user_chunk_kv_gib": args.kv_gb if args.kv_gb > 0 else "module default",
-        "user_sequence": "gathered inside the K/V projection" if args.fused_gather else "materialised per encoder call",
-        "users_per_encoder_call": args.users_per_call if args.users_per_call > 0 else "module default (4096 at S = 1600)",
-        "user_cross_attention": ("K/V projected inside the attention kernel (no K/V in HBM)" if args.fused_kv
-                                 else "layer-major: K/V of one layer materialised per chunk of users (<= 14 GiB), then "
-                                      "attention; all other ops of a layer on every user of the call"),
+        "user_sequence": "gathered inside the K/V projection" if args.fused_gather else "materialised per chunk",
+        "user_cross_attention": ("K/V projected inside the attention kernel (no K/V in HBM)" if args.fused_kv else
+                                 "layer-major: K/V of one layer materialised per chunk of users (<= 14 GiB), then attention"
+                                 if args.layer_major else "K/V of all layers materialised per chunk, then attention"),
         "history_items": args.history, "tokens_per_item": 32, "keys_per_user": args.history * 32,
         "user_qformer": "4 layers x 64 queries, hidden 1024, 16 heads, FFN 4096, cross-attn every layer",
         "item_qformer": "12 layers x 32 queries, 14 fields x 1024, cross-attn every 2nd layer",
         "pool_items": args.pool_items, "top_k": args.top_k, "item_batch": args.item_batch,
-        "parallelism": f"users dp{n_gpus}; candidate rows sharded /{n_gpus}; all-gather + merge of top-k",
+        "parallelism": f"users dp{n_gpus}; candidate rows sharded /{n_gpus}; all-gather of user vectors, "
+                       + ("all-to-all of the per-rank top-k lists (int32 index + shard base), every rank merges its own users"
+                          if args.exchange == "alltoall" else "all-gather + merge of top-k on every rank"),
         "l2": "inputs larger than L2 every step (user sequences 13.4 GB, candidate pool 2 GB / n_gpus, "
               "item field batches cycled over a 0.9 GB pool)",
     }
@@ -584,8 +587,7 @@ def run_ours(args, rank, world, local_rank):
     if args.kv_gb > 0:
         user.max_kv_bytes = int(args.kv_gb * (1 << 30))
     user.fused_kv_attention = bool(args.fused_kv)
-    if args.users_per_call > 0:
-        user.max_seq_bytes = args.users_per_call * args.history * 32 * 1024 * 2
+    user.layer_major = bool(args.layer_major)
 
     # ------------------------------------------------------------------ stage A: item-token generation (cfg 3)
     N, Bi = args.pool_items, args.item_batch
@@ -644,8 +646,9 @@ def run_ours(args, rank, world, local_rank):
     hist_batches = [torch.randint(0, N, (Bu, Hh), device=dev, generator=hgen) for _ in range(3)]
     lengths = torch.full((Bu,), Hh, device=dev, dtype=torch.int32)
 
+    local_res = args.exchange == "alltoall"
     for s in range(args.warmup):
-        ranker(hist_batches[s % 3], lengths)
+        ranker(hist_batches[s % 3], lengths, local_result=local_res)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -657,7 +660,7 @@ def run_ours(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for s in range(args.steps):
-        scores, idx = ranker(hist_batches[s % 3], lengths)
+        scores, idx = ranker(hist_batches[s % 3], lengths, local_result=local_res)
     e1.record()
     barrier()
     if args.profile_range == "users":
@@ -675,13 +678,14 @@ def run_ours(args, rank, world, local_rank):
     # ------------------------------------------------------------------ e2e: host buffers in, host results out
     h_hist = [b.cpu().pin_memory() for b in hist_batches]
     h_len = lengths.cpu().pin_memory()
-    h_scores = torch.empty(Bu * world, k, dtype=torch.float32).pin_memory()
-    h_idx = torch.empty(Bu * world, k, dtype=torch.int64).pin_memory()
+    out_rows = Bu if (local_res or world == 1) else Bu * world          # result rows a rank hands back to its host
+    h_scores = torch.empty(out_rows, k, dtype=torch.float32).pin_memory()
+    h_idx = torch.empty(out_rows, k, dtype=torch.int64).pin_memory()
 
     def e2e_step(s):
         d_hist = h_hist[s % 3].to(dev, non_blocking=True)
         d_len = h_len.to(dev, non_blocking=True)
-        sc, ix = ranker(d_hist, d_len)
+        sc, ix = ranker(d_hist, d_len, local_result=local_res)
         h_scores.copy_(sc, non_blocking=True)
         h_idx.copy_(ix, non_blocking=True)
         torch.cuda.synchronize()
@@ -694,8 +698,8 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_users = Bu * world * args.steps / e2e_s
-    h2d = Bu * Hh * 8 + Bu * 4
-    d2h = Bu * world * k * 12
+    h2d = (Bu * Hh * 8 + Bu * 4) * world        # whole job: every rank copies its users' histories in ...
+    d2h = out_rows * k * 12 * world             # ... and its result rows (fp32 score + int64 index) out
 
     # items e2e: fp32 field embeddings from pinned host memory, bf16 tokens back to pinned host memory
     h_fields = fpool[0].cpu().pin_memory()
@@ -869,7 +873,7 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": user_launches,
         "roofline": {
             "kernel": f"gemm_bf16_cg2_kernel<bias>, cross-attention K/V projection, M x N x K = {dom_shape} "
-                      "(M = users of a K/V chunk x 1600 keys, N = 2 x 1024 per layer [x 4 layers in the chunk-major loop]; "
+                      "(M = users of a K/V chunk x 1600 keys, N = 2 x 1024 per layer x 4 layers [one layer with --layer-major 1]; "
                       "tcgen05 cta_group::2, 256 x 256 tiles)",
             "bound": "tensor", "achieved": dom["achieved"] if dom else None, "peak": pk["bf16_sustained"],
             "unit": "TFLOP/s", "frac": dom["frac"] if dom else None,

@@ -42,6 +42,25 @@ def _worker(rank, world, port, q):
         merged_i = torch.gather(i_all.permute(1, 0, 2).reshape(B, world * k), 1, pos)
         ref_s, ref_i = O.cosine_topk(users, cands, k)
         ok = torch.allclose(merged_s, ref_s, atol=1e-6) and torch.equal(merged_i, ref_i)
+        # all-to-all variant: local int32 indices + shard bases on the wire, every rank receives ITS users' lists from
+        # every rank and merges only those; one user's list holds -1 entries (a shard with fewer than k candidates)
+        from unirec_b200.pipeline import exchange_lists
+        bases = gather_rows(torch.tensor([lo], dtype=torch.int64))
+        assert bases.tolist() == [shard_range(N, r, world)[0] for r in range(world)]
+        i_loc = i.clone()
+        s_loc = s.clone()
+        i_loc[0, -2:] = -1
+        s_loc[0, -2:] = float("-inf")
+        s_x, i_x = exchange_lists(s_loc, i_loc, bases)
+        b = B // world
+        assert tuple(s_x.shape) == (world, b, k) and i_x.dtype == torch.int64
+        mine_s, pos = torch.topk(s_x.permute(1, 0, 2).reshape(b, world * k), k, dim=-1)
+        mine_i = torch.gather(i_x.permute(1, 0, 2).reshape(b, world * k), 1, pos)
+        if rank == 0:
+            ok = ok and bool((i_x[:, 0, -2:] == -1).all())           # the marker survives the base shift
+            ok = ok and torch.allclose(mine_s[1:], ref_s[ulo + 1:uhi], atol=1e-6) and torch.equal(mine_i[1:], ref_i[ulo + 1:uhi])
+        else:
+            ok = ok and torch.allclose(mine_s, ref_s[ulo:uhi], atol=1e-6) and torch.equal(mine_i, ref_i[ulo:uhi])
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

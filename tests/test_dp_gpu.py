@@ -137,6 +137,9 @@ def _rank_worker(rank, world, port, q):
         ok = ok and float(cos.min()) > 0.9999
         s3, i3 = two(history[ulo:uhi].contiguous(), lengths[ulo:uhi].contiguous())
         ok = ok and bool(torch.allclose(s1, s3, atol=2e-3))
+        # all-to-all exchange: this rank's users only, the same lists
+        s4, i4 = two.rank(u_all[ulo:uhi].contiguous(), local_result=True)
+        ok = ok and bool(torch.equal(s4, s1[ulo:uhi])) and bool(torch.equal(i4, i1[ulo:uhi]))
         print(f"rank {rank}: merged == single-GPU list: {bool(torch.equal(i1, i2))}, min cos {float(cos.min()):.6f}", flush=True)
         torch.cuda.synchronize()
         q.put((rank, bool(ok)))

