@@ -816,6 +816,7 @@ topk_select_kernel(const SelectParams p) {
 // Host
 // ---------------------------------------------------------------------------------------------
 struct ScorePlan {
+    int pair;                  // 1: CTA-pair kernel (256-user blocks, clusters of two CTAs); 0: single-CTA kernel (128)
     int num_m_blocks, n_tiles, R, tiles_per_range, grid;
     int dense_mode;            // 1: small pool, score everything densely and rank with row_kth_kernel
     int n_dense_tiles, tile_stride;
@@ -828,23 +829,30 @@ static size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255);
 static ScorePlan make_plan(long long B, long long N) {
     ScorePlan pl;
     const int sms = num_sms() > 0 ? num_sms() : 148;
-    pl.num_m_blocks = static_cast<int>((B + PIPE_BLOCK_M - 1) / PIPE_BLOCK_M);
+    // more than one 128-user block: pairs of CTAs share every candidate tile (score_pair_kernel); a single block (the
+    // HBM-bound small-batch regime) keeps the single-CTA kernel, whose 148 CTAs each stream their own candidate range
+    pl.pair = B > PIPE_BLOCK_M ? 1 : 0;
+    const int block_m = pl.pair ? SP_TILE_M : PIPE_BLOCK_M;
+    const int units = pl.pair ? sms / 2 : sms;          // clusters or CTAs that run concurrently
+    const int ctas_per_unit = pl.pair ? 2 : 1;
+    pl.num_m_blocks = static_cast<int>((B + block_m - 1) / block_m);
     pl.n_tiles = static_cast<int>((N + SC_BLOCK_N - 1) / SC_BLOCK_N);
-    const size_t b_pad = static_cast<size_t>(pl.num_m_blocks) * PIPE_BLOCK_M;
+    const size_t b_pad = static_cast<size_t>(pl.num_m_blocks) * block_m;
     pl.dense_mode = N <= SC_DENSE_MAX_N ? 1 : 0;
     if (pl.dense_mode) {
         pl.n_dense_tiles = pl.n_tiles;
         pl.tile_stride = 1;
         pl.R = 0; pl.tiles_per_range = 0;
         const long long items = static_cast<long long>(pl.n_dense_tiles) * pl.num_m_blocks;
-        pl.grid = static_cast<int>(items < sms ? items : sms);
+        pl.grid = static_cast<int>(items < units ? items : units) * ctas_per_unit;
         pl.scratch_bytes = pl.partial_bytes = pl.cnt_bytes = pl.tau_bytes = 0;
         pl.dense_bytes = align256(b_pad * static_cast<size_t>(pl.n_dense_tiles) * SC_BLOCK_N * sizeof(float));
         return pl;
     }
-    // sampled start threshold: every tile_stride-th candidate tile, 32..128 tiles (8192..32768 candidates)
+    // sampled start threshold: every tile_stride-th candidate tile, 1/32 of the pool but at least 16 tiles (4096 candidates:
+    // ~k * N / 4096 scores per user pass the filter) and at most 128 (what row_kth_kernel holds in registers)
     int nd = pl.n_tiles / 32;
-    nd = nd < 32 ? 32 : (nd > SC_DENSE_MAX_N / SC_BLOCK_N ? SC_DENSE_MAX_N / SC_BLOCK_N : nd);
+    nd = nd < 16 ? 16 : (nd > SC_DENSE_MAX_N / SC_BLOCK_N ? SC_DENSE_MAX_N / SC_BLOCK_N : nd);
     pl.n_dense_tiles = nd;
     pl.tile_stride = pl.n_tiles / nd;
     pl.dense_bytes = align256(b_pad * static_cast<size_t>(nd) * SC_BLOCK_N * sizeof(float));
@@ -855,16 +863,16 @@ static ScorePlan make_plan(long long B, long long N) {
     double best_waste = 1e30;
     for (int r = 1; r <= r_max; ++r) {
         const long long items = static_cast<long long>(r) * pl.num_m_blocks;
-        if (items < sms) continue;
-        if (items > 16LL * sms) break;
-        const long long waves = (items + sms - 1) / sms;
-        const double waste = static_cast<double>(waves * sms) / static_cast<double>(items);
+        if (items < units) continue;
+        if (items > 16LL * units) break;
+        const long long waves = (items + units - 1) / units;
+        const double waste = static_cast<double>(waves * units) / static_cast<double>(items);
         if (waste < best_waste - 1e-9) { best_waste = waste; best_r = r; }   // ties: keep the smaller r
     }
     pl.tiles_per_range = (pl.n_tiles + best_r - 1) / best_r;
     pl.R = (pl.n_tiles + pl.tiles_per_range - 1) / pl.tiles_per_range;
     const long long items = static_cast<long long>(pl.R) * pl.num_m_blocks;
-    pl.grid = static_cast<int>(items < sms ? items : sms);
+    pl.grid = static_cast<int>(items < units ? items : units) * ctas_per_unit;
     pl.scratch_bytes = align256(static_cast<size_t>(pl.grid) * 8 * SC_CAP * 32 * sizeof(uint2));
     pl.partial_bytes = align256(b_pad * 2 * pl.R * SC_KMAX * sizeof(uint2));
     pl.cnt_bytes = align256(b_pad * 2 * pl.R * sizeof(int));
@@ -916,12 +924,14 @@ static int score_topk_pass(const void* users, int64_t ldu, const float* user_inv
     CUtensorMap tu, tc;
     int rc = make_tmap_bf16_2d(&tu, users, B, D, ldu, PIPE_BLOCK_M);
     if (rc != UNIREC_OK) return rc;
-    rc = make_tmap_bf16_2d(&tc, cands, N, D, ldc, SC_BLOCK_N);
+    rc = make_tmap_bf16_2d(&tc, cands, N, D, ldc, pl.pair ? 128 : SC_BLOCK_N);     // a CTA of a pair loads 128 candidate rows
     if (rc != UNIREC_OK) return rc;
     static bool attr_set = false;
     if (!attr_set) {
         if ((rc = set_smem_attr(score_tile_kernel<MODE_FILTER>, ScPipe::SMEM_BYTES, "score_topk")) != UNIREC_OK) return rc;
         if ((rc = set_smem_attr(score_tile_kernel<MODE_DENSE>, ScPipe::SMEM_BYTES, "score_topk")) != UNIREC_OK) return rc;
+        if ((rc = set_smem_attr(score_pair_kernel<MODE_FILTER>, SP_SMEM_BYTES, "score_topk")) != UNIREC_OK) return rc;
+        if ((rc = set_smem_attr(score_pair_kernel<MODE_DENSE>, SP_SMEM_BYTES, "score_topk")) != UNIREC_OK) return rc;
         if ((rc = set_smem_attr(topk_select_kernel<true>, SC_SEL_CAP * 8, "score_topk")) != UNIREC_OK) return rc;
         if ((rc = set_smem_attr(topk_select_kernel<false>, SC_SEL_CAP * 8, "score_topk")) != UNIREC_OK) return rc;
         attr_set = true;
@@ -930,8 +940,13 @@ static int score_topk_pass(const void* users, int64_t ldu, const float* user_inv
     {
         const long long items = static_cast<long long>(pl.n_dense_tiles) * pl.num_m_blocks;
         const int sms = num_sms() > 0 ? num_sms() : 148;
-        const int grid = static_cast<int>(items < sms ? items : sms);
-        score_tile_kernel<MODE_DENSE><<<grid, SC_THREADS, ScPipe::SMEM_BYTES, stream>>>(tu, tc, p);
+        if (pl.pair) {
+            const int clusters = static_cast<int>(items < sms / 2 ? items : sms / 2);
+            score_pair_kernel<MODE_DENSE><<<2 * clusters, SC_THREADS, SP_SMEM_BYTES, stream>>>(tu, tc, p);
+        } else {
+            const int grid = static_cast<int>(items < sms ? items : sms);
+            score_tile_kernel<MODE_DENSE><<<grid, SC_THREADS, ScPipe::SMEM_BYTES, stream>>>(tu, tc, p);
+        }
     }
     RowKthParams rp{};
     rp.dense = p.dense; rp.ldd = p.ldd; rp.ncols = pl.n_dense_tiles * SC_BLOCK_N; rp.k = (int)k;
@@ -945,7 +960,8 @@ static int score_topk_pass(const void* users, int64_t ldu, const float* user_inv
         rp.tau_out = tau;
         launch_row_kth(rp, (int)B, false, stream);
         p.row_tau = tau;
-        score_tile_kernel<MODE_FILTER><<<pl.grid, SC_THREADS, ScPipe::SMEM_BYTES, stream>>>(tu, tc, p);
+        if (pl.pair) score_pair_kernel<MODE_FILTER><<<pl.grid, SC_THREADS, SP_SMEM_BYTES, stream>>>(tu, tc, p);
+        else score_tile_kernel<MODE_FILTER><<<pl.grid, SC_THREADS, ScPipe::SMEM_BYTES, stream>>>(tu, tc, p);
         SelectParams sp{};
         sp.packed = p.partial; sp.counts = p.partial_cnt; sp.scores = nullptr; sp.idx = nullptr;
         sp.rows = (int)B; sp.L = 2 * pl.R; sp.slots = SC_KMAX; sp.k = (int)k;
@@ -973,8 +989,13 @@ int64_t unirec_score_topk_workspace_bytes(int64_t B, int64_t N, int64_t k) {
         set_last_error("score_topk: need B > 0, N > 0, 0 < k <= %d", SC_KMAX);
         return -1;
     }
-    const ScorePlan pl = make_plan(B < SC_MAX_USERS_PER_PASS ? B : SC_MAX_USERS_PER_PASS, N);
-    return static_cast<int64_t>(pl.total() + 1024);
+    // the passes of a call share one workspace: full passes of SC_MAX_USERS_PER_PASS users and a shorter last one
+    size_t need = make_plan(B < SC_MAX_USERS_PER_PASS ? B : SC_MAX_USERS_PER_PASS, N).total();
+    if (B > SC_MAX_USERS_PER_PASS && B % SC_MAX_USERS_PER_PASS != 0) {
+        const size_t last = make_plan(B % SC_MAX_USERS_PER_PASS, N).total();
+        need = last > need ? last : need;
+    }
+    return static_cast<int64_t>(need + 1024);
 }
 
 int unirec_score_topk(const void* users, int64_t ldu, const float* user_inv, const void* cands, int64_t ldc,
