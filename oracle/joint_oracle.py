@@ -3,12 +3,12 @@
 fp32 torch-CPU restatement, every function citing the reference lines it follows
 (training/train_item_individual_token_joint.py under /root/reference).  Only tests/ may import it.
 
-Parity status: PINNED for `infonce_loss` and `reciprocal_ranks` - oracle/pin_joint_against_reference.py extracts the
-UNMODIFIED source of the reference's `InfoNCELoss` and `MRREvaluator` classes (the file itself cannot be imported:
-it needs peft and calls torch.cuda.set_device(0) at import, :33), executes them on seeded inputs, checks this
-restatement against them and stores the reference's outputs in tests/golden/joint_scoring.npz.
-`inject_tokens` restates the three nested loops of JointQwen3WithQFormer.forward (:160-171), which cannot be run
-without the Qwen3 base model: parity unpinned for that function (it is an indexed copy; the test compares bit-exactly).
+Parity status: PINNED - oracle/pin_joint_against_reference.py extracts the UNMODIFIED source of the reference's
+`InfoNCELoss`, `MRREvaluator` and `MultiModalQwenEmbedding` classes (the file itself cannot be imported: it needs peft and
+calls torch.cuda.set_device(0) at import, :33), executes them on seeded inputs, checks this restatement against them and
+stores the reference's outputs in tests/golden/joint_scoring.npz.  `inject_tokens` is pinned against the unmodified
+`MultiModalQwenEmbedding.forward` (:146-171) run with a stub tokenizer and an identity stand-in for the Qwen3 base model
+(the injection loop touches neither): bit-exact.
 """
 from __future__ import annotations
 

@@ -20,6 +20,17 @@ def _free_port():
     return p
 
 
+def _leave(q):
+    """End a worker without tearing NCCL down: destroy_process_group() blocks for minutes while a captured CUDA graph still
+    references the communicator, and a test process has nothing to release gracefully."""
+    import sys
+    sys.stdout.flush()
+    sys.stderr.flush()
+    q.close()
+    q.join_thread()
+    os._exit(0)
+
+
 def _grad_worker(rank, world, port, wire, q):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -94,8 +105,11 @@ def _grad_worker(rank, world, port, wire, q):
         same = all(float((a - b).abs().max()) <= 1e-3 * float(a.abs().max()) + 1e-7 for a, b in zip(first, tg.grad_tensors()))
         torch.cuda.synchronize()
         q.put((rank, bool(ok and same)))
-    finally:
-        dist.destroy_process_group()
+    except Exception:
+        import traceback
+        traceback.print_exc()
+        q.put((rank, False))
+    _leave(q)
 
 
 def _rank_worker(rank, world, port, q):
@@ -119,8 +133,9 @@ def _rank_worker(rank, world, port, q):
         gen = torch.Generator().manual_seed(36)
         history = torch.randint(0, N, (B, Hmax), generator=gen).to(dev)
         lengths = torch.randint(1, Hmax + 1, (B,), generator=gen, dtype=torch.int32).to(dev)
-        # single GPU: all users, whole pool
-        one = NestedRanker(um, table, cands, k=k)
+        # single GPU: all users, whole pool - on a one-rank group (group=None would be the 2-rank default group)
+        solo = [dist.new_group([r_]) for r_ in range(world)][rank]
+        one = NestedRanker(um, table, cands, k=k, group=solo)
         u_all = one.encode_users(history, lengths)
         s1, i1 = one.rank(u_all)
         # two ranks: users split, candidate rows split, all-gather of the user vectors, per-rank top-k with global indices,
@@ -141,10 +156,17 @@ def _rank_worker(rank, world, port, q):
         s4, i4 = two.rank(u_all[ulo:uhi].contiguous(), local_result=True)
         ok = ok and bool(torch.equal(s4, s1[ulo:uhi])) and bool(torch.equal(i4, i1[ulo:uhi]))
         print(f"rank {rank}: merged == single-GPU list: {bool(torch.equal(i1, i2))}, min cos {float(cos.min()):.6f}", flush=True)
+        if not ok:
+            print(f"rank {rank}: scores equal {bool(torch.equal(s1, s2))} (max diff {float((s1 - s2).abs().max()):.3g}), "
+                  f"{int((i1 != i2).sum())} of {i1.numel()} indices differ; first rows:\n{i1[0, :8].tolist()}\n{i2[0, :8].tolist()}\n"
+                  f"{s1[0, :8].tolist()}\n{s2[0, :8].tolist()}", flush=True)
         torch.cuda.synchronize()
         q.put((rank, bool(ok)))
-    finally:
-        dist.destroy_process_group()
+    except Exception:
+        import traceback
+        traceback.print_exc()
+        q.put((rank, False))
+    _leave(q)
 
 
 def _run(target, *args):
@@ -156,10 +178,14 @@ def _run(target, *args):
     procs = [ctx.Process(target=target, args=(r, world, port) + args + (q,)) for r in range(world)]
     for p in procs:
         p.start()
-    for p in procs:
-        p.join(timeout=300)
-        assert p.exitcode == 0
-    assert dict(q.get(timeout=5) for _ in range(world)) == {0: True, 1: True}
+    try:
+        results = dict(q.get(timeout=240) for _ in range(world))
+    finally:
+        for p in procs:
+            p.join(timeout=20)
+            if p.is_alive():
+                p.kill()                     # our own child, by handle
+    assert results == {0: True, 1: True}
 
 
 needs2 = pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")

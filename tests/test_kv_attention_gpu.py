@@ -12,6 +12,15 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture(autouse=True, params=["umma", "mma_sync"])
+def kv_attention_impl(request, monkeypatch):
+    """Every test of this file runs on both variants of the fused kernel (UNIREC_KV_ATTENTION_IMPL is read per call):
+    "umma" - S / PV on tcgen05 with the attention state in registers, four partials per (user, head); "mma_sync" - the
+    first version (attention on mma.sync over the shared K/V tile, two partials)."""
+    monkeypatch.setenv("UNIREC_KV_ATTENTION_IMPL", request.param)
+    return request.param
+
+
 def _reference(x, wk, bk, wv, bv, q, mask, B, S, heads, q_broadcast):
     """fp32 torch restatement (mask: finfo.min added to masked keys, all-masked rows come out uniform)."""
     H = heads * 64
