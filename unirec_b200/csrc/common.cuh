@@ -166,6 +166,35 @@ UNIREC_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Non-blocking test (try_wait may suspend the thread up to a system-dependent time limit before it reports failure:
+// wrong for a thread that polls several barriers while it has other work to issue).
+UNIREC_DEVICE bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+UNIREC_DEVICE bool mbar_test_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
 // Cluster-scope variants (used by the LayerNorm-fused GEMM epilogue to exchange row statistics).
 UNIREC_DEVICE uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t cta_rank) {
     uint32_t r;

@@ -541,7 +541,7 @@ kv_attention_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                     const uint32_t tmem_att = tmem_base + (att_iter & 1u) * KA_TILE;
                     if (att_state == 0) {
                         if (blocking) mbar_wait(kv_ready, ph);
-                        else if (!mbar_try_wait(kv_ready, ph)) return;
+                        else if (!mbar_test_wait(kv_ready, ph)) return;
                         tc_fence_after();
 #pragma unroll 1
                         for (int h = 0; h < 2; ++h) {
@@ -566,7 +566,7 @@ kv_attention_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                         for (int h = 0; h < 2; ++h) {
                             if ((pv_mask >> h) & 1u) continue;
                             if (blocking) mbar_wait(&p_ready[h], ph);
-                            else if (!mbar_try_wait(&p_ready[h], ph)) continue;
+                            else if (!mbar_test_wait(&p_ready[h], ph)) continue;
                             tc_fence_after();
                             if (half_user(h) >= 0) {
                                 const uint32_t a_addr = c_addr + h * KA_SLAB_BYTES;      // P_h, written over K slab h
@@ -604,11 +604,11 @@ kv_attention_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                         const uint32_t aphase = (iter >> 1) & 1u;
                         // the accumulator stage comes back when the attention of the tile before last has read its O rows:
                         // keep serving this CTA's attention while waiting for it
-                        while (!mbar_try_wait_cluster(&tmem_empty_bar[as], aphase ^ 1)) service(false);
+                        while (!mbar_test_wait_cluster(&tmem_empty_bar[as], aphase ^ 1)) service(false);
                         tc_fence_after();
                         const uint32_t tmem_d = tmem_base + as * KA_TILE;
                         for (int kb = 0; kb < num_kb; ++kb) {
-                            while (!mbar_try_wait(&full_bar[stage], phase)) service(false);
+                            while (!mbar_test_wait(&full_bar[stage], phase)) service(false);
                             tc_fence_after();
                             const uint32_t a_addr = smem_u32(smem_a + stage * KA_A_BYTES);
                             const uint32_t b_addr = smem_u32(smem_b + stage * KA_B_BYTES);
