@@ -399,11 +399,11 @@ kv_attention_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
 //     columns per half.
 //   * P (bf16) is written over the K slabs (dead once S has been accumulated) as the K-major A operand of PV; V is used
 //     in place as the MN-major B operand.
-//   * the leader's issuer thread interleaves: projection k-blocks of the next tile, and - polled between them - the S / PV
-//     MMAs of its own CTA's current tile; the other CTA's issuer thread only does attention.
+//   * two issuer threads: warp 1 of the leader runs the projection main loop exactly as in gemm_cg2.cu; warp 3 of EACH CTA
+//     issues the S / PV MMAs of its CTA's current tile as the epilogue warps hand them over.
 // =====================================================================================================================
 constexpr int KU_STAGES = 4;
-constexpr int KU_THREADS = 352;                             // producer, issuer, TMEM allocator, 8 epilogue warps
+constexpr int KU_THREADS = 384;                             // producer, two issuers, TMEM allocator, 8 epilogue warps
 constexpr int KU_Q_BYTES = 128 * 64 * 2;                     // stacked queries of one user (rows 0-63 head a, 64-127 head b)
 constexpr int KU_SMEM_BYTES = KU_STAGES * KA_STAGE_BYTES + KA_SLABS * KA_SLAB_BYTES + 2 * KU_Q_BYTES + 1024 + KA_BARRIER_BYTES;
 static_assert(KU_SMEM_BYTES <= 232448, "shared memory budget exceeded");
@@ -489,9 +489,6 @@ kv_attention_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
 
     const int num_kb = p.K / KA_BLOCK_K;
     const int item_rows = p.users_per_item * p.S;
-    int my_items = 0;
-    if (cluster_id < p.num_items) my_items = (p.num_items - cluster_id + num_clusters - 1) / num_clusters;
-    const int total_iters = my_items * p.tiles_per_item;
 
     if (warp_idx == 0) {
         // ===================== TMA producer (both CTAs) =====================
@@ -518,118 +515,104 @@ kv_attention_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
             }
         }
     } else if (warp_idx == 1) {
-        // ===================== UMMA issuer: one thread per CTA =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc_proj = umma_idesc_bf16(KA_TILE, KA_TILE);
-            constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64);                       // both operands K-major
-            constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64) | (1u << 16);         // B (= V) MN-major
-            const uint32_t q_addr = smem_u32(smem_q);
-            const uint32_t c_addr = smem_u32(smem_c);
-            // ---- attention of this CTA's tiles, in tile order: state machine polled by `service`
-            int att_iter = 0, att_item = cluster_id, att_t = 0;
-            int att_state = 0;                           // 0: waiting for the K/V slabs; 1: S issued, PVs pending
-            uint32_t pv_mask = 0;
-            auto half_user = [&](int h) -> int {        // user whose keys the half holds, or -1 beyond the last row
-                const int grp = att_item / p.n_blocks;
-                const int m0 = grp * item_rows + att_t * KA_TILE + static_cast<int>(cta_rank) * 128 + 64 * h;
-                return m0 < p.M ? m0 / p.S : -1;
-            };
-            auto service = [&](bool blocking) {
-                for (;;) {
-                    if (att_iter >= total_iters) return;
-                    const uint32_t ph = att_iter & 1u;
-                    const uint32_t tmem_att = tmem_base + (att_iter & 1u) * KA_TILE;
-                    if (att_state == 0) {
-                        if (blocking) mbar_wait(kv_ready, ph);
-                        else if (!mbar_test_wait(kv_ready, ph)) return;
+        // ===================== projection UMMA issuer (leader CTA only): the main loop of gemm_cg2.cu =====================
+        if (is_leader) {
+            constexpr uint32_t idesc = umma_idesc_bf16(KA_TILE, KA_TILE);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t iter = 0;
+            for (int item = cluster_id; item < p.num_items; item += num_clusters) {
+                for (int t = 0; t < p.tiles_per_item; ++t, ++iter) {
+                    const uint32_t as = iter & 1u;
+                    const uint32_t aphase = (iter >> 1) & 1u;
+                    // the stage comes back when the attention of the tile before last has read its O rows (both CTAs)
+                    mbar_wait_cluster(&tmem_empty_bar[as], aphase ^ 1);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + as * KA_TILE;
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
-#pragma unroll 1
-                        for (int h = 0; h < 2; ++h) {
-                            const int u = half_user(h);
-                            if (u < 0) continue;
-                            const uint32_t a_addr = q_addr + (u & 1) * KU_Q_BYTES;
-#pragma unroll 1
-                            for (int hd = 0; hd < 2; ++hd) {                             // head a -> lanes 0-63, head b -> 64-127
-                                const uint32_t b_addr = c_addr + hd * KA_SLAB_BYTES + h * (64 * 128);
-#pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    umma_bf16_ss_lanes(tmem_att + 64 * h, umma_smem_desc_sw128(a_addr + k * 32),
-                                                       umma_smem_desc_sw128(b_addr + k * 32), idesc_s, k != 0 ? 1u : 0u, hd == 0);
-                            }
-                        }
-                        umma_commit(s_full);
-                        att_state = 1;
-                        pv_mask = 0;
-                    } else {
-                        bool progressed = false;
-#pragma unroll 1
-                        for (int h = 0; h < 2; ++h) {
-                            if ((pv_mask >> h) & 1u) continue;
-                            if (blocking) mbar_wait(&p_ready[h], ph);
-                            else if (!mbar_test_wait(&p_ready[h], ph)) continue;
-                            tc_fence_after();
-                            if (half_user(h) >= 0) {
-                                const uint32_t a_addr = c_addr + h * KA_SLAB_BYTES;      // P_h, written over K slab h
-#pragma unroll 1
-                                for (int hd = 0; hd < 2; ++hd) {
-                                    const uint32_t b_addr = c_addr + (2 + hd) * KA_SLAB_BYTES + h * (64 * 128);
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k)
-                                        umma_bf16_ss_lanes(tmem_att + 128 + 64 * h, umma_smem_desc_sw128(a_addr + k * 32),
-                                                           ku_desc_mn_sw128(b_addr + k * (16 * 128)), idesc_pv, k != 0 ? 1u : 0u,
-                                                           hd == 0);
-                                }
-                            }
-                            umma_commit(&pv_done[h]);
-                            pv_mask |= 1u << h;
-                            progressed = true;
-                        }
-                        if (pv_mask == 3u) {
-                            att_state = 0;
-                            ++att_iter;
-                            if (++att_t == p.tiles_per_item) { att_t = 0; att_item += num_clusters; }
-                            continue;
-                        }
-                        if (!progressed && !blocking) return;
-                    }
-                }
-            };
-            if (is_leader) {
-                int stage = 0;
-                uint32_t phase = 0;
-                uint32_t iter = 0;
-                for (int item = cluster_id; item < p.num_items; item += num_clusters) {
-                    for (int t = 0; t < p.tiles_per_item; ++t, ++iter) {
-                        const uint32_t as = iter & 1u;
-                        const uint32_t aphase = (iter >> 1) & 1u;
-                        // the accumulator stage comes back when the attention of the tile before last has read its O rows:
-                        // keep serving this CTA's attention while waiting for it
-                        while (!mbar_test_wait_cluster(&tmem_empty_bar[as], aphase ^ 1)) service(false);
-                        tc_fence_after();
-                        const uint32_t tmem_d = tmem_base + as * KA_TILE;
-                        for (int kb = 0; kb < num_kb; ++kb) {
-                            while (!mbar_test_wait(&full_bar[stage], phase)) service(false);
-                            tc_fence_after();
+                        if (lane == 0) {
                             const uint32_t a_addr = smem_u32(smem_a + stage * KA_A_BYTES);
                             const uint32_t b_addr = smem_u32(smem_b + stage * KA_B_BYTES);
 #pragma unroll
                             for (int k = 0; k < KA_BLOCK_K / 16; ++k)
                                 umma_bf16_ss_cg2(tmem_d, umma_smem_desc_sw128(a_addr + k * 32),
-                                                 umma_smem_desc_sw128(b_addr + k * 32), idesc_proj, (kb | k) != 0 ? 1u : 0u);
+                                                 umma_smem_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
                             umma_commit_cg2_mc(&empty_bar[stage], 0x3);
                             if (kb == num_kb - 1) umma_commit_cg2_mc(&tmem_full_bar[as], 0x3);
-                            if (++stage == KU_STAGES) { stage = 0; phase ^= 1; }
-                            service(false);
                         }
+                        __syncwarp();
+                        if (++stage == KU_STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
-            service(true);                               // the remaining attention work of this CTA
         }
-    } else if (warp_idx >= 3) {
-        // ===================== epilogue warps 3..10: drain the K/V tile, softmax, O accumulation (both CTAs) ==============
-        // (eight warps, two per TMEM lane quadrant = warp % 4; 352 threads per CTA leave 184 registers per thread)
-        const int ew = warp_idx - 3;
+    } else if (warp_idx == 3) {
+        // ===================== attention UMMA issuer (both CTAs, cta_group::1): S and PV of this CTA's tiles =================
+        // A thread of its own: the first version polled these barriers from the projection issuer between k-blocks and the
+        // polling (mbarrier test / try_wait round trips) throttled the main loop to 41 % tensor-pipe activity (profiles/r02_f).
+        // The tensor core executes what the two issuers hand it in arrival order; every dependency is an mbarrier.
+        constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64);                       // both operands K-major
+        constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64) | (1u << 16);         // B (= V) MN-major
+        const uint32_t q_addr = smem_u32(smem_q);
+        const uint32_t c_addr = smem_u32(smem_c);
+        uint32_t iter = 0;
+        for (int item = cluster_id; item < p.num_items; item += num_clusters) {
+            const int grp = item / p.n_blocks;
+            for (int t = 0; t < p.tiles_per_item; ++t, ++iter) {
+                const uint32_t ph = iter & 1u;
+                const uint32_t tmem_att = tmem_base + (iter & 1u) * KA_TILE;
+                const int m_cta = grp * item_rows + t * KA_TILE + static_cast<int>(cta_rank) * 128;
+                // user whose keys each 64-key half holds (-1: rows beyond the last user, nothing to attend)
+                const int u0 = m_cta < p.M ? m_cta / p.S : -1;
+                const int u1 = m_cta + 64 < p.M ? (m_cta + 64) / p.S : -1;
+                mbar_wait(kv_ready, ph);
+                tc_fence_after();
+                if (lane == 0) {
+#pragma unroll 1
+                    for (int h = 0; h < 2; ++h) {
+                        const int u = h == 0 ? u0 : u1;
+                        if (u < 0) continue;
+                        const uint32_t a_addr = q_addr + (u & 1) * KU_Q_BYTES;
+#pragma unroll 1
+                        for (int hd = 0; hd < 2; ++hd) {                                 // head a -> lanes 0-63, head b -> 64-127
+                            const uint32_t b_addr = c_addr + hd * KA_SLAB_BYTES + h * (64 * 128);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16_ss_lanes(tmem_att + 64 * h, umma_smem_desc_sw128(a_addr + k * 32),
+                                                   umma_smem_desc_sw128(b_addr + k * 32), idesc_s, k != 0 ? 1u : 0u, hd == 0);
+                        }
+                    }
+                    umma_commit(s_full);
+                }
+                __syncwarp();
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    mbar_wait(&p_ready[h], ph);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        if ((h == 0 ? u0 : u1) >= 0) {
+                            const uint32_t a_addr = c_addr + h * KA_SLAB_BYTES;          // P_h, written over K slab h
+#pragma unroll 1
+                            for (int hd = 0; hd < 2; ++hd) {
+                                const uint32_t b_addr = c_addr + (2 + hd) * KA_SLAB_BYTES + h * (64 * 128);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    umma_bf16_ss_lanes(tmem_att + 128 + 64 * h, umma_smem_desc_sw128(a_addr + k * 32),
+                                                       ku_desc_mn_sw128(b_addr + k * (16 * 128)), idesc_pv, k != 0 ? 1u : 0u,
+                                                       hd == 0);
+                            }
+                        }
+                        umma_commit(&pv_done[h]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp_idx >= 4) {
+        // ===================== epilogue warps 4..11: drain the K/V tile, softmax, O accumulation (both CTAs) ==============
+        const int ew = warp_idx - 4;
         const int quad = warp_idx & 3;           // TMEM lane quadrant this warp may access
         const int half = ew >> 2;                // drain: column half (0 = K slabs, 1 = V slabs); attention: 64-key half
         const int r = quad * 32 + lane;          // drain: key row of this CTA's tile; attention: row (head = r >> 6, query = r & 63)
