@@ -871,7 +871,7 @@ def run_ours(args, rank, world, local_rank):
             Mk, Nk, Kk = (int(x) for x in kshape.split("x"))          # rows = users x keys, 2 H, encoder width
             users_l = Mk // (Hh * 32)
             dom_shape, dom = kshape, kdom
-            dom_kernel = "kv_attention_umma_kernel" if os.environ.get("UNIREC_KV_ATTENTION_IMPL", "umma") != "mma_sync" \
+            dom_kernel = "kv_attention_umma_kernel" if os.environ.get("UNIREC_KV_ATTENTION_IMPL", "mma_sync") == "umma" \
                 else "kv_attention_fused_kernel"
             dom_text = (f"{dom_kernel}: K/V projection of one cross-attention layer (M x N x K = {kshape}, tcgen05 cta_group::2) "
                         "with the 64-query attention over the projected tile fused in (no K/V in HBM); one launch per layer")

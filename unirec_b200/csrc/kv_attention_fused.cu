@@ -67,6 +67,7 @@ struct KvAttnParams {
     float scale_log2;
     float* o_part;               // [(user * heads + head) * 2 + cta][64][64] unnormalised context
     float* ml_part;              // [(user * heads + head) * 2 + cta][2][64] running max (log2 domain), running sum
+    int debug;                   // timing experiments only (UNIREC_KV_DEBUG): bit 0 skips the S MMAs, bit 1 the PV MMAs
 };
 
 UNIREC_DEVICE void epi_bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(KA_EPI_WARPS * 32) : "memory"); }
@@ -573,7 +574,7 @@ kv_attention_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
 #pragma unroll 1
                     for (int h = 0; h < 2; ++h) {
                         const int u = h == 0 ? u0 : u1;
-                        if (u < 0) continue;
+                        if (u < 0 || (p.debug & 1)) continue;
                         const uint32_t a_addr = q_addr + (u & 1) * KU_Q_BYTES;
 #pragma unroll 1
                         for (int hd = 0; hd < 2; ++hd) {                                 // head a -> lanes 0-63, head b -> 64-127
@@ -592,7 +593,7 @@ kv_attention_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                     mbar_wait(&p_ready[h], ph);
                     tc_fence_after();
                     if (lane == 0) {
-                        if ((h == 0 ? u0 : u1) >= 0) {
+                        if ((h == 0 ? u0 : u1) >= 0 && !(p.debug & 2)) {
                             const uint32_t a_addr = c_addr + h * KA_SLAB_BYTES;          // P_h, written over K slab h
 #pragma unroll 1
                             for (int hd = 0; hd < 2; ++hd) {
@@ -893,9 +894,13 @@ int kv_attention_fused(const void* x, long long ldx, const void* w_packed, long 
     p.q_batch_rows = static_cast<int>(q_batch_rows);
     p.key_mask = key_mask;
     p.scale_log2 = scale * 1.4426950408889634f;
-    // variant: "umma" (S / PV on tcgen05, four partials per (user, head)) or "mma_sync" (two partials); UNIREC_KV_ATTENTION_IMPL
-    const char* env = getenv("UNIREC_KV_ATTENTION_IMPL");           // read per call: tests switch between the two
-    const int impl = (env != nullptr && strcmp(env, "mma_sync") == 0) ? 0 : 1;
+    const char* dbg = getenv("UNIREC_KV_DEBUG");
+    p.debug = dbg != nullptr ? atoi(dbg) : 0;
+    // variant: "mma_sync" (two partials per (user, head)) or "umma" (S / PV on tcgen05, four partials); UNIREC_KV_ATTENTION_IMPL
+    // read per call (tests switch between the two); the mma.sync variant is the faster one in the step (30.1 vs 33.4 ms per
+    // layer and 4096 users, profiles/r02_b / r02_g) and therefore the default of this optional path
+    const char* env = getenv("UNIREC_KV_ATTENTION_IMPL");
+    const int impl = (env != nullptr && strcmp(env, "umma") == 0) ? 1 : 0;
     const int parts = impl == 1 ? 4 : 2;
     p.o_part = reinterpret_cast<float*>(workspace);
     p.ml_part = p.o_part + users * num_heads * parts * (KA_NQ * 64);
