@@ -36,6 +36,7 @@ struct AttnParams {
     const float* key_mask;   // [B, nk] (1 attend / 0 masked) or nullptr
     int num_heads, nq, nk;
     int q_broadcast;         // 1: the same queries serve every batch element
+    int reverse;             // 1: walk the work items from the last to the first (see stream_reverse(), common.cuh)
     float scale_log2;        // softmax scale * log2(e)
     DropoutParams drop;      // train-mode dropout of the probabilities (models/qformer.py:258); DROP kernels only
 };
@@ -90,7 +91,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     auto issue = [&](int g) {
         if (g >= total) return;
         const int it = g / ntiles, tile = g - it * ntiles;
-        const int w = blockIdx.x + it * gridDim.x;
+        const int w0 = blockIdx.x + it * gridDim.x;
+        const int w = p.reverse ? num_items - 1 - w0 : w0;
         const int b = w / p.num_heads, h = w - b * p.num_heads;
         const int buf = g % ATT_STAGES;
         if (!plain) {
@@ -210,7 +212,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             // the row sum above is that of the un-dropped probabilities (softmax first, dropout second, :250-258)
             const DropoutParams drop = dropout_resolve(p.drop);
             const unsigned long long row0 =
-                static_cast<unsigned long long>(blockIdx.x + it * gridDim.x) * p.nq + warp * 16 + g4;
+                static_cast<unsigned long long>(p.reverse ? num_items - 1 - static_cast<int>(blockIdx.x + it * gridDim.x)
+                                                          : static_cast<int>(blockIdx.x + it * gridDim.x)) * p.nq + warp * 16 + g4;
 #pragma unroll
             for (int kb = 0; kb < (KT + 31) / 32; ++kb) {
                 const uint32_t group = static_cast<uint32_t>(((tile * KT) >> 5) + kb) * 4 + t;
@@ -259,7 +262,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if (tile == ntiles - 1) {
             // ---- normalise, stage this warp's 16 context rows (swizzled like a TMA tile) and hand them to the TMA
             //      store engine: head-merged [B*nq, H] output, rows beyond nq are clipped by the tensor map
-            const int w = blockIdx.x + it * gridDim.x;
+            const int w0 = blockIdx.x + it * gridDim.x;
+            const int w = p.reverse ? num_items - 1 - w0 : w0;
             const int b = w / p.num_heads, h = w - b * p.num_heads;
             float inv[2];
 #pragma unroll
@@ -344,6 +348,7 @@ int attention(const void* q, long long ldq, long long q_batch_rows, const void* 
     p.key_mask = key_mask;
     p.num_heads = static_cast<int>(num_heads); p.nq = static_cast<int>(nq); p.nk = static_cast<int>(nk);
     p.q_broadcast = q_batch_rows == 0 ? 1 : 0;
+    p.reverse = stream_reverse() ? 1 : 0;
     p.scale_log2 = scale * 1.4426950408889634f;
     p.drop.thr16 = drop_thr16; p.drop.seed = drop_seed; p.drop.site = drop_site; p.drop.seed_offset = drop_seed_offset;
     p.drop.scale = 65536.0f / (65536.0f - static_cast<float>(drop_thr16));

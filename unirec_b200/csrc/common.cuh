@@ -3,6 +3,7 @@
 // mma.sync, plus small numeric utilities.  Everything here is written against the PTX ISA for
 // sm_100a; there is no other architecture path.
 #pragma once
+#include <cstdlib>
 
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -10,6 +11,15 @@
 #include <stdint.h>
 
 namespace unirec {
+
+// Streaming kernels that consume what a GEMM has just written (LayerNorm, the small-tile attention) walk their rows /
+// work items from the LAST to the FIRST: a persistent GEMM finishes with its highest row blocks, so those are the lines
+// still in the 126 MB L2, and what the streaming kernel writes last (the lowest rows) is what the next GEMM reads first.
+// On a power-capped part the DRAM bytes saved are clock.  UNIREC_STREAM_REVERSE=0 restores the forward order (A/B runs).
+inline bool stream_reverse() {
+    const char* e = getenv("UNIREC_STREAM_REVERSE");
+    return !(e != nullptr && e[0] == '0');
+}
 
 #define UNIREC_DEVICE __device__ __forceinline__
 

@@ -98,10 +98,19 @@ template <int MAX_VEC>
 __global__ void __launch_bounds__(256)
 layernorm_bf16_stream_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                              const float* __restrict__ beta, float eps, void* __restrict__ out_, long long ldo,
-                             int out_fp32, int rows, int H) {
+                             int out_fp32, int rows, int H, int reverse) {
     const int lane = threadIdx.x & 31;
     const int warps_total = (gridDim.x * blockDim.x) >> 5;
     int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // reverse: visit row (rows - 1 - i) at step i (stream_reverse(), common.cuh); x / out are re-based so that the loop below
+    // runs unchanged on mirrored row numbers
+    if (reverse) {
+        x += static_cast<long long>(rows - 1) * ldx;
+        ldx = -ldx;
+        out_ = out_fp32 ? static_cast<void*>(reinterpret_cast<float*>(out_) + static_cast<long long>(rows - 1) * ldo)
+                        : static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(out_) + static_cast<long long>(rows - 1) * ldo);
+        ldo = -ldo;
+    }
     const int nvec = H / 8;
     uint4 cur[MAX_VEC], nxt[MAX_VEC];
     auto load = [&](int r, uint4 (&dst)[MAX_VEC]) {
@@ -200,12 +209,13 @@ int layernorm(const void* x, int x_fp32, long long ldx, int in_row_mod, const vo
         long long grid = static_cast<long long>(sms) * (H <= 256 ? per_sm_1 : per_sm_4);
         if (grid > blocks) grid = blocks;
         const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+        const int rev = stream_reverse() ? 1 : 0;
         if (H <= 256)
             layernorm_bf16_stream_kernel<1><<<static_cast<unsigned>(grid), threads, 0, stream>>>(xb, ldx, gamma, beta, eps, out, ldo,
-                                                                                              out_fp32, (int)rows, (int)H);
+                                                                                              out_fp32, (int)rows, (int)H, rev);
         else
             layernorm_bf16_stream_kernel<4><<<static_cast<unsigned>(grid), threads, 0, stream>>>(xb, ldx, gamma, beta, eps, out, ldo,
-                                                                                              out_fp32, (int)rows, (int)H);
+                                                                                              out_fp32, (int)rows, (int)H, rev);
         cudaError_t e2 = cudaGetLastError();
         if (e2 != cudaSuccess) {
             set_last_error("layernorm launch: %s", cudaGetErrorString(e2));
