@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, call J (1 GPU): reverse traversal of the streaming kernels (LayerNorm, small-tile attention) - tests, then an A/B
-# of the bench on one box (UNIREC_STREAM_REVERSE = 1 / 0, twice each, alternating).
+# of the bench on one box (UNIREC_STREAM_REVERSE = 1 (alternating traversal directions) / 0 (all forward), twice each, interleaved).
 set -u
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_kernels_gpu.py tests/test_modules_gpu.py tests/test_train_gpu.py -m gpu -q --timeout 300 -p no:cacheprovider -x > gpurun_out/pytest_reverse.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_reverse.log

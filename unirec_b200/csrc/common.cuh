@@ -12,14 +12,14 @@
 
 namespace unirec {
 
-// Streaming kernels that consume what a GEMM has just written (LayerNorm, the small-tile attention) walk their rows /
-// work items from the LAST to the FIRST: a persistent GEMM finishes with its highest row blocks, so those are the lines
-// still in the 126 MB L2, and what the streaming kernel writes last (the lowest rows) is what the next GEMM reads first.
-// On a power-capped part the DRAM bytes saved are clock.  UNIREC_STREAM_REVERSE=0 restores the forward order (A/B runs).
-inline bool stream_reverse() {
-    const char* e = getenv("UNIREC_STREAM_REVERSE");
-    return !(e != nullptr && e[0] == '0');
-}
+// Traversal order.  The kernels of an encoder layer form a chain - each one reads what its predecessor wrote - and every
+// one of them walks its rows / output tiles in order.  A persistent kernel finishes with its LAST rows, so those are the
+// lines still in the 126 MB L2 when the successor starts: the successor therefore walks in the OPPOSITE direction (it starts
+// with hot lines, and what it writes last is what ITS successor reads first).  `next_traversal()` hands out alternating
+// directions to the participating launches (CTA-pair GEMM, streaming LayerNorm, small-tile attention); any order is
+// arithmetically the same.  On a power-capped part the DRAM bytes saved are clock.  UNIREC_STREAM_REVERSE=0: always forward.
+bool next_traversal();             // defined in capi.cu
+inline bool stream_reverse() { return next_traversal(); }
 
 #define UNIREC_DEVICE __device__ __forceinline__
 

@@ -59,6 +59,7 @@ struct Gemm2Params {
     int slots_per_user;
     int table_rows;                 // rows of the token table viewed 2-D: an out-of-bounds coordinate (TMA zero fill)
     int res_period;                 // > 0: the residual tile of rows m.. is read at rows (m % res_period).. of its table
+    int reverse;                    // 1: walk the output tiles from the last to the first (next_traversal(), common.cuh)
 };
 
 template <int MODE, bool GATHER = false>
@@ -126,8 +127,9 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-            const int m_blk = tile / p.num_n_blocks;
-            const int n_blk = tile % p.num_n_blocks;
+            const int tile_e = p.reverse ? num_tiles - 1 - tile : tile;
+            const int m_blk = tile_e / p.num_n_blocks;
+            const int n_blk = tile_e % p.num_n_blocks;
             const int m_coord = m_blk * G2_TILE_M + static_cast<int>(cta_rank) * 128;
             const int n_coord = n_blk * G2_TILE_N + static_cast<int>(cta_rank) * 128;
             // GATHER: source row of each of this CTA's four 32-row groups (the same for every k-block of the tile)
@@ -214,8 +216,9 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         int prev_m = 0, prev_n = 0;
         uint32_t iter = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++iter) {
-            const int m_blk = tile / p.num_n_blocks;
-            const int n_blk = tile % p.num_n_blocks;
+            const int tile_e = p.reverse ? num_tiles - 1 - tile : tile;
+            const int m_blk = tile_e / p.num_n_blocks;
+            const int n_blk = tile_e % p.num_n_blocks;
             const int m_coord = m_blk * G2_TILE_M + static_cast<int>(cta_rank) * 128;
             const int n_coord = n_blk * G2_TILE_N;
 #pragma unroll 1
@@ -266,7 +269,7 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         const uint32_t tmem_empty_leader0 = mapa_u32(smem_u32(&tmem_empty_bar[0]), 0);
         uint32_t iter = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++iter) {
-            const int n_blk = tile % p.num_n_blocks;
+            const int n_blk = (p.reverse ? num_tiles - 1 - tile : tile) % p.num_n_blocks;
             const uint32_t as = iter & 1u;
             const uint32_t aphase = (iter >> 1) & 1u;
             mbar_wait(&tmem_full_bar[as], aphase);
@@ -389,6 +392,7 @@ int gemm_bf16_cg2(const void* A, long long lda, const void* W, long long ldw, co
     p.num_m_blocks = static_cast<int>((M + G2_TILE_M - 1) / G2_TILE_M);
     p.num_n_blocks = static_cast<int>(N / G2_TILE_N);
     p.gather_ids = nullptr; p.gather_len = nullptr; p.slots_per_user = 0; p.table_rows = 0; p.res_period = 0;
+    p.reverse = next_traversal() ? 1 : 0;
     CUtensorMap ta, tb, to, tr;
     int rc = make_tmap_bf16_2d(&ta, A, M, K, lda, 128);
     if (rc != UNIREC_OK) return rc;
@@ -441,6 +445,7 @@ int gemm_bf16_cg2_gather(const void* table, long long ld_table, long long table_
     p.num_n_blocks = static_cast<int>(N / G2_TILE_N);
     p.gather_ids = ids; p.gather_len = lengths; p.slots_per_user = static_cast<int>(slots_per_user);
     p.table_rows = static_cast<int>(table_rows); p.res_period = static_cast<int>(period);
+    p.reverse = 0;
     CUtensorMap ta, tb, to, tr, tp;
     int rc = make_tmap_bf16_2d(&ta, table, table_rows, K, ld_table, 32);
     if (rc != UNIREC_OK) return rc;
