@@ -6,16 +6,6 @@
 #include <atomic>
 
 namespace unirec {
-// see common.cuh: alternating traversal directions for the kernels of a chain
-bool next_traversal() {
-    static std::atomic<unsigned> counter{0};
-    const char* e = getenv("UNIREC_STREAM_REVERSE");
-    if (e != nullptr && e[0] == '0') return false;
-    return (counter.fetch_add(1, std::memory_order_relaxed) & 1u) == 0u;
-}
-}  // namespace unirec
-
-namespace unirec {
 const char* get_last_error();
 int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias, const void* residual,
               long long ldr, int res_row_mod, void* out, long long ldo, int out_fp32, long long M, long long N,

@@ -12,14 +12,16 @@
 
 namespace unirec {
 
-// Traversal order.  The kernels of an encoder layer form a chain - each one reads what its predecessor wrote - and every
-// one of them walks its rows / output tiles in order.  A persistent kernel finishes with its LAST rows, so those are the
-// lines still in the 126 MB L2 when the successor starts: the successor therefore walks in the OPPOSITE direction (it starts
-// with hot lines, and what it writes last is what ITS successor reads first).  `next_traversal()` hands out alternating
-// directions to the participating launches (CTA-pair GEMM, streaming LayerNorm, small-tile attention); any order is
-// arithmetically the same.  On a power-capped part the DRAM bytes saved are clock.  UNIREC_STREAM_REVERSE=0: always forward.
-bool next_traversal();             // defined in capi.cu
-inline bool stream_reverse() { return next_traversal(); }
+// Traversal order.  The streaming kernels that consume what a GEMM has just written (LayerNorm, the small-tile attention)
+// walk their rows / work items from the LAST to the FIRST: a persistent GEMM finishes with its highest row blocks, so those
+// are the lines still in the 126 MB L2, and what the streaming kernel writes last (the lowest rows) is what the next GEMM
+// reads first.  Any order is arithmetically the same; on a power-capped part the DRAM bytes saved are clock: +0.7 % users/s,
+// +0.4 % items/s in an interleaved A/B on one box (profiles/r02_j_*).  Letting the directions ALTERNATE along the whole chain,
+// GEMMs included, measured -0.4 % against all-forward (same profiles) and was dropped.  UNIREC_STREAM_REVERSE=0: forward.
+inline bool stream_reverse() {
+    const char* e = getenv("UNIREC_STREAM_REVERSE");
+    return !(e != nullptr && e[0] == '0');
+}
 
 #define UNIREC_DEVICE __device__ __forceinline__
 

@@ -59,7 +59,7 @@ struct Gemm2Params {
     int slots_per_user;
     int table_rows;                 // rows of the token table viewed 2-D: an out-of-bounds coordinate (TMA zero fill)
     int res_period;                 // > 0: the residual tile of rows m.. is read at rows (m % res_period).. of its table
-    int reverse;                    // 1: walk the output tiles from the last to the first (next_traversal(), common.cuh)
+    int reverse;                    // 1: walk the output tiles from the last to the first (experiment, see common.cuh)
 };
 
 template <int MODE, bool GATHER = false>
@@ -392,7 +392,7 @@ int gemm_bf16_cg2(const void* A, long long lda, const void* W, long long ldw, co
     p.num_m_blocks = static_cast<int>((M + G2_TILE_M - 1) / G2_TILE_M);
     p.num_n_blocks = static_cast<int>(N / G2_TILE_N);
     p.gather_ids = nullptr; p.gather_len = nullptr; p.slots_per_user = 0; p.table_rows = 0; p.res_period = 0;
-    p.reverse = next_traversal() ? 1 : 0;
+    p.reverse = 0;      // GEMMs walk forward; reversing them as well (alternating directions) measured slower, see common.cuh
     CUtensorMap ta, tb, to, tr;
     int rc = make_tmap_bf16_2d(&ta, A, M, K, lda, 128);
     if (rc != UNIREC_OK) return rc;
