@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--layer-major", type=int, default=0, help="1: user Q-Former in layer-major order (one encoder call per "
                     "step, K/V of ONE layer materialised per chunk of users inside it); 0: chunk-major (K/V of all 4 layers "
                     "per 512-user chunk, the sequence is read once)")
+    ap.add_argument("--fold-ln", type=int, default=-1, help="1 / 0: LayerNorms of both encoders folded into the GEMMs around "
+                    "them (no LayerNorm kernels between the GEMMs) / separate streaming LayerNorm kernels; -1: module default")
     ap.add_argument("--exchange", default="alltoall", choices=["alltoall", "allgather"], help="N > 1: how the per-rank top-k "
                     "lists travel (alltoall: every rank merges and returns its own users; allgather: every rank merges all)")
     ap.add_argument("--top-k", type=int, default=100)
@@ -82,6 +84,7 @@ def config_dict(args, n_gpus):
         "user_cross_attention": ("K/V projected inside the attention kernel (no K/V in HBM)" if args.fused_kv else
                                  "layer-major: K/V of one layer materialised per chunk of users (<= 14 GiB), then attention"
                                  if args.layer_major else "K/V of all layers materialised per chunk, then attention"),
+        "layernorm": "module default" if args.fold_ln < 0 else ("folded into the GEMMs" if args.fold_ln else "streaming kernels"),
         "history_items": args.history, "tokens_per_item": 32, "keys_per_user": args.history * 32,
         "user_qformer": "4 layers x 64 queries, hidden 1024, 16 heads, FFN 4096, cross-attn every layer",
         "item_qformer": "12 layers x 32 queries, 14 fields x 1024, cross-attn every 2nd layer",
@@ -588,6 +591,8 @@ def run_ours(args, rank, world, local_rank):
         user.max_kv_bytes = int(args.kv_gb * (1 << 30))
     user.fused_kv_attention = bool(args.fused_kv)
     user.layer_major = bool(args.layer_major)
+    if args.fold_ln >= 0:
+        item.qformer.fold_layernorm = user.qformer.fold_layernorm = bool(args.fold_ln)
 
     # ------------------------------------------------------------------ stage A: item-token generation (cfg 3)
     N, Bi = args.pool_items, args.item_batch

@@ -119,6 +119,82 @@ def test_linear_cta_pair_strided_and_few_clusters():
         ops.linear(a, w, None, block_n=2, out_dtype=torch.float32)
 
 
+@pytest.mark.parametrize("M,H,I", [(300, 256, 512), (2048, 1024, 4096), (37, 1024, 1024)])
+def test_linear_with_folded_layernorm(M, H, I):
+    """unirec_linear_ln_bf16: the LayerNorm between two GEMMs is never materialised (models/qformer.py:285-289, 371-375).
+    Producer: pre = dense(x) + residual, row statistics of the stored bf16 values.  Consumers: Linear(LN(pre)) through
+    gamma-scaled weights + rank-one epilogue correction (plain and GELU), and dense(y) + LN(pre) as a residual.
+    Reference: fp32 torch on the same bf16 inputs; tolerance = bf16 output rounding (2^-9 relative) + accumulated input
+    rounding, rtol 1.5e-2 / atol 3e-2 on O(1) outputs."""
+    from unirec_b200 import ops
+    eps = 1e-12
+    x = _randn(M, I, seed=11, dtype=torch.bfloat16)
+    w2 = _randn(H, I, seed=12, scale=0.03, dtype=torch.bfloat16)
+    b2 = _randn(H, seed=13, scale=0.3)
+    res = _randn(M, H, seed=14, dtype=torch.bfloat16) + 0.25      # a non-zero row mean
+    gamma = 1.0 + _randn(H, seed=15, scale=0.1)
+    beta = _randn(H, seed=16, scale=0.1)
+    # --- producer: pre + statistics
+    stats = ops.ln_stats_buffer(M, H, _dev()).fill_(float("nan"))        # every slot must be written
+    pre = ops.linear_ln(x, w2, b2, epilogue=ops.EPI_BIAS_RESIDUAL, residual=res, stats_out=stats, eps=eps, hidden=H)
+    pre_ref = x.float() @ w2.float().t() + b2 + res.float()
+    torch.testing.assert_close(pre.float(), pre_ref, rtol=1e-2, atol=2e-2)
+    pf = pre.float()                                             # the statistics describe the STORED values
+    assert tuple(stats.shape) == (M, H // 128, 2)
+    torch.testing.assert_close(stats[..., 0], pf.view(M, H // 128, 128).sum(2), rtol=1e-5, atol=1e-3)
+    torch.testing.assert_close(stats[..., 1], (pf * pf).view(M, H // 128, 128).sum(2), rtol=1e-5, atol=1e-3)
+    # deterministic: a second launch writes the same bits (no atomics)
+    stats_b = ops.ln_stats_buffer(M, H, _dev())
+    pre_b = ops.linear_ln(x, w2, b2, epilogue=ops.EPI_BIAS_RESIDUAL, residual=res, stats_out=stats_b, eps=eps, hidden=H)
+    assert torch.equal(pre, pre_b) and torch.equal(stats, stats_b)
+    h_ref = F.layer_norm(pf, (H,), gamma, beta, eps)
+    # --- consumer 1: Linear(LN(pre)), bias and GELU epilogues
+    w1 = _randn(I, H, seed=17, scale=0.03)
+    b1 = _randn(I, seed=18, scale=0.3)
+    wf, bf, cf = ops.fold_layernorm_weights(w1, b1, gamma, beta)
+    lin_ref = h_ref @ w1.t() + b1
+    y = ops.linear_ln(pre, wf, bf, ln_in=(stats, cf), eps=eps, hidden=H)
+    torch.testing.assert_close(y.float(), lin_ref, rtol=1.5e-2, atol=3e-2)
+    y = ops.linear_ln(pre, wf, bf, epilogue=ops.EPI_BIAS_GELU, ln_in=(stats, cf), eps=eps, hidden=H)
+    torch.testing.assert_close(y.float(), F.gelu(lin_ref), rtol=1.5e-2, atol=3e-2)
+    # against the materialised pair of kernels (LayerNorm kernel + plain GEMM): same error class
+    h = ops.layernorm(pre, gamma, beta, eps)
+    y_mat = ops.linear(h, w1.to(torch.bfloat16), b1, epilogue=ops.EPI_BIAS_GELU)
+    e_fold = float((y.float() - F.gelu(lin_ref)).abs().max())
+    e_mat = float((y_mat.float() - F.gelu(lin_ref)).abs().max())
+    print(f"folded LN->GEMM max|d| {e_fold:.4f}, materialised {e_mat:.4f}")
+    assert e_fold <= max(2.0 * e_mat, 2e-2)
+    # --- consumer 2: dense(inter) + LN(pre) as the residual, statistics of the result
+    inter = _randn(M, I, seed=19, dtype=torch.bfloat16)
+    stats2 = ops.ln_stats_buffer(M, H, _dev())
+    pre2 = ops.linear_ln(inter, w2, b2, epilogue=ops.EPI_BIAS_RESIDUAL, residual=pre, ln_res=(stats, gamma, beta),
+                         stats_out=stats2, eps=eps, hidden=H)
+    pre2_ref = inter.float() @ w2.float().t() + b2 + h_ref
+    torch.testing.assert_close(pre2.float(), pre2_ref, rtol=1e-2, atol=2e-2)
+    torch.testing.assert_close(stats2[..., 0].sum(1), pre2.float().sum(1), rtol=1e-5, atol=2e-3)
+    # all three at once: A and the residual are the same folded tensor (the FFN-down GEMM never has that, the kernel allows it)
+    if I == H:
+        y3 = ops.linear_ln(pre, wf, bf, epilogue=ops.EPI_BIAS_RESIDUAL, residual=pre, ln_in=(stats, cf),
+                           ln_res=(stats, gamma, beta), eps=eps, hidden=H)
+        torch.testing.assert_close(y3.float(), lin_ref + h_ref, rtol=1.5e-2, atol=3e-2)
+
+
+def test_linear_ln_rejects_bad_arguments():
+    from unirec_b200 import ops
+    a = _randn(64, 256, seed=1, dtype=torch.bfloat16)
+    w = _randn(256, 256, seed=2, dtype=torch.bfloat16)
+    b = _randn(256, seed=3)
+    st = ops.ln_stats_buffer(64, 256, _dev())
+    with pytest.raises(RuntimeError):          # N not a multiple of 256
+        ops.linear_ln(a, w[:128].contiguous(), b[:128].contiguous(), stats_out=st)
+    with pytest.raises(RuntimeError):          # statistics of the wrong shape
+        ops.linear_ln(a, w, b, stats_out=torch.zeros(64, 2, device=_dev()))
+    with pytest.raises(RuntimeError):          # residual statistics without the residual epilogue
+        ops.linear_ln(a, w, b, ln_res=(st, b, b))
+    with pytest.raises(RuntimeError):          # CPU tensors
+        ops.linear_ln(a.cpu(), w.cpu(), b.cpu())
+
+
 def test_linear_rejects_bad_arguments():
     from unirec_b200 import ops
     a = _randn(64, 100, dtype=torch.bfloat16)  # K not a multiple of 64

@@ -116,6 +116,67 @@ def test_user_qformer_matches_reference_golden(name):
     print("layer-major per-user chunks == one chunk, bit for bit:", bool(torch.equal(out_l, out_l2)))
 
 
+@pytest.mark.parametrize("name", list(ITEM_CASES))
+def test_item_qformer_folded_layernorm_matches_reference_golden(name):
+    """QFormerBackbone.fold_layernorm: no LayerNorm kernels between the GEMMs (unirec_linear_ln_bf16) - same bar as the
+    materialised path against the reference's goldens, and the two paths agree with each other at bf16 noise level."""
+    from unirec_b200 import _lib
+    from unirec_b200.modules import QFormerForItemRepresentation
+    c = ITEM_CASES[name]
+    mk = c["model"]
+    if mk["hidden"] % 256 or mk["inter"] % 256:
+        pytest.skip("the folded path needs hidden and FFN widths that are multiples of 256")
+    sd = synth.item_qformer_state_dict(**mk, seed=c["seed"], attn_std=c["attn_std"])
+    model = QFormerForItemRepresentation(hidden_size=mk["hidden"], num_hidden_layers=mk["layers"],
+                                         num_attention_heads=c["heads"], intermediate_size=mk["inter"],
+                                         num_query_tokens=mk["num_query"], field_embedding_dim=mk["field_dim"],
+                                         num_fields=mk["num_fields"])
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).eval()
+    model.prelayernorm_dtype = torch.bfloat16
+    x, mask = synth.item_fields(**c["input"])
+    g = np.load(os.path.join(GOLDEN, f"item_{name}.npz"))
+    n0 = _lib.launch_count()
+    plain = model(x.to(DEV), mask.to(DEV))["query_outputs"]
+    n_plain = _lib.launch_count() - n0
+    model.qformer.fold_layernorm = True
+    n0 = _lib.launch_count()
+    out = model(x.to(DEV), mask.to(DEV))
+    n_fold = _lib.launch_count() - n0
+    print(f"item[{name}] launches: {n_plain} materialised, {n_fold} folded")
+    assert n_fold < n_plain
+    tol = _item_tolerances(name, sd, x, mask, c["heads"], g["query_outputs"])
+    _check(f"item[{name}].query_outputs (folded LN)", out["query_outputs"], g["query_outputs"], **tol)
+    _report(f"item[{name}] folded vs materialised", out["query_outputs"], plain.cpu())
+    model.qformer.hoist_layer0 = False           # the folded chain starts at the broadcast embedding LayerNorm
+    out2 = model(x.to(DEV), mask.to(DEV))
+    _check(f"item[{name}].query_outputs (folded LN, no hoist)", out2["query_outputs"], g["query_outputs"], **tol)
+
+
+@pytest.mark.parametrize("name", list(USER_CASES))
+def test_user_qformer_folded_layernorm_matches_reference_golden(name):
+    from unirec_b200.modules import UserQFormer
+    c = USER_CASES[name]
+    mk = c["model"]
+    if mk["hidden"] % 256 or mk["inter"] % 256:
+        pytest.skip("the folded path needs hidden and FFN widths that are multiples of 256")
+    sd = synth.user_qformer_state_dict(**mk, seed=c["seed"], attn_std=c["attn_std"])
+    model = UserQFormer(hidden_size=mk["hidden"], num_hidden_layers=mk["layers"], num_attention_heads=c["heads"],
+                        intermediate_size=mk["inter"], num_query_tokens=mk["num_query"],
+                        input_embedding_dim=mk["input_dim"], num_item_tokens_to_predict=mk["num_predict"])
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).eval()
+    model.prelayernorm_dtype = torch.bfloat16
+    model.qformer.fold_layernorm = True
+    x, mask = synth.user_sequences(**c["input"])
+    g = np.load(os.path.join(GOLDEN, f"user_{name}.npz"))["predicted_item_tokens"]
+    out = model(x.to(DEV), mask.to(DEV))
+    _check(f"user[{name}].predicted_item_tokens (folded LN)", out, g, max_tol=0.1, mean_tol=0.015, cos_tol=0.9995)
+    model.max_kv_bytes = 1                       # one user per encoder call
+    out_c = model(x.to(DEV), mask.to(DEV))
+    _check(f"user[{name}].chunked (folded LN)", out_c, g, max_tol=0.1, mean_tol=0.015, cos_tol=0.9995)
+
+
 def test_item_qformer_against_oracle_larger_batch():
     """B = 300 (not a multiple of any tile size) on the small model, oracle computed here on CPU."""
     from oracle import qformer_oracle as O

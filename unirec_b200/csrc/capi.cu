@@ -1,12 +1,16 @@
 // extern "C" surface of libunirec_b200.so (declared in include/unirec_b200.h): thin argument
 // marshalling over the kernel launchers; no torch types, borrowed device pointers, caller's stream.
 #include "common.cuh"
+#include "umma_pipe.cuh"
 #include "../../include/unirec_b200.h"
 
 #include <atomic>
 
 namespace unirec {
 const char* get_last_error();
+int gemm_bf16_ln(const void* A, long long lda, const void* W, long long ldw, const float* bias, const void* residual,
+                 long long ldr, void* out, long long ldo, long long M, long long N, long long K, int epilogue,
+                 const LnFold& ln, cudaStream_t stream);
 int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias, const void* residual,
               long long ldr, int res_row_mod, void* out, long long ldo, int out_fp32, long long M, long long N,
               long long K, int epilogue, int block_n, int max_ctas, cudaStream_t stream);
@@ -115,6 +119,19 @@ int unirec_linear_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, c
                        int64_t M, int64_t N, int64_t K, int epilogue, int block_n, int max_ctas, void* stream) {
     COUNTED(gemm_bf16(A, lda, W, ldw, bias, residual, ldr, static_cast<int>(res_row_mod), out, ldo, out_fp32, M, N, K,
                       epilogue, block_n, max_ctas, static_cast<cudaStream_t>(stream)));
+}
+
+int unirec_linear_ln_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const void* residual,
+                          int64_t ldr, void* out, int64_t ldo, int64_t M, int64_t N, int64_t K, int epilogue,
+                          const float* ln_in_stats, const float* ln_in_c, const float* ln_res_stats,
+                          const float* ln_res_gamma, const float* ln_res_beta, float* stats_out, int ln_parts,
+                          float ln_eps, int64_t ln_hidden, void* stream) {
+    LnFold ln;
+    ln.parts = ln_parts;
+    ln.in_stats = ln_in_stats; ln.in_c = ln_in_c; ln.res_stats = ln_res_stats; ln.res_gamma = ln_res_gamma;
+    ln.res_beta = ln_res_beta; ln.stats_out = stats_out; ln.eps = ln_eps; ln.hidden = ln_hidden;
+    COUNTED(gemm_bf16_ln(A, lda, W, ldw, bias, residual, ldr, out, ldo, M, N, K, epilogue, ln,
+                         static_cast<cudaStream_t>(stream)));
 }
 
 int unirec_layernorm(const void* x, int x_fp32, int64_t ldx, int64_t in_row_mod, const void* residual, int64_t ldres,

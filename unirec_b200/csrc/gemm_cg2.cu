@@ -60,6 +60,19 @@ struct Gemm2Params {
     int table_rows;                 // rows of the token table viewed 2-D: an out-of-bounds coordinate (TMA zero fill)
     int res_period;                 // > 0: the residual tile of rows m.. is read at rows (m % res_period).. of its table
     int reverse;                    // 1: walk the output tiles from the last to the first (experiment, see common.cuh)
+    // ---- LayerNorm folded into the GEMMs around it (unirec_linear_ln_bf16; models/qformer.py:288, :374: h = LN(pre)):
+    // the LayerNorm output is never materialised.  Its PRODUCER (the dense + residual GEMM that writes `pre`) also adds the
+    // row sums / sums of squares of the bf16 values it stores into stats_out; its CONSUMERS read `pre` and these statistics:
+    //   * as the A operand (W already scaled by gamma): y = rstd (pre W'^T) - mu rstd c + b', c[n] = sum_k W'[n,k]
+    //   * as the residual: h = (pre - mu) rstd gamma + beta, evaluated on the residual tile in the epilogue
+    const float* ln_in_stats;       // [M, ln_parts, 2] (sum, sum of squares) partials of the rows of A, or nullptr
+    const float* ln_in_c;           // [N] column sums of the gamma-scaled weight
+    const float* ln_res_stats;      // [M, ln_parts, 2] of the rows of the residual tensor, or nullptr (residual is used as is)
+    const float* ln_res_gamma;      // [N]
+    const float* ln_res_beta;       // [N]
+    float* stats_out;               // [M, 2 N / 256, 2]: one (sum, sum of squares) partial per 128-column half tile, or nullptr
+    int ln_parts;                   // partials per row in ln_in_stats / ln_res_stats (summed in index order: deterministic)
+    float ln_eps, ln_inv_h;         // LayerNorm epsilon, 1 / hidden size
 };
 
 template <int MODE, bool GATHER = false>
@@ -275,6 +288,26 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             mbar_wait(&tmem_full_bar[as], aphase);
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + as * G2_TILE_N + (static_cast<uint32_t>(q * 32) << 16);
+            // LayerNorm folding: this thread's row scalars (rows beyond M: neutral values, their outputs are clipped)
+            const long long grow = static_cast<long long>((p.reverse ? num_tiles - 1 - tile : tile) / p.num_n_blocks) * G2_TILE_M +
+                                   cta_rank * 128 + r;
+            float in_rstd = 1.f, in_shift = 0.f, res_rstd = 1.f, res_shift = 0.f, st1 = 0.f, st2 = 0.f;
+            if (p.ln_in_stats != nullptr && grow < p.M) {
+                const float2* st = reinterpret_cast<const float2*>(p.ln_in_stats) + grow * p.ln_parts;
+                float s1 = 0.f, s2 = 0.f;
+                for (int i = 0; i < p.ln_parts; ++i) { const float2 t = __ldg(st + i); s1 += t.x; s2 += t.y; }
+                const float mu = s1 * p.ln_inv_h;
+                in_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_h - mu * mu, 0.f) + p.ln_eps);
+                in_shift = -mu * in_rstd;
+            }
+            if (MODE == G2_EPI_BIAS_RESIDUAL && p.ln_res_stats != nullptr && grow < p.M) {
+                const float2* st = reinterpret_cast<const float2*>(p.ln_res_stats) + grow * p.ln_parts;
+                float s1 = 0.f, s2 = 0.f;
+                for (int i = 0; i < p.ln_parts; ++i) { const float2 t = __ldg(st + i); s1 += t.x; s2 += t.y; }
+                const float mu = s1 * p.ln_inv_h;
+                res_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_h - mu * mu, 0.f) + p.ln_eps);
+                res_shift = -mu * res_rstd;
+            }
 #pragma unroll 1
             for (int s = 0; s < 2; ++s) {
                 const int slab = half * 2 + s;
@@ -302,7 +335,18 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     float f[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                    if (p.bias != nullptr) {
+                    if (p.ln_in_stats != nullptr) {
+                        // A = pre of a folded LayerNorm: y = rstd acc + (-mu rstd) c[n] + b'[n]
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j * 4));
+                            const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.ln_in_c + n0 + j * 4));
+                            f[4 * j + 0] = fmaf(f[4 * j + 0], in_rstd, fmaf(in_shift, c4.x, b.x));
+                            f[4 * j + 1] = fmaf(f[4 * j + 1], in_rstd, fmaf(in_shift, c4.y, b.y));
+                            f[4 * j + 2] = fmaf(f[4 * j + 2], in_rstd, fmaf(in_shift, c4.z, b.z));
+                            f[4 * j + 3] = fmaf(f[4 * j + 3], in_rstd, fmaf(in_shift, c4.w, b.w));
+                        }
+                    } else if (p.bias != nullptr) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j * 4));
@@ -314,26 +358,59 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                         for (int j = 0; j < 32; j += 2) gelu_erf_x2(f[j], f[j + 1]);
                     }
                     if constexpr (MODE == G2_EPI_BIAS_RESIDUAL) {
+                        if (p.ln_res_stats != nullptr) {
+                            // residual = LayerNorm of the tile just loaded: h = x (rstd gamma) + (beta - mu rstd gamma)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint32_t w[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
+                            for (int j = 0; j < 4; ++j) {
+                                const uint32_t w[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
+                                const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_res_gamma + n0 + 8 * j));
+                                const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.ln_res_gamma + n0 + 8 * j) + 1);
+                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.ln_res_beta + n0 + 8 * j));
+                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.ln_res_beta + n0 + 8 * j) + 1);
+                                const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                f[8 * j + 2 * t] += bf16_lo(w[t]);
-                                f[8 * j + 2 * t + 1] += bf16_hi(w[t]);
+                                for (int t = 0; t < 4; ++t) {
+                                    f[8 * j + 2 * t] += fmaf(bf16_lo(w[t]), res_rstd * g[2 * t], fmaf(res_shift, g[2 * t], bb[2 * t]));
+                                    f[8 * j + 2 * t + 1] +=
+                                        fmaf(bf16_hi(w[t]), res_rstd * g[2 * t + 1], fmaf(res_shift, g[2 * t + 1], bb[2 * t + 1]));
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const uint32_t w[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) {
+                                    f[8 * j + 2 * t] += bf16_lo(w[t]);
+                                    f[8 * j + 2 * t + 1] += bf16_hi(w[t]);
+                                }
                             }
                         }
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        *reinterpret_cast<uint4*>(slab_smem + swz128(r, c * 4 + j)) =
-                            make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                                       pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 o = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                                                   pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+                        *reinterpret_cast<uint4*>(slab_smem + swz128(r, c * 4 + j)) = o;
+                        if (p.stats_out != nullptr) {
+                            // statistics of the values as stored (bf16): what the consumers of this tensor will read
+                            const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const float a = bf16_lo(w[t]), b = bf16_hi(w[t]);
+                                st1 += a + b;
+                                st2 = fmaf(a, a, fmaf(b, b, st2));
+                            }
+                        }
+                    }
                 }
                 fence_proxy_async_smem();        // generic-proxy smem writes -> visible to the TMA store
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&slab_written_bar[slab]);
             }
+            if (p.stats_out != nullptr && grow < p.M)     // this thread's 128 columns of the row: its own slot, no atomics
+                reinterpret_cast<float2*>(p.stats_out)[(grow * p.num_n_blocks + n_blk) * 2 + half] = make_float2(st1, st2);
         }
     }
 
@@ -385,7 +462,7 @@ bool gemm_cg2_supported(long long M, long long N, long long K, int out_fp32, int
 
 int gemm_bf16_cg2(const void* A, long long lda, const void* W, long long ldw, const float* bias, const void* residual,
                   long long ldr, void* out, long long ldo, long long M, long long N, long long K, int epilogue,
-                  int max_ctas, cudaStream_t stream) {
+                  int max_ctas, cudaStream_t stream, const LnFold* ln) {
     Gemm2Params p;
     p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
     p.bias = bias;
@@ -393,6 +470,15 @@ int gemm_bf16_cg2(const void* A, long long lda, const void* W, long long ldw, co
     p.num_n_blocks = static_cast<int>(N / G2_TILE_N);
     p.gather_ids = nullptr; p.gather_len = nullptr; p.slots_per_user = 0; p.table_rows = 0; p.res_period = 0;
     p.reverse = 0;      // GEMMs walk forward; reversing them as well (alternating directions) measured slower, see common.cuh
+    p.ln_in_stats = ln != nullptr ? ln->in_stats : nullptr;
+    p.ln_in_c = ln != nullptr ? ln->in_c : nullptr;
+    p.ln_res_stats = ln != nullptr ? ln->res_stats : nullptr;
+    p.ln_res_gamma = ln != nullptr ? ln->res_gamma : nullptr;
+    p.ln_res_beta = ln != nullptr ? ln->res_beta : nullptr;
+    p.stats_out = ln != nullptr ? ln->stats_out : nullptr;
+    p.ln_parts = ln != nullptr ? ln->parts : 0;
+    p.ln_eps = ln != nullptr ? ln->eps : 0.f;
+    p.ln_inv_h = ln != nullptr ? 1.0f / static_cast<float>(ln->hidden) : 0.f;
     CUtensorMap ta, tb, to, tr;
     int rc = make_tmap_bf16_2d(&ta, A, M, K, lda, 128);
     if (rc != UNIREC_OK) return rc;
@@ -446,6 +532,8 @@ int gemm_bf16_cg2_gather(const void* table, long long ld_table, long long table_
     p.gather_ids = ids; p.gather_len = lengths; p.slots_per_user = static_cast<int>(slots_per_user);
     p.table_rows = static_cast<int>(table_rows); p.res_period = static_cast<int>(period);
     p.reverse = 0;
+    p.ln_in_stats = p.ln_in_c = p.ln_res_stats = p.ln_res_gamma = p.ln_res_beta = nullptr;
+    p.stats_out = nullptr; p.ln_parts = 0; p.ln_eps = 0.f; p.ln_inv_h = 0.f;
     CUtensorMap ta, tb, to, tr, tp;
     int rc = make_tmap_bf16_2d(&ta, table, table_rows, K, ld_table, 32);
     if (rc != UNIREC_OK) return rc;

@@ -277,7 +277,40 @@ bool gemm_cg2_supported(long long M, long long N, long long K, int out_fp32, int
                         long long ldw, long long ldo, long long ldr, int epilogue);
 int gemm_bf16_cg2(const void* A, long long lda, const void* W, long long ldw, const float* bias, const void* residual,
                   long long ldr, void* out, long long ldo, long long M, long long N, long long K, int epilogue,
-                  int max_ctas, cudaStream_t stream);
+                  int max_ctas, cudaStream_t stream, const LnFold* ln = nullptr);
+
+// out = epilogue(LN?(A) W^T + bias [+ LN?(residual)]) with the LayerNorms folded in (see LnFold); CTA-pair kernel only.
+int gemm_bf16_ln(const void* A, long long lda, const void* W, long long ldw, const float* bias, const void* residual,
+                 long long ldr, void* out, long long ldo, long long M, long long N, long long K, int epilogue,
+                 const LnFold& ln, cudaStream_t stream) {
+    if (A == nullptr || W == nullptr || out == nullptr || bias == nullptr || M <= 0 || N <= 0 || K <= 0) {
+        set_last_error("linear_ln: null pointer or empty shape (M=%lld N=%lld K=%lld; bias is required)", M, N, K);
+        return UNIREC_ERR_BAD_ARG;
+    }
+    if (!gemm_cg2_supported(M, N, K, 0, 0, lda, ldw, ldo, ldr, epilogue) || (reinterpret_cast<uintptr_t>(A) & 15) ||
+        (reinterpret_cast<uintptr_t>(W) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
+        (reinterpret_cast<uintptr_t>(bias) & 15)) {
+        set_last_error("linear_ln: needs bf16 output, N%%256==0, K%%64==0, 16-byte aligned rows (M=%lld N=%lld K=%lld)", M, N, K);
+        return UNIREC_ERR_BAD_ARG;
+    }
+    if (epilogue == EPI_BIAS_RESIDUAL && (residual == nullptr || (reinterpret_cast<uintptr_t>(residual) & 15))) {
+        set_last_error("linear_ln: residual epilogue needs a 16-byte aligned bf16 residual");
+        return UNIREC_ERR_BAD_ARG;
+    }
+    if ((ln.in_stats != nullptr && (ln.in_c == nullptr || (reinterpret_cast<uintptr_t>(ln.in_c) & 15) ||
+                                    (reinterpret_cast<uintptr_t>(ln.in_stats) & 7))) ||
+        (ln.res_stats != nullptr && (epilogue != EPI_BIAS_RESIDUAL || ln.res_gamma == nullptr || ln.res_beta == nullptr ||
+                                     (reinterpret_cast<uintptr_t>(ln.res_gamma) & 15) ||
+                                     (reinterpret_cast<uintptr_t>(ln.res_beta) & 15) ||
+                                     (reinterpret_cast<uintptr_t>(ln.res_stats) & 7))) ||
+        (ln.stats_out != nullptr && (reinterpret_cast<uintptr_t>(ln.stats_out) & 7)) || ln.hidden <= 0 ||
+        ((ln.in_stats != nullptr || ln.res_stats != nullptr) && (ln.parts <= 0 || ln.parts > 256))) {
+        set_last_error("linear_ln: inconsistent LayerNorm-folding arguments (in_stats needs in_c; res_stats needs the residual "
+                       "epilogue, gamma and beta; vectors 16-byte aligned; 1 <= ln_parts <= 256)");
+        return UNIREC_ERR_BAD_ARG;
+    }
+    return gemm_bf16_cg2(A, lda, W, ldw, bias, residual, ldr, out, ldo, M, N, K, epilogue, 0, stream, &ln);
+}
 
 int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias, const void* residual,
               long long ldr, int res_row_mod, void* out, long long ldo, int out_fp32, long long M, long long N,

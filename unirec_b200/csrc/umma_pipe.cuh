@@ -150,6 +150,19 @@ UNIREC_DEVICE void pipe_epilogue_release(Pipe& pipe, uint32_t iter) {
     mbar_arrive(&pipe.tmem_empty_bar[iter & 1u]);
 }
 
+// LayerNorm folded into the GEMMs around it (gemm_cg2.cu, unirec_linear_ln_bf16): device pointers, all optional
+struct LnFold {
+    const float* in_stats;    // [M, parts, 2] row (sum, sum of squares) partials of the tensor A was read from -> A is LayerNorm-ed on the fly
+    const float* in_c;        // [N] column sums of the gamma-scaled weight (required with in_stats)
+    const float* res_stats;   // [M, parts, 2] of the residual tensor -> the residual is LayerNorm-ed on the fly
+    const float* res_gamma;   // [N]
+    const float* res_beta;    // [N]
+    float* stats_out;         // [M, 2 N / 256, 2]: (sum, sum of squares) of each 128-column piece of the bf16 output rows
+    int parts;                // partials per row of in_stats / res_stats (= 2 hidden / 256 when a call of this kernel wrote them)
+    float eps;
+    long long hidden;         // width the statistics were taken over
+};
+
 // Host: 2-D bf16 row-major tensor map, box [box_rows, 64 cols], 128-byte swizzle (gemm_tcgen05.cu).
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows);
 int make_tmap_bf16_3d(CUtensorMap* map, const void* base, long long batch, long long rows, long long cols, long long ld,

@@ -122,6 +122,75 @@ def linear(a: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     return out
 
 
+def linear_ln(a: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, *, epilogue: int = EPI_BIAS,
+              residual: Optional[torch.Tensor] = None, ln_in: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+              ln_res: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None,
+              stats_out: Optional[torch.Tensor] = None, eps: float = 1e-12, hidden: Optional[int] = None) -> torch.Tensor:
+    """nn.Linear with the LayerNorms around it folded in (C ABI unirec_linear_ln_bf16; bf16 in / out, N % 256 == 0):
+      ln_in  = (stats fp32 [M, P, 2], c fp32 [N]): `a` is the INPUT of a LayerNorm (never materialised); `weight` / `bias`
+               are the gamma-scaled weight W' = W o gamma and b' = b + W beta, c = row sums of W' (fold_layernorm_weights);
+      ln_res = (stats fp32 [M, P, 2], gamma fp32 [N], beta fp32 [N]): `residual` is the input of a LayerNorm and enters
+               normalised;
+      stats_out fp32 [M, 2 N / 256, 2] (see `ln_stats_buffer`): receives, per row, the (sum, sum of squares) of every
+               128-column piece of the bf16 output - the `stats` of the calls that consume this output."""
+    _req(a, torch.bfloat16, "linear_ln.a")
+    _req(weight, torch.bfloat16, "linear_ln.weight")
+    _req(bias, torch.float32, "linear_ln.bias")
+    M, K, lda = _rows2d(a, "linear_ln.a")
+    N, K2 = weight.shape
+    if K2 != K:
+        raise RuntimeError(f"linear_ln: inner dims differ ({K} vs {K2})")
+    out = torch.empty(*a.shape[:-1], N, device=a.device, dtype=torch.bfloat16)
+    ldr = 0
+    if residual is not None:
+        _req(residual, torch.bfloat16, "linear_ln.residual")
+        _, _, ldr = _rows2d(residual, "linear_ln.residual")
+    parts = 0
+    for t, n in ((ln_in, "ln_in"), (ln_res, "ln_res")):
+        if t is not None:
+            for x in t:
+                _req(x, torch.float32, f"linear_ln.{n}")
+            st = t[0]
+            if st.dim() != 3 or st.shape[0] != M or st.shape[2] != 2 or not st.is_contiguous():
+                raise RuntimeError(f"linear_ln.{n}: statistics must be contiguous fp32 [M, parts, 2]")
+            if parts and st.shape[1] != parts:
+                raise RuntimeError("linear_ln: ln_in and ln_res statistics must have the same number of partials")
+            parts = int(st.shape[1])
+    if stats_out is not None:
+        _req(stats_out, torch.float32, "linear_ln.stats_out")
+        if tuple(stats_out.shape) != (M, 2 * (N // 256), 2) or not stats_out.is_contiguous():
+            raise RuntimeError("linear_ln.stats_out must be contiguous fp32 [M, 2 N / 256, 2]")
+    hid = int(hidden) if hidden is not None else (K if ln_in is not None else N)
+    with _Timed("gemm", 2.0 * M * N * K, f"{M}x{N}x{K}"):
+        rc = _lib.load().unirec_linear_ln_bf16(
+            a.data_ptr(), lda, weight.data_ptr(), weight.stride(0), bias.data_ptr(), _ptr(residual), ldr, out.data_ptr(),
+            out.stride(-2) if out.dim() >= 2 else N, M, N, K, epilogue,
+            _ptr(ln_in[0]) if ln_in is not None else None, _ptr(ln_in[1]) if ln_in is not None else None,
+            _ptr(ln_res[0]) if ln_res is not None else None, _ptr(ln_res[1]) if ln_res is not None else None,
+            _ptr(ln_res[2]) if ln_res is not None else None, _ptr(stats_out), parts, float(eps), hid, _stream())
+    _lib.check(rc, "unirec_linear_ln_bf16")
+    return out
+
+
+def ln_stats_buffer(rows: int, width: int, device, count: Optional[int] = None) -> torch.Tensor:
+    """Uninitialised statistics buffer(s) for `linear_ln(..., stats_out=)` of a GEMM with `width` output columns:
+    fp32 [rows, 2 width / 256, 2], or [count, rows, 2 width / 256, 2]."""
+    shape = (rows, 2 * (width // 256), 2)
+    return torch.empty(shape if count is None else (count,) + shape, device=device, dtype=torch.float32)
+
+
+def fold_layernorm_weights(weight: torch.Tensor, bias: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor):
+    """(W' bf16 [N, K], b' fp32 [N], c fp32 [N]) of a Linear that consumes LayerNorm(x; gamma, beta):
+    Linear(LN(x)) = rstd (x W'^T) - mu rstd c + b' with W' = W o gamma (rounded to bf16, what the tensor cores multiply),
+    c = row sums of that rounded W' (so that the mean term cancels exactly what was accumulated), b' = b + W beta."""
+    w = weight.detach().float()
+    wp = (w * gamma.detach().float()[None, :]).to(torch.bfloat16).contiguous()
+    b = w @ beta.detach().float()
+    if bias is not None:
+        b = b + bias.detach().float()
+    return wp, b.contiguous(), wp.float().sum(dim=1).contiguous()
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *,
               residual: Optional[torch.Tensor] = None, rows: Optional[int] = None, in_row_mod: int = 0,
               out_dtype: torch.dtype = torch.bfloat16, out: Optional[torch.Tensor] = None) -> torch.Tensor:
