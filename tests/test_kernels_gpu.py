@@ -279,6 +279,22 @@ def test_attention(nq, nk, heads):
         torch.testing.assert_close(out[1].float(), uniform, rtol=2e-2, atol=2e-2)
 
 
+def test_attention_two_group_kernel_in_subprocess():
+    """attention_pp.cu (two softmax groups on alternate key tiles; optional, UNIREC_ATTENTION_PP=1 is read once per process):
+    the long-key attention tests of this file in a child process that has the kernel switched on."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, UNIREC_ATTENTION_PP="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_kernels_gpu.py"), "-m", "gpu", "-q",
+                        "-x", "-p", "no:cacheprovider", "--timeout", "120", "-k",
+                        "test_attention and not two_group and not torch_ops"], env=env, cwd=root, capture_output=True,
+                       text=True, timeout=600)
+    print(r.stdout[-2000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_attention_long_keys_growing_scores_and_strided_kv():
     """tcgen05 path (nk > 64): K/V as column slices of a wide [rows, 8*H] buffer (the user model's kv_all layout),
     many work items per CTA, and scores that grow tile after tile so that the lazily raised running max and the

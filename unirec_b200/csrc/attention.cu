@@ -299,12 +299,30 @@ static int attention_ctas_per_sm(K kern, int threads, size_t smem) {
     return n;
 }
 
+constexpr int ATTENTION_PP_DEFAULT = 0;
 // tcgen05 kernel for long key sequences (attention_tc.cu)
 bool attention_tc_supported(long long num_heads, long long nq, long long nk, long long head_dim, long long ldk,
                             long long ldv, long long kv_batch_rows);
 int attention_tc(const void* q, long long ldq, long long q_batch_rows, const void* k, long long ldk, const void* v,
                  long long ldv, long long kv_batch_rows, const float* key_mask, void* out, long long ldo, long long batch,
                  long long num_heads, long long nq, long long nk, float scale, cudaStream_t stream);
+
+// two softmax groups on alternate key tiles (attention_pp.cu), more than 128 keys
+bool attention_pp_supported(long long num_heads, long long nq, long long nk, long long head_dim, long long ldk,
+                            long long ldv, long long kv_batch_rows);
+int attention_pp(const void* q, long long ldq, long long q_batch_rows, const void* k, long long ldk, const void* v,
+                 long long ldv, long long kv_batch_rows, const float* key_mask, void* out, long long ldo, long long batch,
+                 long long num_heads, long long nq, long long nk, float scale, cudaStream_t stream);
+
+static bool attention_pp_enabled() {
+    // UNIREC_ATTENTION_PP=1 / 0: long key sequences on the two-group kernel / on attention_tc_kernel (A/B measurements)
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("UNIREC_ATTENTION_PP");
+        on = e != nullptr ? (e[0] != '0' ? 1 : 0) : ATTENTION_PP_DEFAULT;
+    }
+    return on == 1;
+}
 
 static bool attention_tc_enabled() {
     // UNIREC_ATTENTION_TC=0 forces the mma.sync kernel for every shape (A/B measurements and tests)
@@ -336,6 +354,10 @@ int attention(const void* q, long long ldq, long long q_batch_rows, const void* 
         set_last_error("attention: dropout probability must be < 1");
         return UNIREC_ERR_BAD_ARG;
     }
+    if (drop_thr16 == 0 && attention_tc_enabled() && attention_pp_enabled() &&
+        attention_pp_supported(num_heads, nq, nk, head_dim, ldk, ldv, kv_batch_rows))
+        return attention_pp(q, ldq, q_batch_rows, k, ldk, v, ldv, kv_batch_rows, key_mask, out, ldo, batch, num_heads, nq,
+                            nk, scale, stream);
     if (drop_thr16 == 0 && attention_tc_enabled() && attention_tc_supported(num_heads, nq, nk, head_dim, ldk, ldv, kv_batch_rows))
         return attention_tc(q, ldq, q_batch_rows, k, ldk, v, ldv, kv_batch_rows, key_mask, out, ldo, batch, num_heads, nq,
                             nk, scale, stream);
