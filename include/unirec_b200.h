@@ -59,15 +59,18 @@ int unirec_linear_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, c
 
 /* nn.Linear with the LayerNorms around it folded in (models/qformer.py:285-289, 371-375: h = LayerNorm(dropout(dense(x)) + input);
  * the LayerNorm output h is never written).  CTA-pair kernel: bf16 output, N % 256 == 0, K % 64 == 0, bias required.
- *   stats_out    fp32 [M, 2 N / 256, 2]: the call WRITES, per row, one (sum, sum of squares) partial of the bf16 values it
- *                stores per 128-column piece (no atomics: consumers add the partials in index order, so results do not
- *                depend on the launch geometry) - this GEMM is the producer of a LayerNorm input `pre`;
+ *   stats_out    fp32 [M, unirec_linear_ln_stats_parts(N), 2]: the call WRITES, per row, one (sum, sum of squares) partial of
+ *                the bf16 values it stores per column piece of an epilogue warp (no atomics: consumers add the partials in
+ *                index order, so results do not depend on the launch geometry) - this GEMM is the producer of a LayerNorm
+ *                input `pre`;
  *   ln_in_stats  fp32 [M, ln_parts, 2] + ln_in_c fp32 [N]: A is such a `pre`; W must already be scaled by the LayerNorm's
  *                gamma, bias = b + W beta, ln_in_c[n] = sum_k W'[n, k]: out = rstd (A W'^T) - mu rstd c + bias;
  *   ln_res_stats fp32 [M, ln_parts, 2] + ln_res_gamma / ln_res_beta fp32 [N] (epilogue UNIREC_EPI_BIAS_RESIDUAL): the
  *                residual tensor is such a `pre` and enters as LayerNorm(residual) = (x - mu) rstd gamma + beta.
  * Any of the three groups may be NULL (plain behaviour of unirec_linear_bf16).  ln_hidden = width the statistics cover,
- * ln_parts = partials per row in ln_in_stats / ln_res_stats (2 ln_hidden / 256 when this entry point wrote them). */
+ * ln_parts = partials per row in ln_in_stats / ln_res_stats (unirec_linear_ln_stats_parts(ln_hidden) when this entry point
+ * wrote them). */
+int64_t unirec_linear_ln_stats_parts(int64_t N);
 int unirec_linear_ln_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const void* residual,
                           int64_t ldr, void* out, int64_t ldo, int64_t M, int64_t N, int64_t K, int epilogue,
                           const float* ln_in_stats, const float* ln_in_c, const float* ln_res_stats,

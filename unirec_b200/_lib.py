@@ -82,6 +82,7 @@ _SIGNATURES = {
     "unirec_linear_ln_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                       c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_int, c_float, c_int64, c_void_p]),
+    "unirec_linear_ln_stats_parts": (c_int64, [c_int64]),
     "unirec_kv_attention_workspace_bytes": (c_int64, [c_int64, c_int64]),
     "unirec_kv_attention_fused": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p,
                                           c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,

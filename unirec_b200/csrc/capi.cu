@@ -11,6 +11,7 @@ const char* get_last_error();
 int gemm_bf16_ln(const void* A, long long lda, const void* W, long long ldw, const float* bias, const void* residual,
                  long long ldr, void* out, long long ldo, long long M, long long N, long long K, int epilogue,
                  const LnFold& ln, cudaStream_t stream);
+long long gemm_cg2_stats_parts(long long N);
 int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias, const void* residual,
               long long ldr, int res_row_mod, void* out, long long ldo, int out_fp32, long long M, long long N,
               long long K, int epilogue, int block_n, int max_ctas, cudaStream_t stream);
@@ -120,6 +121,8 @@ int unirec_linear_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, c
     COUNTED(gemm_bf16(A, lda, W, ldw, bias, residual, ldr, static_cast<int>(res_row_mod), out, ldo, out_fp32, M, N, K,
                       epilogue, block_n, max_ctas, static_cast<cudaStream_t>(stream)));
 }
+
+int64_t unirec_linear_ln_stats_parts(int64_t N) { return gemm_cg2_stats_parts(N); }
 
 int unirec_linear_ln_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const void* residual,
                           int64_t ldr, void* out, int64_t ldo, int64_t M, int64_t N, int64_t K, int epilogue,

@@ -423,6 +423,10 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     }
 }
 
+// (sum, sum of squares) partials per row that a LayerNorm-producer call writes for N output columns: one per column half of
+// every 256-column tile (unirec_linear_ln_stats_parts)
+long long gemm_cg2_stats_parts(long long N) { return 2 * (N / G2_TILE_N); }
+
 template <int MODE, bool GATHER = false>
 static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
                         const Gemm2Params& p, int max_ctas, cudaStream_t stream, const CUtensorMap* tpad = nullptr) {

@@ -131,8 +131,8 @@ def linear_ln(a: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, *, epil
                are the gamma-scaled weight W' = W o gamma and b' = b + W beta, c = row sums of W' (fold_layernorm_weights);
       ln_res = (stats fp32 [M, P, 2], gamma fp32 [N], beta fp32 [N]): `residual` is the input of a LayerNorm and enters
                normalised;
-      stats_out fp32 [M, 2 N / 256, 2] (see `ln_stats_buffer`): receives, per row, the (sum, sum of squares) of every
-               128-column piece of the bf16 output - the `stats` of the calls that consume this output."""
+      stats_out fp32 [M, parts(N), 2] (see `ln_stats_buffer`): receives, per row, the (sum, sum of squares) of every
+               column piece of the bf16 output - the `stats` of the calls that consume this output."""
     _req(a, torch.bfloat16, "linear_ln.a")
     _req(weight, torch.bfloat16, "linear_ln.weight")
     _req(bias, torch.float32, "linear_ln.bias")
@@ -158,8 +158,8 @@ def linear_ln(a: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, *, epil
             parts = int(st.shape[1])
     if stats_out is not None:
         _req(stats_out, torch.float32, "linear_ln.stats_out")
-        if tuple(stats_out.shape) != (M, 2 * (N // 256), 2) or not stats_out.is_contiguous():
-            raise RuntimeError("linear_ln.stats_out must be contiguous fp32 [M, 2 N / 256, 2]")
+        if tuple(stats_out.shape) != (M, ln_stats_parts(N), 2) or not stats_out.is_contiguous():
+            raise RuntimeError("linear_ln.stats_out must be contiguous fp32 [M, ln_stats_parts(N), 2]")
     hid = int(hidden) if hidden is not None else (K if ln_in is not None else N)
     with _Timed("gemm", 2.0 * M * N * K, f"{M}x{N}x{K}"):
         rc = _lib.load().unirec_linear_ln_bf16(
@@ -172,10 +172,15 @@ def linear_ln(a: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, *, epil
     return out
 
 
+def ln_stats_parts(width: int) -> int:
+    """Partials per row that `linear_ln(..., stats_out=)` writes for `width` output columns (one per epilogue warp part)."""
+    return int(_lib.load().unirec_linear_ln_stats_parts(int(width)))
+
+
 def ln_stats_buffer(rows: int, width: int, device, count: Optional[int] = None) -> torch.Tensor:
     """Uninitialised statistics buffer(s) for `linear_ln(..., stats_out=)` of a GEMM with `width` output columns:
-    fp32 [rows, 2 width / 256, 2], or [count, rows, 2 width / 256, 2]."""
-    shape = (rows, 2 * (width // 256), 2)
+    fp32 [rows, parts, 2], or [count, rows, parts, 2], parts = ln_stats_parts(width)."""
+    shape = (rows, ln_stats_parts(width), 2)
     return torch.empty(shape if count is None else (count,) + shape, device=device, dtype=torch.float32)
 
 
