@@ -33,6 +33,8 @@
 #include "common.cuh"
 #include "umma_pipe.cuh"
 
+#include <cstdlib>
+
 namespace unirec {
 
 constexpr int AT_KT = 128;                       // keys per tile
@@ -45,6 +47,7 @@ constexpr int AT_SMEM_BYTES = 2 * AT_TILE /*Q2 x2*/ + AT_KSTAGES * AT_TILE /*K|P
 static_assert(AT_SMEM_BYTES <= 232448, "shared memory budget exceeded");
 constexpr float AT_MASKED = -1.2676506002282294e30f;   // -2^100: stands in for finfo.min, exact in bf16 (row-max exchange)
 constexpr float AT_LAZY = 8.0f;                  // raise the running max only when exceeded by 2^8
+constexpr bool AT_PTMEM_DEFAULT = true;         // P through tensor memory (see attention_tc_kernel<PTMEM>)
 
 struct AttnTcParams {
     const __nv_bfloat16* q; long long ldq; long long q_batch_rows;
@@ -70,10 +73,27 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_bmn(uint32_t m, uint32_t 
     return umma_idesc_bf16(m, n) | (1u << 16);   // B operand MN-major
 }
 
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (M = 128 rows = TMEM lanes, K along the columns, two bf16 per 32-bit
+// column) is read from tensor memory - P goes from the softmax registers to the second MMA without touching shared memory
+UNIREC_DEVICE void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 UNIREC_DEVICE void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// PTMEM = true: P(g) is written to tensor memory (columns 384..511: two 64-column buffers of packed bf16 pairs) and PV(g)
+// takes it from there as its A operand; the K slot is released as soon as S(g) has been accumulated.  PTMEM = false: P(g) is
+// written in place over K(g) in shared memory (the round-1 kernel).
+template <bool PTMEM>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                     const AttnTcParams p) {
@@ -179,6 +199,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
                                  umma_smem_desc_sw128(b_addr + off), idesc_s, ks != 0 ? 1u : 0u);
                 }
                 umma_commit(&s_full[slot]);
+                if constexpr (PTMEM) umma_commit(&k_empty[kslot]);      // K(g) is dead once S(g) has been accumulated
                 if (t == T - 1) umma_commit(&q_free[it & 1]);
             }
             __syncwarp();
@@ -198,11 +219,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
                 for (int ks = 0; ks < 8; ++ks) {
                     const uint32_t a_off = (ks >> 2) * AT_SLAB + (ks & 3) * 32;     // 16 keys = 32 B along K
                     const uint32_t b_off = ks * 16 * 128;                            // 16 key rows of 128 B
-                    umma_bf16_ss(tmem_o, umma_smem_desc_sw128(a_addr + a_off),
-                                 umma_smem_desc_mn_sw128(b_addr + b_off, AT_SLAB), idesc_pv, (t | ks) != 0 ? 1u : 0u);
+                    if constexpr (PTMEM)
+                        umma_bf16_ts(tmem_o, tmem_base + 384 + slot * 64 + ks * 8,   // 16 keys = 8 packed columns
+                                     umma_smem_desc_mn_sw128(b_addr + b_off, AT_SLAB), idesc_pv, (t | ks) != 0 ? 1u : 0u);
+                    else
+                        umma_bf16_ss(tmem_o, umma_smem_desc_sw128(a_addr + a_off),
+                                     umma_smem_desc_mn_sw128(b_addr + b_off, AT_SLAB), idesc_pv, (t | ks) != 0 ? 1u : 0u);
                 }
                 umma_commit(&v_empty[slot]);
-                umma_commit(&k_empty[g % AT_KSTAGES]);
+                if constexpr (!PTMEM) umma_commit(&k_empty[g % AT_KSTAGES]);
                 umma_commit(pv_done);
             }
             __syncwarp();
@@ -255,7 +280,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
         }
         float m_used = -INFINITY, l_part = 0.f;
         // key_mask values of keys (64*hf + lane) and (+32) of tile (it_, t_), fetched one tile AHEAD (ncu: issued at the
-        // tile's start, the load's latency sat on the critical path of every tile); 1.0 = attend
+        // tile's start, the load's latency sat on the critical path of every tile); 1.0 = attend.  (Keeping the mask row
+        // pointers per item instead of this per-tile division measured 4-6 % SLOWER, profiles/r02_s_*: left as it is.)
         auto mask_fetch = [&](int it_, int t_, float& a, float& bq) {
             a = 1.0f; bq = 1.0f;
             if (p.key_mask == nullptr) return;
@@ -360,29 +386,44 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
             }
             // ---- p = 2^(x - m_used) -> bf16 -> P tile in shared memory (slab hf = this thread's 64 keys); row sum
             const float neg_m = -m_used;
+            const unsigned long long xs2 = pack_f32x2(xs, xs), nm2 = pack_f32x2(neg_m, neg_m);
             uint8_t* prow = sK + (g % AT_KSTAGES) * AT_TILE + hf * AT_SLAB;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                float psum = 0.f;
+                // two elements per FMA-pipe instruction (fma.rn.f32x2 / add.rn.f32x2): the exponent x * scale - m and the row
+                // sum cost 32 + 32 instead of 64 + 64 issue slots per 64 keys next to the 64 MUFU.EX2
+                unsigned long long psum2 = pack_f32x2(0.f, 0.f);
                 uint32_t pk[16];
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
-                    const float p0 = ex2_approx(fmaf(__uint_as_float(sv[c][j]), xs, neg_m));
-                    const float p1 = ex2_approx(fmaf(__uint_as_float(sv[c][j + 1]), xs, neg_m));
-                    psum += p0 + p1;
+                    float x0, x1;
+                    unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(sv[c][j]), __uint_as_float(sv[c][j + 1])), xs2, nm2), x0, x1);
+                    const float p0 = ex2_approx(x0);
+                    const float p1 = ex2_approx(x1);
+                    psum2 = add_f32x2(psum2, pack_f32x2(p0, p1));
                     pk[j >> 1] = pack_bf16(p0, p1);
                 }
-                l_part += psum;
+                {
+                    float s0, s1;
+                    unpack_f32x2(psum2, s0, s1);
+                    l_part += s0 + s1;
+                }
+                if constexpr (PTMEM) {
+                    // this thread's keys 64 hf + 32 c .. + 31 of the row: 16 packed columns of the P buffer
+                    tmem_st_32x16(tmem_base + 384 + slot * 64 + hf * 32 + c * 16 + lane_field, pk);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    *reinterpret_cast<uint4*>(prow + swz128(r, c * 4 + j)) =
-                        make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4*>(prow + swz128(r, c * 4 + j)) =
+                            make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                }
             }
+            if constexpr (PTMEM) tmem_st_wait();
             // every phase of pv_done is consumed in order, and phase g-1 before p_ready(g) is signalled: PV(g) cannot be
             // issued earlier, so the barrier is never more than one phase ahead of this thread's parity bookkeeping
             if (!pv_seen) mbar_wait(pv_done, (g - 1) & 1);
-            tc_fence_before();               // orders the O rescale (tcgen05.st) before the issuer's next MMA
-            fence_proxy_async_smem();        // P writes -> visible to the tensor core
+            tc_fence_before();               // orders the O rescale / the P stores (tcgen05.st) before the issuer's next MMA
+            if constexpr (!PTMEM) fence_proxy_async_smem();        // P writes in shared memory -> visible to the tensor core
             __syncwarp();
             if (lane == 0) mbar_arrive(p_ready);
 
@@ -458,9 +499,15 @@ int attention_tc(const void* q, long long ldq, long long q_batch_rows, const voi
     if (rc != UNIREC_OK) return rc;
     rc = make_tmap_bf16_2d(&tv, v, batch * kv_batch_rows, num_heads * 64, ldv, AT_KT);
     if (rc != UNIREC_OK) return rc;
+    // UNIREC_ATTENTION_PTMEM = 1 / 0: P as a tensor-memory operand of the second MMA / P in shared memory over the K tile
+    static const bool ptmem = [] {
+        const char* e = getenv("UNIREC_ATTENTION_PTMEM");
+        return e != nullptr ? e[0] != '0' : AT_PTMEM_DEFAULT;
+    }();
+    auto kern = ptmem ? attention_tc_kernel<true> : attention_tc_kernel<false>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
         if (e != cudaSuccess) {
             set_last_error("attention (tcgen05): cudaFuncSetAttribute(%d): %s", AT_SMEM_BYTES, cudaGetErrorString(e));
             return UNIREC_ERR_CUDA;
@@ -469,7 +516,7 @@ int attention_tc(const void* q, long long ldq, long long q_batch_rows, const voi
     }
     int grid = num_sms() > 0 ? num_sms() : 148;
     if (grid > p.num_items) grid = p.num_items;
-    attention_tc_kernel<<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tk, tv, p);
+    kern<<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tk, tv, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_last_error("attention (tcgen05) launch: %s", cudaGetErrorString(e));

@@ -85,6 +85,11 @@ UNIREC_DEVICE unsigned long long fma_f32x2(unsigned long long a, unsigned long l
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
+UNIREC_DEVICE unsigned long long add_f32x2(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 UNIREC_DEVICE unsigned long long mul_f32x2(unsigned long long a, unsigned long long b) {
     unsigned long long d;
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
