@@ -41,6 +41,28 @@ def case_gemm_cg2():
     close(ops.linear(a, w, b, epilogue=ops.EPI_BIAS_GELU), torch.nn.functional.gelu(ref), 0.05, "cg2 gelu")
 
 
+def case_gemm_ln():
+    # LayerNorm folded into the GEMMs (unirec_linear_ln_bf16): producer statistics, both consumer forms, ragged M
+    M, H, I = 300, 256, 512
+    eps = 1e-12
+    x, w2, b2 = rnd(M, I), rnd(H, I, scale=0.04), rnd(H, dtype=torch.float32)
+    res = rnd(M, H)
+    gamma = 1.0 + rnd(H, scale=0.1, dtype=torch.float32)
+    beta = rnd(H, scale=0.1, dtype=torch.float32)
+    st = ops.ln_stats_buffer(M, H, dev)
+    pre = ops.linear_ln(x, w2, b2, epilogue=ops.EPI_BIAS_RESIDUAL, residual=res, stats_out=st, eps=eps, hidden=H)
+    close(pre, x.float() @ w2.float().t() + b2 + res.float(), 0.06, "ln producer")
+    h = torch.nn.functional.layer_norm(pre.float(), (H,), gamma, beta, eps)
+    w1, b1 = rnd(I, H, scale=0.04, dtype=torch.float32), rnd(I, dtype=torch.float32)
+    wf, bf_, cf = ops.fold_layernorm_weights(w1, b1, gamma, beta)
+    y = ops.linear_ln(pre, wf, bf_, epilogue=ops.EPI_BIAS_GELU, ln_in=(st, cf), eps=eps, hidden=H)
+    close(y, torch.nn.functional.gelu(h @ w1.t() + b1), 0.06, "ln consumer (A operand, gelu)")
+    st2 = ops.ln_stats_buffer(M, H, dev)
+    pre2 = ops.linear_ln(x, w2, b2, epilogue=ops.EPI_BIAS_RESIDUAL, residual=pre, ln_res=(st, gamma, beta), stats_out=st2,
+                         eps=eps, hidden=H)
+    close(pre2, x.float() @ w2.float().t() + b2 + h, 0.06, "ln consumer (residual)")
+
+
 def case_gemm_1cta():
     M, N, K = 200, 384, 192
     a, w, b = rnd(M, K), rnd(N, K, scale=0.06), rnd(N, dtype=torch.float32)

@@ -414,6 +414,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 // ---- merge the two groups' partial results of the item: thread = (row, 16 of its head's 64 columns)
                 mbar_wait(item_done, par);
                 tc_fence_after();
+                pp_bar_sync(9, 512);         // both groups have published (m, l): a direct ordering next to the transitive one
                 const float m0 = sM[(par * 2 + 0) * 128 + r], m1 = sM[(par * 2 + 1) * 128 + r];
                 const float l0 = sL[((par * 2 + 0) * 2 + 0) * 128 + r] + sL[((par * 2 + 0) * 2 + 1) * 128 + r];
                 const float l1 = sL[((par * 2 + 1) * 2 + 0) * 128 + r] + sL[((par * 2 + 1) * 2 + 1) * 128 + r];
