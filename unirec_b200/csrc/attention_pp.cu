@@ -144,129 +144,132 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    // 640 threads start with 96 registers each; the control warp group shrinks to 64, the softmax warp groups grow to 104 (16 x 8 = 4 x 32: the CTA pool balances exactly)
+    // 640 threads start with 96 registers each; the control warp group shrinks to 64 and the softmax warp groups grow to 104
+    // (16 warps x 8 = 4 warps x 32: the CTA's register pool balances exactly - an increase the pool cannot serve blocks forever).
+    // The role code sits INSIDE the two branches: ptxas only gives the softmax code its 104 registers that way.
     if (warp_idx >= 16) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-    if (warp_idx == 16) {
-        // ===================== TMA producer: Q and the K ring =====================
-        int it = 0, t = 0;
-        for (int g = 0; g < G; ++g, ++t) {
-            if (t == T) { t = 0; ++it; }
-            const int w = blockIdx.x + it * gridDim.x;
-            const int b = w / pairs, hp = w - b * pairs;
-            if (t == 0) {
-                if (it > 0) mbar_wait(q_free, (it - 1) & 1);
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        if (warp_idx == 16) {
+            // ===================== TMA producer: Q and the K ring =====================
+            int it = 0, t = 0;
+            for (int g = 0; g < G; ++g, ++t) {
+                if (t == T) { t = 0; ++it; }
+                const int w = blockIdx.x + it * gridDim.x;
+                const int b = w / pairs, hp = w - b * pairs;
+                if (t == 0) {
+                    if (it > 0) mbar_wait(q_free, (it - 1) & 1);
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(q_full, PP_SLAB);
+                        tma_load_2d(&tmap_q, q_full, sQ, hp * 128, b * p.q_batch_rows);
+                        tma_load_2d(&tmap_q, q_full, sQ + 64 * 128, hp * 128 + 64, b * p.q_batch_rows);
+                    }
+                    __syncwarp();
+                }
+                const int kslot = g & (PP_KSTAGES - 1);
+                const int row = b * p.kv_batch_rows + t * PP_KT;
+                mbar_wait(&k_empty[kslot], ((g >> 2) & 1) ^ 1);
                 if (lane == 0) {
-                    mbar_arrive_expect_tx(q_full, PP_SLAB);
-                    tma_load_2d(&tmap_q, q_full, sQ, hp * 128, b * p.q_batch_rows);
-                    tma_load_2d(&tmap_q, q_full, sQ + 64 * 128, hp * 128 + 64, b * p.q_batch_rows);
+                    mbar_arrive_expect_tx(&k_full[kslot], PP_TILE);
+                    tma_load_2d(&tmap_k, &k_full[kslot], sK + kslot * PP_TILE, hp * 128, row);
+                    tma_load_2d(&tmap_k, &k_full[kslot], sK + kslot * PP_TILE + PP_SLAB, hp * 128 + 64, row);
                 }
                 __syncwarp();
             }
-            const int kslot = g & (PP_KSTAGES - 1);
-            const int row = b * p.kv_batch_rows + t * PP_KT;
-            mbar_wait(&k_empty[kslot], ((g >> 2) & 1) ^ 1);
-            if (lane == 0) {
-                mbar_arrive_expect_tx(&k_full[kslot], PP_TILE);
-                tma_load_2d(&tmap_k, &k_full[kslot], sK + kslot * PP_TILE, hp * 128, row);
-                tma_load_2d(&tmap_k, &k_full[kslot], sK + kslot * PP_TILE + PP_SLAB, hp * 128 + 64, row);
-            }
-            __syncwarp();
-        }
-    } else if (warp_idx == 18) {
-        // ===================== TMA producer: the V ring (its own warp: a V slot only frees when PV(g-2) has completed,
-        // and a producer that waits for it in line would hold back the K tiles the issuer needs two tiles ahead) ==========
-        int it = 0, t = 0;
-        for (int g = 0; g < G; ++g, ++t) {
-            if (t == T) { t = 0; ++it; }
-            const int w = blockIdx.x + it * gridDim.x;
-            const int b = w / pairs, hp = w - b * pairs;
-            const int vslot = g & 1;
-            const int row = b * p.kv_batch_rows + t * PP_KT;
-            mbar_wait(&v_empty[vslot], ((g >> 1) & 1) ^ 1);
-            if (lane == 0) {
-                mbar_arrive_expect_tx(&v_full[vslot], PP_TILE);
-                tma_load_2d(&tmap_v, &v_full[vslot], sV + vslot * PP_TILE, hp * 128, row);
-                tma_load_2d(&tmap_v, &v_full[vslot], sV + vslot * PP_TILE + PP_SLAB, hp * 128 + 64, row);
-            }
-            __syncwarp();
-        }
-    } else if (warp_idx == 17) {
-        // ===================== UMMA issuer =====================
-        constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
-        constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128) | (1u << 16);      // B operand MN-major
-        // The S stream (S(g) needs Q, K(g) and the group's free accumulator) and the PV stream (PV(g) needs V(g) and P(g)) are
-        // each issued in order, but whichever is ready goes first: a PV must not queue behind the K tile of an S two tiles
-        // ahead (measured: with the fixed order S(g+2), PV(g) the kernel ran 40 % slower than attention_tc_kernel).
-        auto s_ready = [&](int g) {
-            const int it = g / T, t = g - it * T;
-            const uint32_t n = static_cast<uint32_t>(g >> 1);
-            if (t == 0 && !mbar_test_wait(q_full, it & 1)) return false;
-            return mbar_test_wait(&k_full[g & (PP_KSTAGES - 1)], (g >> 2) & 1) && mbar_test_wait(&s_free[g & 1], (n & 1) ^ 1);
-        };
-        auto pv_ready = [&](int g) {
-            const int it = g / T, t = g - it * T;
-            const uint32_t n = static_cast<uint32_t>(g >> 1);
-            if (t < 2 && it > 0 && !mbar_test_wait(o_free, (it - 1) & 1)) return false;
-            return mbar_test_wait(&p_ready[g & 1], n & 1) && mbar_test_wait(&v_full[g & 1], n & 1);
-        };
-        auto issue_s = [&](int g) {
-            const int it = g / T, t = g - it * T;
-            const int grp = g & 1;
-            const int kslot = g & (PP_KSTAGES - 1);
-            tc_fence_after();
-            if (lane == 0) {
-                const uint32_t a_addr = smem_u32(sQ);
-                const uint32_t b_addr = smem_u32(sK + kslot * PP_TILE);
-#pragma unroll
-                for (int hd = 0; hd < 2; ++hd)
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        pp_umma_lanes(tmem_base + grp * 128, umma_smem_desc_sw128(a_addr + ks * 32),
-                                      umma_smem_desc_sw128(b_addr + hd * PP_SLAB + ks * 32), idesc_s, ks != 0 ? 1u : 0u,
-                                      hd == 0);
-                umma_commit(&s_full[grp]);
-                if (t == T - 1) umma_commit(q_free);
-            }
-            __syncwarp();
-        };
-        auto issue_pv = [&](int g) {
-            const int it = g / T, t = g - it * T;
-            const int grp = g & 1;
-            const int kslot = g & (PP_KSTAGES - 1);
-            const bool first = t < 2;                       // this group's first tile of the item: O starts from zero
-            tc_fence_after();
-            if (lane == 0) {
-                const uint32_t a_addr = smem_u32(sK + kslot * PP_TILE);     // P(g), written over K(g)
-                const uint32_t b_addr = smem_u32(sV + grp * PP_TILE);
-                const uint32_t tmem_o = tmem_base + 256 + grp * 128;
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                    const uint32_t a_off = (ks >> 2) * PP_SLAB + (ks & 3) * 32;     // 16 keys = 32 B along K
-                    const uint32_t b_off = ks * 16 * 128;                            // 16 key rows of 128 B
-                    umma_bf16_ss(tmem_o, umma_smem_desc_sw128(a_addr + a_off), pp_desc_mn_sw128(b_addr + b_off, PP_SLAB),
-                                 idesc_pv, (!first || ks != 0) ? 1u : 0u);
+        } else if (warp_idx == 18) {
+            // ===================== TMA producer: the V ring (its own warp: a V slot only frees when PV(g-2) has completed,
+            // and a producer that waits for it in line would hold back the K tiles the issuer needs two tiles ahead) ==========
+            int it = 0, t = 0;
+            for (int g = 0; g < G; ++g, ++t) {
+                if (t == T) { t = 0; ++it; }
+                const int w = blockIdx.x + it * gridDim.x;
+                const int b = w / pairs, hp = w - b * pairs;
+                const int vslot = g & 1;
+                const int row = b * p.kv_batch_rows + t * PP_KT;
+                mbar_wait(&v_empty[vslot], ((g >> 1) & 1) ^ 1);
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&v_full[vslot], PP_TILE);
+                    tma_load_2d(&tmap_v, &v_full[vslot], sV + vslot * PP_TILE, hp * 128, row);
+                    tma_load_2d(&tmap_v, &v_full[vslot], sV + vslot * PP_TILE + PP_SLAB, hp * 128 + 64, row);
                 }
-                umma_commit(&v_empty[grp]);
-                umma_commit(&k_empty[kslot]);
-                umma_commit(&pv_done[grp]);
-                if (t == T - 1) umma_commit(item_done);
+                __syncwarp();
             }
-            __syncwarp();
-        };
-        int gs = 0, gp = 0;
-        while (gp < G) {
-            // lane 0's view of the barriers decides for the warp
-            if (gs < G && __shfl_sync(0xffffffffu, s_ready(gs) ? 1 : 0, 0) != 0) {
-                issue_s(gs);
-                ++gs;
-            }
-            if (gp < gs && __shfl_sync(0xffffffffu, pv_ready(gp) ? 1 : 0, 0) != 0) {
-                issue_pv(gp);
-                ++gp;
+        } else if (warp_idx == 17) {
+            // ===================== UMMA issuer =====================
+            constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
+            constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128) | (1u << 16);      // B operand MN-major
+            // The S stream (S(g) needs Q, K(g) and the group's free accumulator) and the PV stream (PV(g) needs V(g) and
+            // P(g)) are each issued in order, but whichever is ready goes first: a PV must not queue behind the K tile of
+            // an S two tiles ahead (measured: with the fixed order S(g+2), PV(g) the kernel ran 40 % slower than
+            // attention_tc_kernel).
+            auto s_ready = [&](int g) {
+                const int it = g / T, t = g - it * T;
+                const uint32_t n = static_cast<uint32_t>(g >> 1);
+                if (t == 0 && !mbar_test_wait(q_full, it & 1)) return false;
+                return mbar_test_wait(&k_full[g & (PP_KSTAGES - 1)], (g >> 2) & 1) && mbar_test_wait(&s_free[g & 1], (n & 1) ^ 1);
+            };
+            auto pv_ready = [&](int g) {
+                const int it = g / T, t = g - it * T;
+                const uint32_t n = static_cast<uint32_t>(g >> 1);
+                if (t < 2 && it > 0 && !mbar_test_wait(o_free, (it - 1) & 1)) return false;
+                return mbar_test_wait(&p_ready[g & 1], n & 1) && mbar_test_wait(&v_full[g & 1], n & 1);
+            };
+            auto issue_s = [&](int g) {
+                const int it = g / T, t = g - it * T;
+                const int grp = g & 1;
+                const int kslot = g & (PP_KSTAGES - 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_u32(sQ);
+                    const uint32_t b_addr = smem_u32(sK + kslot * PP_TILE);
+    #pragma unroll
+                    for (int hd = 0; hd < 2; ++hd)
+    #pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            pp_umma_lanes(tmem_base + grp * 128, umma_smem_desc_sw128(a_addr + ks * 32),
+                                          umma_smem_desc_sw128(b_addr + hd * PP_SLAB + ks * 32), idesc_s, ks != 0 ? 1u : 0u,
+                                          hd == 0);
+                    umma_commit(&s_full[grp]);
+                    if (t == T - 1) umma_commit(q_free);
+                }
+                __syncwarp();
+            };
+            auto issue_pv = [&](int g) {
+                const int it = g / T, t = g - it * T;
+                const int grp = g & 1;
+                const int kslot = g & (PP_KSTAGES - 1);
+                const bool first = t < 2;                       // this group's first tile of the item: O starts from zero
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_u32(sK + kslot * PP_TILE);     // P(g), written over K(g)
+                    const uint32_t b_addr = smem_u32(sV + grp * PP_TILE);
+                    const uint32_t tmem_o = tmem_base + 256 + grp * 128;
+    #pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint32_t a_off = (ks >> 2) * PP_SLAB + (ks & 3) * 32;     // 16 keys = 32 B along K
+                        const uint32_t b_off = ks * 16 * 128;                            // 16 key rows of 128 B
+                        umma_bf16_ss(tmem_o, umma_smem_desc_sw128(a_addr + a_off), pp_desc_mn_sw128(b_addr + b_off, PP_SLAB),
+                                     idesc_pv, (!first || ks != 0) ? 1u : 0u);
+                    }
+                    umma_commit(&v_empty[grp]);
+                    umma_commit(&k_empty[kslot]);
+                    umma_commit(&pv_done[grp]);
+                    if (t == T - 1) umma_commit(item_done);
+                }
+                __syncwarp();
+            };
+            int gs = 0, gp = 0;
+            while (gp < G) {
+                // lane 0's view of the barriers decides for the warp
+                if (gs < G && __shfl_sync(0xffffffffu, s_ready(gs) ? 1 : 0, 0) != 0) {
+                    issue_s(gs);
+                    ++gs;
+                }
+                if (gp < gs && __shfl_sync(0xffffffffu, pv_ready(gp) ? 1 : 0, 0) != 0) {
+                    issue_pv(gp);
+                    ++gp;
+                }
             }
         }
-    }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         // ===================== softmax groups: thread = (accumulator row r, key half hf) of the group's tiles =============
