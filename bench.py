@@ -62,6 +62,7 @@ def parse_args():
     ap.add_argument("--cpu-users", type=int, default=32, help="users in the bounded CPU-baseline sample (timed); the "
                     "top-k parity check against the GPU result uses the first 8 of them")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernels-alone", action="store_true", help="skip the per-kernel burst timings (kernels_alone)")
     ap.add_argument("--train-batch", type=int, default=1024, help="GLOBAL batch of the cfg-2 training block (0 = skip)")
     ap.add_argument("--train-steps", type=int, default=4)
     ap.add_argument("--train-dropout", type=float, default=0.2, help="dropout of the cfg-2 training block "
@@ -72,6 +73,68 @@ def parse_args():
     ap.add_argument("--profile-range", default="", choices=["", "items", "users", "train"],
                     help="bracket that timed region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     return ap.parse_args()
+
+
+def kernels_alone(dev, pk, pooled, k):
+    """The HBM-bound kernels of the path timed ALONE (short bursts after an idle pause, CUDA events per launch, median of 9):
+    the north star's per-kernel targets (attention and scoring >= 70 % of the HBM peak) next to the in-step figures of
+    `roofline.other_kernels`, which are taken under the power cap of the 160 ms step (SM clock ~1.4 GHz instead of 1.9).
+    Bytes are the algorithmic ones of SURVEY.md 8(d)."""
+    import time
+    from unirec_b200 import ops
+    H, heads = 1024, 16
+    bf = torch.bfloat16
+    g = torch.Generator(device=dev).manual_seed(77)
+    rnd = lambda *shape: (torch.randn(*shape, device=dev, generator=g) * 0.5).to(bf)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        time.sleep(0.3)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(9)]
+        for a, b in ev:
+            a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        return sorted(a.elapsed_time(b) for a, b in ev)[4]
+
+    out = {}
+
+    def hbm(name, ms, nbytes):
+        gbs = nbytes / ms / 1e6
+        out[name] = {"ms": ms, "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "bound": "hbm"}
+
+    Bu, Q, S = 512, 64, 1600                                  # user cross-attention of one K/V chunk, one layer
+    qc, kv, mask = rnd(Bu * Q, H), rnd(Bu * S, 2 * H), torch.ones(Bu, S, device=dev)
+    hbm("attention_user_cross_512x64x1600",
+        timed(lambda: ops.attention(qc, kv[:, :H], kv[:, H:], batch=Bu, num_heads=heads, nq=Q, nk=S, key_mask=mask)),
+        (2 * Q + 2 * S) * Bu * H * 2)
+    del kv
+    qkv = rnd(2048 * 64, 3 * H)
+    hbm("attention_user_self_2048x64x64",
+        timed(lambda: ops.attention(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], batch=2048, num_heads=heads, nq=64, nk=64)),
+        4 * 2048 * 64 * H * 2)
+    del qkv
+    Bi = 8192
+    qkv = rnd(Bi * 32, 3 * H)
+    hbm("attention_item_self_8192x32x32",
+        timed(lambda: ops.attention(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], batch=Bi, num_heads=heads, nq=32, nk=32)),
+        4 * Bi * 32 * H * 2)
+    qi, kvi, mi = qkv[:, :H], rnd(Bi * 14, 2 * H), torch.ones(Bi, 14, device=dev)
+    hbm("attention_item_cross_8192x32x14",
+        timed(lambda: ops.attention(qi, kvi[:, :H], kvi[:, H:], batch=Bi, num_heads=heads, nq=32, nk=14, key_mask=mi)),
+        (2 * 32 + 2 * 14) * Bi * H * 2)
+    del qkv, kvi
+    N = pooled.shape[0]
+    cinv = ops.inv_l2_norm(pooled)
+    u128 = rnd(128, H)
+    hbm(f"score_topk_128_users_x_{N}", timed(lambda: ops.score_topk(u128, pooled, k, cand_inv=cinv)), N * H * 2)
+    u4k = rnd(4096, H)
+    ms = timed(lambda: ops.score_topk(u4k, pooled, k, cand_inv=cinv))
+    tf = 2.0 * 4096 * N * H / ms / 1e9
+    out[f"score_topk_4096_users_x_{N}"] = {"ms": ms, "achieved": tf, "peak": pk["bf16_burst"], "unit": "TFLOP/s",
+                                             "frac": tf / pk["bf16_burst"], "bound": "tensor (burst peak: kernel timed alone)"}
+    return out
 
 
 def config_dict(args, n_gpus):
@@ -779,6 +842,14 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         eager = torch_eager_gpu_sample(item, user, fpool, tokens, pooled, hist_batches[0], lengths, k, dev)
 
+    # ------------------------------------------------------------------ HBM-bound kernels timed alone (N == 1)
+    alone = None
+    if world == 1 and not args.no_kernels_alone:
+        try:
+            alone = kernels_alone(dev, pk, pooled, k)
+        except Exception as e:                      # diagnostics only: never fail the bench line
+            alone = {"error": repr(e)}
+
     # ------------------------------------------------------------------ cfg 2: training step
     train_block = None
     if args.train_batch > 0 and args.train_batch % world == 0:
@@ -921,6 +992,7 @@ def run_ours(args, rank, world, local_rank):
         "cpu_baseline": cpu_baseline,
         "parity_vs_gpu": (cpu_baseline or {}).get("parity_vs_gpu") if world == 1 else multi_parity,
         "torch_eager_same_gpu": eager,
+        "kernels_alone": alone,
         "items": {
             "metric": "items/sec (item Q-Former: 14 x 1024 field embeddings -> 32 x 1024 query tokens + pooled row)",
             "value": items_per_sec, "unit": "items/s", "items_timed": items_timed, "ms_total": item_ms,
