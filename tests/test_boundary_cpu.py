@@ -136,6 +136,12 @@ def test_torch_custom_ops_are_registered_with_fake_impls_and_no_cpu_kernel():
     assert tuple(y.shape) == (64, 4096) and y.dtype == torch.bfloat16
     y = ns.linear(m(2, 32, 1024), m(1024, 1024), None, m(2, 32, 1024), 2, True)
     assert tuple(y.shape) == (2, 32, 1024) and y.dtype == f32
+    y, st = ns.linear_ln(m(64, 4096), m(1024, 4096), m(1024, dt=f32), m(64, 1024), 2, None, None, m(64, 8, 2, dt=f32),
+                         m(1024, dt=f32), m(1024, dt=f32), True, 1e-12, 1024)
+    assert tuple(y.shape) == (64, 1024) and y.dtype == torch.bfloat16 and tuple(st.shape) == (64, 8, 2) and st.dtype == f32
+    y, st = ns.linear_ln(m(64, 1024), m(4096, 1024), m(4096, dt=f32), None, 1, m(64, 8, 2, dt=f32), m(4096, dt=f32), None,
+                         None, None, False, 1e-12, 1024)
+    assert tuple(y.shape) == (64, 4096) and st.numel() == 0
     assert tuple(ns.layernorm(m(32, 1024, dt=f32), m(1024, dt=f32), m(1024, dt=f32), 1e-12, None, 256, 32, False).shape) == (256, 1024)
     assert tuple(ns.attention(m(64, 1024), m(28, 1024), m(28, 1024), m(2, 14, dt=f32), 2, 16, 32, 14, False).shape) == (64, 1024)
     assert ns.cast_bf16(m(3, 5, dt=f32)).dtype == torch.bfloat16

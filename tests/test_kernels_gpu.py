@@ -400,6 +400,17 @@ def test_torch_ops_match_direct_wrappers():
     assert torch.equal(ns.linear(x, w, b, None, 1, False), ops.linear(x, w, b, epilogue=ops.EPI_BIAS_GELU))
     gam, bet = torch.rand(1024, generator=g).to(_dev()), torch.randn(1024, generator=g).to(_dev())
     assert torch.equal(ns.layernorm(x, gam, bet, 1e-12, None, 0, 0, False), ops.layernorm(x, gam, bet, 1e-12))
+    # LayerNorm folding: producer (statistics out) and consumer (statistics in) through the dispatcher = the direct wrappers
+    res = torch.randn(300, 512, generator=g).to(torch.bfloat16).to(_dev())
+    st = ops.ln_stats_buffer(300, 512, _dev())
+    pre = ops.linear_ln(x, w, b, epilogue=ops.EPI_BIAS_RESIDUAL, residual=res, stats_out=st, hidden=512)
+    pre_t, st_t = ns.linear_ln(x, w, b, res, 2, None, None, None, None, None, True, 1e-12, 512)
+    assert torch.equal(pre, pre_t) and torch.equal(st, st_t)
+    w1 = (torch.randn(256, 512, generator=g) * 0.03).to(_dev())
+    wf, bf_, cf = ops.fold_layernorm_weights(w1, None, gam[:512], bet[:512])
+    y_t, none_t = ns.linear_ln(pre, wf, bf_, None, 1, st, cf, None, None, None, False, 1e-12, 512)
+    assert torch.equal(y_t, ops.linear_ln(pre, wf, bf_, epilogue=ops.EPI_BIAS_GELU, ln_in=(st, cf), hidden=512))
+    assert none_t.numel() == 0
     B, heads, nq, nk = 3, 16, 32, 14
     q = torch.randn(B * nq, 1024, generator=g).to(torch.bfloat16).to(_dev())
     k = torch.randn(B * nk, 1024, generator=g).to(torch.bfloat16).to(_dev())

@@ -44,6 +44,32 @@ def _(a, weight, bias, residual, epilogue, out_fp32):
     return a.new_empty(*a.shape[:-1], weight.shape[0], dtype=_dt(out_fp32))
 
 
+@torch.library.custom_op(f"{NAMESPACE}::linear_ln", mutates_args=(), device_types="cuda")
+def linear_ln(a: Tensor, weight: Tensor, bias: Tensor, residual: Optional[Tensor], epilogue: int,
+              ln_in_stats: Optional[Tensor], ln_in_c: Optional[Tensor], ln_res_stats: Optional[Tensor],
+              ln_res_gamma: Optional[Tensor], ln_res_beta: Optional[Tensor], want_stats: bool, eps: float,
+              hidden: int) -> Tuple[Tensor, Tensor]:
+    """nn.Linear with the LayerNorms around it folded in (unirec_linear_ln_bf16): returns (out bf16, stats fp32
+    [M, parts, 2] of out's rows - empty unless want_stats).  ln_in_* : `a` is a LayerNorm input, weight / bias are folded
+    (ops.fold_layernorm_weights); ln_res_*: `residual` is a LayerNorm input and enters normalised.  Inference only."""
+    M = a.numel() // a.shape[-1]
+    stats = ops.ln_stats_buffer(M, weight.shape[0], a.device) if want_stats else a.new_empty(0, dtype=_F32)
+    out = ops.linear_ln(a, weight, bias, epilogue=epilogue, residual=residual,
+                        ln_in=None if ln_in_stats is None else (ln_in_stats, ln_in_c),
+                        ln_res=None if ln_res_stats is None else (ln_res_stats, ln_res_gamma, ln_res_beta),
+                        stats_out=stats if want_stats else None, eps=eps, hidden=hidden)
+    return out, stats
+
+
+@linear_ln.register_fake
+def _(a, weight, bias, residual, epilogue, ln_in_stats, ln_in_c, ln_res_stats, ln_res_gamma, ln_res_beta, want_stats, eps,
+      hidden):
+    N = weight.shape[0]
+    M = a.numel() // a.shape[-1]
+    stats = a.new_empty((M, 2 * (N // 256), 2) if want_stats else (0,), dtype=_F32)
+    return a.new_empty(*a.shape[:-1], N, dtype=_BF16), stats
+
+
 @torch.library.custom_op(f"{NAMESPACE}::layernorm", mutates_args=(), device_types="cuda")
 def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, residual: Optional[Tensor], rows: int,
               in_row_mod: int, out_fp32: bool) -> Tensor:
@@ -264,5 +290,5 @@ def _(sims, temperature):
     return sims.new_empty(sims.shape[0]), sims.new_empty(sims.shape[0], dtype=torch.int32)
 
 
-OPS = ("linear", "layernorm", "attention", "cast_bf16", "mean_tokens", "field_projection", "build_user_sequence",
+OPS = ("linear", "linear_ln", "layernorm", "attention", "cast_bf16", "mean_tokens", "field_projection", "build_user_sequence",
        "inv_l2_norm", "score_topk", "topk_merge", "list_scores", "infonce_rank")
