@@ -81,6 +81,7 @@ def kernels_alone(dev, pk, pooled, k):
     `roofline.other_kernels`, which are taken under the power cap of the 160 ms step (SM clock ~1.4 GHz instead of 1.9).
     Bytes are the algorithmic ones of SURVEY.md 8(d)."""
     import time
+    import torch
     from unirec_b200 import ops
     H, heads = 1024, 16
     bf = torch.bfloat16
@@ -156,7 +157,7 @@ def config_dict(args, n_gpus):
                        + ("all-to-all of the per-rank top-k lists (int32 index + shard base), every rank merges its own users"
                           if args.exchange == "alltoall" else "all-gather + merge of top-k on every rank"),
         "l2": "inputs larger than L2 every step (user sequences 13.4 GB, candidate pool 2 GB / n_gpus, "
-              "item field batches cycled over a 0.9 GB pool)",
+              "item field batches generated on device per chunk: 1 M distinct items)",
     }
 
 
@@ -673,7 +674,13 @@ def run_ours(args, rank, world, local_rank):
 
     def encode_chunk(ci):
         c0, c1 = chunks[ci]
-        tok = item.encode_query_tokens(fpool[ci % pool_chunks, :c1 - c0], fmask[:c1 - c0], out_dtype=torch.bfloat16)
+        # every chunk gets its own field embeddings (SURVEY.md 8d cfg 3: generated on device per chunk): one in-place
+        # normal_ over a rotating 235 MB buffer inside the timed loop (~0.3 % of a chunk's time).  Cycling over four fixed
+        # batches instead made every item occur ~61 times in the 1 M pool - 61-fold ties at every rank of every top-100
+        fbuf = fpool[ci % pool_chunks]
+        fbuf.normal_(generator=gen)
+        fbuf[:, 7, 768:] = 0                     # CLIP ViT-L/14 768-d field zero-padded to 1024
+        tok = item.encode_query_tokens(fbuf[:c1 - c0], fmask[:c1 - c0], out_dtype=torch.bfloat16)
         tok_local[c0:c1].copy_(tok)
         pooled[c0:c1].copy_(ops.mean_tokens(tok))
 
