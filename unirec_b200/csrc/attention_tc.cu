@@ -47,7 +47,8 @@ constexpr int AT_SMEM_BYTES = 2 * AT_TILE /*Q2 x2*/ + AT_KSTAGES * AT_TILE /*K|P
 static_assert(AT_SMEM_BYTES <= 232448, "shared memory budget exceeded");
 constexpr float AT_MASKED = -1.2676506002282294e30f;   // -2^100: stands in for finfo.min, exact in bf16 (row-max exchange)
 constexpr float AT_LAZY = 8.0f;                  // raise the running max only when exceeded by 2^8
-constexpr bool AT_PTMEM_DEFAULT = true;         // P through tensor memory (see attention_tc_kernel<PTMEM>)
+constexpr bool AT_PTMEM_DEFAULT = true;
+constexpr bool AT_QTMA_DEFAULT = true;           // stacked queries by TMA + three V stages (attention_tc_kernel<.., QTMA>)
 
 struct AttnTcParams {
     const __nv_bfloat16* q; long long ldq; long long q_batch_rows;
@@ -86,6 +87,21 @@ UNIREC_DEVICE void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_
         : "memory");
 }
 
+// cta_group::1 MMA that leaves the TMEM lanes 64..127 (skip_upper) or 0..63 untouched (disable-output-lane mask; checked on
+// the hardware by tools/probe_mixed_cta_group.cu, used by kv_attention_fused.cu and attention_pp.cu)
+UNIREC_DEVICE void umma_bf16_ss_lanes64(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
+                                        bool skip_upper) {
+    const uint32_t lo = skip_upper ? 0u : 0xffffffffu, hi = skip_upper ? 0xffffffffu : 0u;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+        "}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(lo), "r"(lo), "r"(hi), "r"(hi)
+        : "memory");
+}
+
 UNIREC_DEVICE void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -93,31 +109,37 @@ UNIREC_DEVICE void named_bar_sync(int id, int nthreads) {
 // PTMEM = true: P(g) is written to tensor memory (columns 384..511: two 64-column buffers of packed bf16 pairs) and PV(g)
 // takes it from there as its A operand; the K slot is released as soon as S(g) has been accumulated.  PTMEM = false: P(g) is
 // written in place over K(g) in shared memory (the round-1 kernel).
-template <bool PTMEM>
+// QTMA = true: the queries of a work item are the two heads' 64 x 64 blocks STACKED into one 128 x 64 slab (16 KB, loaded by
+// the TMA producer as two boxes) and S(g) is two MMAs of contraction 64 that each write only their head's 64 TMEM lanes
+// (disable-output-lane mask) - no block-diagonal zero padding, no Q2 code in the softmax warps, and the 32 KB saved buy a
+// third V stage.  QTMA = false: the softmax warps build the block-diagonal 128 x 128 Q2 (the round-1 kernel).
+template <bool PTMEM, bool QTMA>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
-                    const AttnTcParams p) {
+                    const __grid_constant__ CUtensorMap tmap_q, const AttnTcParams p) {
+    constexpr int QBUF = QTMA ? AT_SLAB : AT_TILE;       // bytes per query buffer
+    constexpr int VST = QTMA ? 3 : 2;                    // V ring depth
     extern __shared__ uint8_t smem_raw[];
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ2 = smem;                          // [2][2 slabs]
-    uint8_t* sK = smem + 2 * AT_TILE;             // [3][2 slabs]  K(g), later P(g)
-    uint8_t* sV = smem + 5 * AT_TILE;             // [2][2 slabs]
+    uint8_t* sK = smem + 2 * QBUF;                // [3][2 slabs]  K(g), later P(g) unless PTMEM
+    uint8_t* sV = sK + AT_KSTAGES * AT_TILE;      // [VST][2 slabs]   (2 QBUF + 3 + VST tiles = 7 tiles either way)
     // smem + 7 tiles: [2][2][128] bf16 row-max exchange between the two softmax warps of a row quadrant (1 KB)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * AT_TILE + 2 * 2 * AT_KT * 2);
     uint64_t* k_full = bars;            // [3]
     uint64_t* k_empty = bars + 3;       // [3]  issuer (commit after PV: the slot held K, then P)
-    uint64_t* v_full = bars + 6;        // [2]
-    uint64_t* v_empty = bars + 8;       // [2]
-    uint64_t* q_ready = bars + 10;      // [2]  softmax warps -> issuer
-    uint64_t* q_free = bars + 12;       // [2]  issuer (commit) -> softmax warps
-    uint64_t* s_full = bars + 14;       // [2]  issuer (commit) -> softmax warps
-    uint64_t* s_free = bars + 16;       // [2]  softmax warps -> issuer
-    uint64_t* p_ready = bars + 18;      // softmax warps -> issuer
-    uint64_t* pv_done = bars + 19;      // issuer (commit) -> softmax warps
-    uint64_t* o_free = bars + 20;       // softmax warps -> issuer (O of the finished item has been read)
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 21);
+    uint64_t* v_full = bars + 6;        // [3]
+    uint64_t* v_empty = bars + 9;       // [3]
+    uint64_t* q_ready = bars + 12;      // [2]  softmax warps (or the TMA producer, QTMA) -> issuer
+    uint64_t* q_free = bars + 14;       // [2]  issuer (commit) -> softmax warps (or the TMA producer)
+    uint64_t* s_full = bars + 16;       // [2]  issuer (commit) -> softmax warps
+    uint64_t* s_free = bars + 18;       // [2]  softmax warps -> issuer
+    uint64_t* p_ready = bars + 20;      // softmax warps -> issuer
+    uint64_t* pv_done = bars + 21;      // issuer (commit) -> softmax warps
+    uint64_t* o_free = bars + 22;       // softmax warps -> issuer (O of the finished item has been read)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 23);
 
     const int T = (p.nk + AT_KT - 1) / AT_KT;
     const int my_items = (p.num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
@@ -128,10 +150,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
     if (warp_idx == 8 && lane == 0) {
         tma_prefetch_desc(&tmap_k);
         tma_prefetch_desc(&tmap_v);
+        if constexpr (QTMA) tma_prefetch_desc(&tmap_q);
         for (int i = 0; i < AT_KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+        for (int i = 0; i < 3; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
-            mbar_init(&q_ready[i], 8); mbar_init(&q_free[i], 1);
+            mbar_init(&q_ready[i], QTMA ? 1 : 8); mbar_init(&q_free[i], 1);
             mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 8);
         }
         mbar_init(p_ready, 8);
@@ -155,12 +178,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
             const int it = g / T, t = g - it * T;
             const int w = blockIdx.x + it * gridDim.x;
             const int b = w / pairs, hp = w - b * pairs;
-            const int slot = g & 1;
-            const uint32_t ph = (g >> 1) & 1;
+            const int slot = g % VST;
+            const uint32_t ph = (g / VST) & 1;
             const int kslot = g % AT_KSTAGES;
             const uint32_t kph = (g / AT_KSTAGES) & 1;
             const int row = b * p.kv_batch_rows + t * AT_KT;
             const int col = hp * 128;
+            if constexpr (QTMA) {
+                if (t == 0) {
+                    // stacked queries of the item: rows 0-63 = head 2 hp, rows 64-127 = head 2 hp + 1 (rows beyond nq belong to
+                    // the next batch element or are zero-filled: they land in accumulator rows that are never stored)
+                    mbar_wait(&q_free[it & 1], ((it >> 1) & 1) ^ 1);
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&q_ready[it & 1], AT_SLAB);
+                        tma_load_2d(&tmap_q, &q_ready[it & 1], sQ2 + (it & 1) * AT_SLAB, col, b * static_cast<int>(p.q_batch_rows));
+                        tma_load_2d(&tmap_q, &q_ready[it & 1], sQ2 + (it & 1) * AT_SLAB + 64 * 128, col + 64, b * static_cast<int>(p.q_batch_rows));
+                    }
+                    __syncwarp();
+                }
+            }
             mbar_wait(&k_empty[kslot], kph ^ 1);
             if (lane == 0) {
                 mbar_arrive_expect_tx(&k_full[kslot], AT_TILE);
@@ -190,13 +226,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
             mbar_wait(&s_free[slot], ph ^ 1);
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t a_addr = smem_u32(sQ2 + (it & 1) * AT_TILE);
+                const uint32_t a_addr = smem_u32(sQ2 + (it & 1) * QBUF);
                 const uint32_t b_addr = smem_u32(sK + kslot * AT_TILE);
+                if constexpr (QTMA) {
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                    const uint32_t off = (ks >> 2) * AT_SLAB + (ks & 3) * 32;
-                    umma_bf16_ss(tmem_base + slot * 128, umma_smem_desc_sw128(a_addr + off),
-                                 umma_smem_desc_sw128(b_addr + off), idesc_s, ks != 0 ? 1u : 0u);
+                    for (int hd = 0; hd < 2; ++hd)
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma_bf16_ss_lanes64(tmem_base + slot * 128, umma_smem_desc_sw128(a_addr + ks * 32),
+                                                 umma_smem_desc_sw128(b_addr + hd * AT_SLAB + ks * 32), idesc_s,
+                                                 ks != 0 ? 1u : 0u, hd == 0);
+                } else {
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint32_t off = (ks >> 2) * AT_SLAB + (ks & 3) * 32;
+                        umma_bf16_ss(tmem_base + slot * 128, umma_smem_desc_sw128(a_addr + off),
+                                     umma_smem_desc_sw128(b_addr + off), idesc_s, ks != 0 ? 1u : 0u);
+                    }
                 }
                 umma_commit(&s_full[slot]);
                 if constexpr (PTMEM) umma_commit(&k_empty[kslot]);      // K(g) is dead once S(g) has been accumulated
@@ -207,14 +253,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
         auto issue_pv = [&](int g) {
             const int it = g / T, t = g - it * T;
             const int slot = g & 1;
-            const uint32_t ph = (g >> 1) & 1;
-            mbar_wait(&v_full[slot], ph);
+            const int vslot = g % VST;
+            mbar_wait(&v_full[vslot], (g / VST) & 1);
             mbar_wait(p_ready, g & 1);
             if (t == 0 && it > 0) mbar_wait(o_free, (it - 1) & 1);
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t a_addr = smem_u32(sK + (g % AT_KSTAGES) * AT_TILE);   // P(g), written over K(g)
-                const uint32_t b_addr = smem_u32(sV + slot * AT_TILE);
+                const uint32_t b_addr = smem_u32(sV + vslot * AT_TILE);
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
                     const uint32_t a_off = (ks >> 2) * AT_SLAB + (ks & 3) * 32;     // 16 keys = 32 B along K
@@ -226,7 +272,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
                         umma_bf16_ss(tmem_o, umma_smem_desc_sw128(a_addr + a_off),
                                      umma_smem_desc_mn_sw128(b_addr + b_off, AT_SLAB), idesc_pv, (t | ks) != 0 ? 1u : 0u);
                 }
-                umma_commit(&v_empty[slot]);
+                umma_commit(&v_empty[vslot]);
                 if constexpr (!PTMEM) umma_commit(&k_empty[g % AT_KSTAGES]);
                 umma_commit(pv_done);
             }
@@ -274,9 +320,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
         };
 
         uint4 qv[8];
-        if (my_items > 0) {
-            load_q(0, qv);
-            store_q(0, qv);
+        if constexpr (!QTMA) {
+            if (my_items > 0) {
+                load_q(0, qv);
+                store_q(0, qv);
+            }
         }
         float m_used = -INFINITY, l_part = 0.f;
         // key_mask values of keys (64*hf + lane) and (+32) of tile (it_, t_), fetched one tile AHEAD (ncu: issued at the
@@ -302,7 +350,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
                 hp = w - b * pairs;
                 m_used = -INFINITY;
                 l_part = 0.f;
-                if (it + 1 < my_items) load_q(it + 1, qv);    // in flight during this tile's softmax
+                if constexpr (!QTMA) {
+                    if (it + 1 < my_items) load_q(it + 1, qv);    // in flight during this tile's softmax
+                }
             }
             const int slot = g & 1;
             const uint32_t ph = (g >> 1) & 1;
@@ -427,10 +477,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(p_ready);
 
-            if (t == 0 && it + 1 < my_items) {
-                // Q2 of the next item (its buffer was last read by item it-1, long finished)
-                if (it >= 1) mbar_wait(&q_free[(it + 1) & 1], ((it - 1) >> 1) & 1);
-                store_q(it + 1, qv);
+            if constexpr (!QTMA) {
+                if (t == 0 && it + 1 < my_items) {
+                    // Q2 of the next item (its buffer was last read by item it-1, long finished)
+                    if (it >= 1) mbar_wait(&q_free[(it + 1) & 1], ((it - 1) >> 1) & 1);
+                    store_q(it + 1, qv);
+                }
             }
             if (t == T - 1) {
                 // ---- finalize: row sum over both halves, then O / l -> bf16 -> global (32 of the row's 64 columns)
@@ -499,12 +551,23 @@ int attention_tc(const void* q, long long ldq, long long q_batch_rows, const voi
     if (rc != UNIREC_OK) return rc;
     rc = make_tmap_bf16_2d(&tv, v, batch * kv_batch_rows, num_heads * 64, ldv, AT_KT);
     if (rc != UNIREC_OK) return rc;
-    // UNIREC_ATTENTION_PTMEM = 1 / 0: P as a tensor-memory operand of the second MMA / P in shared memory over the K tile
+    // UNIREC_ATTENTION_PTMEM = 1 / 0: P as a tensor-memory operand of the second MMA / P in shared memory over the K tile;
+    // UNIREC_ATTENTION_QTMA = 1 / 0: stacked queries loaded by TMA + lane-masked S MMAs + three V stages / Q2 built by the
+    // softmax warps
     static const bool ptmem = [] {
         const char* e = getenv("UNIREC_ATTENTION_PTMEM");
         return e != nullptr ? e[0] != '0' : AT_PTMEM_DEFAULT;
     }();
-    auto kern = ptmem ? attention_tc_kernel<true> : attention_tc_kernel<false>;
+    static const bool qtma = [] {
+        const char* e = getenv("UNIREC_ATTENTION_QTMA");
+        return e != nullptr ? e[0] != '0' : AT_QTMA_DEFAULT;
+    }();
+    CUtensorMap tq;
+    const long long q_rows = q_batch_rows > 0 ? (batch - 1) * q_batch_rows + nq : nq;
+    rc = make_tmap_bf16_2d(&tq, q, q_rows, num_heads * 64, ldq, 64);
+    if (rc != UNIREC_OK) return rc;
+    auto kern = ptmem ? (qtma ? attention_tc_kernel<true, true> : attention_tc_kernel<true, false>)
+                      : (qtma ? attention_tc_kernel<false, true> : attention_tc_kernel<false, false>);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
@@ -516,7 +579,7 @@ int attention_tc(const void* q, long long ldq, long long q_batch_rows, const voi
     }
     int grid = num_sms() > 0 ? num_sms() : 148;
     if (grid > p.num_items) grid = p.num_items;
-    kern<<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tk, tv, p);
+    kern<<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tk, tv, tq, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_last_error("attention (tcgen05) launch: %s", cudaGetErrorString(e));
