@@ -20,14 +20,17 @@
 //     warps 0-7  softmax: two warps per TMEM lane quadrant, each thread owns one row x half of the tile's keys
 //                (row maxima / sums exchanged through shared memory between the two).
 //                tcgen05.ld S -> scale + additive mask -> row max -> ex2 -> row sum,
-//                P (bf16) -> shared memory (K-major, swizzled) for the second MMA.  The running max is only
-//                raised when a tile exceeds it by more than 2^8 (exact: O and the row sum are accumulated against the
-//                same reference value), so O in TMEM is almost never rescaled.  Also builds Q2 for the NEXT item.
-//     warp 8     TMA producer: K tiles through a 3-stage ring, V tiles through a 2-stage ring.  P(g) is written IN PLACE
-//                over K(g) (same 32 KB footprint; K(g) is dead once S(g) has been accumulated), so the K slot is only
-//                released by PV(g) - P is effectively triple-buffered and the softmax of tile g+1 never waits for PV(g)
+//                P (bf16) -> tensor memory (tcgen05.st; PTMEM, default) or shared memory (K-major, swizzled, in place over
+//                the K tile) for the second MMA.  The running max is only raised when a tile exceeds it by more than 2^8
+//                (exact: O and the row sum are accumulated against the same reference value), so O in TMEM is almost
+//                never rescaled.  Without QTMA they also build the block-diagonal Q2 of the NEXT item.
+//     warp 8     TMA producer: K tiles through a 3-stage ring, V tiles through a 3-stage (QTMA) / 2-stage ring, and with
+//                QTMA (default) the item's stacked queries [Q_h ; Q_h+1] (two 64 x 64 boxes -> one 128 x 64 slab)
 //     warp 9     TMEM allocator + UMMA issuer; issue order S(g+1), PV(g) so that the softmax of tile g overlaps
-//                the first MMA of tile g+1 (two S accumulators in TMEM) - across work items too
+//                the first MMA of tile g+1 (two S accumulators in TMEM) - across work items too.  With QTMA S(g) is two
+//                MMAs of contraction 64, each writing only its head's 64 TMEM lanes; with PTMEM PV(g) takes P from TMEM
+// Round-2 history of this kernel (512 users x 1600 keys, no mask, alone): 0.635 ms -> 0.608 (P in TMEM + packed f32x2
+// softmax arithmetic) -> 0.581 ms (stacked queries by TMA, third V stage) = 93 % of the measured HBM peak; DESIGN.md 3.2.
 // Mask semantics are those of attention.cu: key_mask == 0 adds -1e30 (log2 domain), keys beyond nk are excluded
 // (-inf), a row whose keys are all masked comes out uniform over the nk keys.
 #include "common.cuh"
