@@ -851,7 +851,13 @@ static ScorePlan make_plan(long long B, long long N) {
     }
     // sampled start threshold: every tile_stride-th candidate tile, 1/32 of the pool but at least 16 tiles (4096 candidates:
     // ~k * N / 4096 scores per user pass the filter) and at most 128 (what row_kth_kernel holds in registers)
+    // Pools of a few 100 k rows (the per-rank shards of the 4- and 8-GPU runs) get a denser sample, 1/8 of the pool up to 64
+    // tiles: the survivors of a user (~k * N / N_sample) are the same ~3000 whatever the pool size, so on a small pool they
+    // are several per 256-candidate tile and the append path of the filter epilogue, not the MMAs, sets the pace
+    // (profiles/r02_z_launches_score_topk.csv: 943 TFLOP/s at 4096 x 125 k against 1415 TFLOP/s at 4096 x 1 M)
     int nd = pl.n_tiles / 32;
+    const int nd_small = pl.n_tiles / 8 < 64 ? pl.n_tiles / 8 : 64;
+    nd = nd > nd_small ? nd : nd_small;
     nd = nd < 16 ? 16 : (nd > SC_DENSE_MAX_N / SC_BLOCK_N ? SC_DENSE_MAX_N / SC_BLOCK_N : nd);
     pl.n_dense_tiles = nd;
     pl.tile_stride = pl.n_tiles / nd;
